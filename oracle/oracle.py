@@ -1,0 +1,344 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle ("port") of the DynaMask per-instance mask path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this module; the product package ``dynamask_b200`` never does.
+
+Every function restates one reference function (paths relative to ``/root/reference``) on host
+memory with numpy/torch-CPU; the kernel arithmetic lives in ``dm_oracle.c`` (plain C, FMA
+contraction off).  Parity pinning: the reference's own tests hold no numeric vectors for this
+path, so the oracle is pinned against (a) golden vectors produced by the
+unmodified reference Python run in the build container through ``oracle/ref_shim.py``
+(``tests/golden/*.npz``, generator ``oracle/gen_golden.py``) and (b) torchvision's CPU
+``roi_align`` -- the stand-in for the absent third-party mmcv==1.0.5 kernel.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, 'libdm_oracle.so')
+    src = os.path.join(_HERE, 'dm_oracle.c')
+    if force or not os.path.exists(so) or (
+            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        subprocess.check_call(['make', '-C', _HERE, '-s'])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _np32(x):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _p(a, t=_f32p):
+    return a.ctypes.data_as(t)
+
+
+# --------------------------------------------------------------------------------------------
+# A0  bbox2roi -- mmdet/core/bbox/transforms.py:54-73
+# --------------------------------------------------------------------------------------------
+def bbox2roi(bbox_list):
+    """[k_i,4+] xyxy per image -> [K,5] (image index as float, x1, y1, x2, y2)."""
+    rows = []
+    for img_id, b in enumerate(bbox_list):
+        b = _np32(b).reshape(-1, b.shape[-1] if len(b.shape) > 1 else 4)
+        col = np.full((b.shape[0], 1), img_id, dtype=np.float32)
+        rows.append(np.concatenate([col, b[:, :4]], axis=1))
+    if not rows:
+        return np.zeros((0, 5), np.float32)
+    return np.concatenate(rows, axis=0).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# A1  resolution bucket -- mmdet/models/roi_heads/dynamask_roi_head.py:84-114 (+ :197-203)
+# --------------------------------------------------------------------------------------------
+def gumbel_softmax_hard(logits, uniform, temperature=0.5, eps=1e-20):
+    """Forward value of the hard (straight-through) Gumbel softmax given the uniform noise."""
+    logits = torch.as_tensor(logits, dtype=torch.float32)
+    u = torch.as_tensor(uniform, dtype=torch.float32)
+    g = -torch.log(-torch.log(u + eps) + eps)
+    y = F.softmax((logits + g) / temperature, dim=-1)
+    ind = y.max(dim=-1)[1]
+    hard = torch.zeros_like(y).view(-1, y.shape[-1])
+    hard.scatter_(1, ind.view(-1, 1), 1)
+    return hard.view_as(y), ind
+
+
+def bucket_of(onehot):
+    """bucket index = argmax of the one-hot mask label (first maximal index)."""
+    return torch.as_tensor(onehot).argmax(dim=1).to(torch.int64)
+
+
+# --------------------------------------------------------------------------------------------
+# A2  map_roi_levels -- .../roi_extractors/single_level_roi_extractor.py:32-51
+# --------------------------------------------------------------------------------------------
+def map_roi_levels(rois, num_levels, finest_scale=56):
+    """The reference expression itself, on whatever device ``rois`` lives on (torch)."""
+    rois = torch.as_tensor(rois, dtype=torch.float32)
+    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    lv = torch.floor(torch.log2(scale / finest_scale + 1e-6))
+    return lv.clamp(min=0, max=num_levels - 1).long()
+
+
+def map_roi_levels_c(rois, num_levels, finest_scale=56.0, recip_mode=0):
+    r = _np32(rois)
+    out = np.empty((r.shape[0],), np.int64)
+    lib().orc_map_levels(_p(r), r.shape[0], int(num_levels), ctypes.c_float(finest_scale),
+                         int(recip_mode), _p(out, _i64p))
+    return out
+
+
+def assign(rois, onehot, num_levels, finest_scale=56):
+    """(lvl, bucket, perm, seg_offsets): stable grouping by bucket."""
+    lvl = map_roi_levels(rois, num_levels, finest_scale).numpy()
+    if onehot is None:
+        bucket = np.zeros_like(lvl)
+        nb = 1
+    else:
+        bucket = bucket_of(onehot).numpy()
+        nb = int(torch.as_tensor(onehot).shape[1])
+    perm = np.argsort(bucket, kind='stable').astype(np.int64)
+    counts = np.bincount(bucket, minlength=nb)
+    seg = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return lvl, bucket, perm, seg
+
+
+# --------------------------------------------------------------------------------------------
+# A12 roi_rescale -- .../roi_extractors/base_roi_extractor.py:57-79
+# --------------------------------------------------------------------------------------------
+def roi_rescale(rois, scale_factor):
+    r = torch.as_tensor(rois, dtype=torch.float32)
+    cx = (r[:, 1] + r[:, 3]) * 0.5
+    cy = (r[:, 2] + r[:, 4]) * 0.5
+    nw = (r[:, 3] - r[:, 1]) * scale_factor
+    nh = (r[:, 4] - r[:, 2]) * scale_factor
+    return torch.stack((r[:, 0], cx - nw * 0.5, cy - nh * 0.5, cx + nw * 0.5, cy + nh * 0.5), -1)
+
+
+# --------------------------------------------------------------------------------------------
+# A4/A5  RoIAlign forward / backward (mmcv.ops.roi_align; see dm_oracle.c header)
+# --------------------------------------------------------------------------------------------
+def _pair(v):
+    return (int(v), int(v)) if np.isscalar(v) else (int(v[0]), int(v[1]))
+
+
+def roi_align(feat, rois, output_size, spatial_scale=1.0, sampling_ratio=0, aligned=True):
+    f = _np32(feat)
+    r = _np32(rois).reshape(-1, 5)
+    ph, pw = _pair(output_size)
+    n, c, h, w = f.shape
+    out = np.empty((r.shape[0], c, ph, pw), np.float32)
+    lib().orc_roi_align_fwd(_p(f), n, c, h, w, _p(r), r.shape[0], ph, pw,
+                            ctypes.c_float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                            _p(out))
+    return torch.from_numpy(out)
+
+
+def roi_align_backward(grad_out, rois, feat_shape, spatial_scale=1.0, sampling_ratio=0,
+                       aligned=True):
+    g = _np32(grad_out)
+    r = _np32(rois).reshape(-1, 5)
+    n, c, h, w = [int(v) for v in feat_shape]
+    ph, pw = g.shape[2], g.shape[3]
+    gi = np.empty((n, c, h, w), np.float32)
+    lib().orc_roi_align_bwd(_p(g), n, c, h, w, _p(r), r.shape[0], ph, pw,
+                            ctypes.c_float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                            _p(gi))
+    return torch.from_numpy(gi)
+
+
+def roi_align_tv(feat, rois, output_size, spatial_scale=1.0, sampling_ratio=0, aligned=True):
+    """The stand-in library kernel (torchvision CPU); used for pinning and as the timed CPU path."""
+    import torchvision.ops
+    return torchvision.ops.roi_align(torch.as_tensor(feat, dtype=torch.float32),
+                                     torch.as_tensor(rois, dtype=torch.float32),
+                                     _pair(output_size), spatial_scale, sampling_ratio, aligned)
+
+
+# --------------------------------------------------------------------------------------------
+# A3  SingleRoIExtractor.forward -- .../single_level_roi_extractor.py:53-81
+# --------------------------------------------------------------------------------------------
+def single_roi_extractor(feats, rois, output_size, featmap_strides, finest_scale=56,
+                         sampling_ratio=0, roi_scale_factor=None, kernel=roi_align):
+    """Per-level select / align / scatter-back; unmatched RoIs stay zero."""
+    rois = torch.as_tensor(rois, dtype=torch.float32)
+    ph, pw = _pair(output_size)
+    feats = [torch.as_tensor(f, dtype=torch.float32) for f in feats]
+    out = torch.zeros((rois.shape[0], feats[0].shape[1], ph, pw), dtype=torch.float32)
+    if len(feats) == 1:
+        if rois.shape[0] == 0:
+            return out
+        return kernel(feats[0], rois, (ph, pw), 1.0 / featmap_strides[0], sampling_ratio, True)
+    lvls = map_roi_levels(rois, len(feats), finest_scale)
+    if roi_scale_factor is not None:
+        rois = roi_rescale(rois, roi_scale_factor)
+    for i, f in enumerate(feats):
+        sel = lvls == i
+        if bool(sel.any()):
+            out[sel] = kernel(f, rois[sel], (ph, pw), 1.0 / featmap_strides[i], sampling_ratio,
+                              True)
+    return out
+
+
+def single_roi_extractor_backward(grad_out, feats_shapes, rois, featmap_strides, finest_scale=56,
+                                  sampling_ratio=0, roi_scale_factor=None):
+    """Gradient w.r.t. every level's feature map of ``single_roi_extractor``."""
+    rois = torch.as_tensor(rois, dtype=torch.float32)
+    grad_out = torch.as_tensor(grad_out, dtype=torch.float32)
+    if len(feats_shapes) == 1:
+        return [roi_align_backward(grad_out, rois, feats_shapes[0], 1.0 / featmap_strides[0],
+                                   sampling_ratio, True)]
+    lvls = map_roi_levels(rois, len(feats_shapes), finest_scale)
+    if roi_scale_factor is not None:
+        rois = roi_rescale(rois, roi_scale_factor)
+    grads = []
+    for i, shp in enumerate(feats_shapes):
+        sel = lvls == i
+        grads.append(roi_align_backward(grad_out[sel], rois[sel], shp, 1.0 / featmap_strides[i],
+                                        sampling_ratio, True))
+    return grads
+
+
+def bucketed_extract(feats, rois, onehot, bucket_sizes, featmap_strides, finest_scale=56,
+                     sampling_ratio=0, kernel=roi_align):
+    """North-star stage 1+2: each RoI aligned at the output size its one-hot label selects.
+
+    Returns (list of [K_b,C,P_b,P_b] in original RoI order within each bucket, perm, seg)."""
+    rois = torch.as_tensor(rois, dtype=torch.float32)
+    _, bucket, perm, seg = assign(rois, onehot, len(feats), finest_scale)
+    outs = []
+    for b, p in enumerate(bucket_sizes):
+        idx = torch.from_numpy(perm[seg[b]:seg[b + 1]])
+        outs.append(single_roi_extractor(feats, rois[idx], p, featmap_strides, finest_scale,
+                                         sampling_ratio, kernel=kernel))
+    return outs, perm, seg
+
+
+# --------------------------------------------------------------------------------------------
+# A8/A9  BitmapMasks.crop_and_resize + mask_target -- mmdet/core/mask/structures.py:256-286,
+#        mmdet/core/mask/mask_target.py:6-62, .../mask_heads/dynamask_head.py:246-271
+# --------------------------------------------------------------------------------------------
+def crop_and_resize(masks_u8, boxes, out_shape, inds, clip=False):
+    """uint8 [G,H,W], boxes [K,4], inds [K] -> bool [K,S_h,S_w]."""
+    m = np.ascontiguousarray(masks_u8, dtype=np.uint8)
+    sh, sw = _pair(out_shape)
+    if m.shape[0] == 0:
+        return np.empty((0, sh, sw), dtype=np.uint8)
+    b = _np32(boxes).reshape(-1, 4)
+    i = np.ascontiguousarray(np.asarray(inds), dtype=np.int64)
+    out = np.empty((b.shape[0], sh, sw), np.float32)
+    lib().orc_mask_target(_p(m, _u8p), m.shape[0], m.shape[1], m.shape[2], _p(b), _p(i, _i64p),
+                          b.shape[0], sh, sw, int(bool(clip)), _p(out))
+    return out >= 0.5
+
+
+def mask_target_single(pos_proposals, pos_assigned_gt_inds, gt_masks_u8, mask_size):
+    sh, sw = _pair(mask_size)
+    b = _np32(pos_proposals).reshape(-1, 4)
+    if b.shape[0] == 0:
+        return torch.zeros((0, sh, sw), dtype=torch.float32)
+    t = crop_and_resize(gt_masks_u8, b, (sh, sw), pos_assigned_gt_inds, clip=True)
+    return torch.from_numpy(t.astype(np.float32))
+
+
+def mask_target(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list, mask_size):
+    ts = [mask_target_single(p, i, g, mask_size)
+          for p, i, g in zip(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list)]
+    return torch.cat(ts) if ts else ts
+
+
+def dyna_get_targets(pos_bboxes_list, pos_assigned_gt_inds_list, gt_masks_list,
+                     stage_sup_size=(14, 28, 56, 112)):
+    return [mask_target(pos_bboxes_list, pos_assigned_gt_inds_list, gt_masks_list, s)
+            for s in stage_sup_size]
+
+
+# --------------------------------------------------------------------------------------------
+# A6/A7  _do_paste_mask + get_seg_masks -- .../mask_heads/fcn_mask_head.py:240-308,
+#        .../mask_heads/dynamask_head.py:279-342
+# --------------------------------------------------------------------------------------------
+def paste_values_c(prob, boxes, img_h, img_w):
+    """Un-thresholded full-canvas paste from probabilities, separable C restatement."""
+    p = _np32(prob)
+    p = p.reshape(p.shape[0], p.shape[-2], p.shape[-1])
+    b = _np32(boxes).reshape(-1, 4)
+    out = np.empty((p.shape[0], int(img_h), int(img_w)), np.float32)
+    lib().orc_paste(_p(p), p.shape[0], p.shape[1], p.shape[2], _p(b), int(img_h), int(img_w),
+                    _p(out))
+    return torch.from_numpy(out)
+
+
+def do_paste_mask(masks, boxes, img_h, img_w, skip_empty=True):
+    """grid_sample form (the reference's own formulation) on CPU tensors."""
+    masks = torch.as_tensor(masks, dtype=torch.float32)
+    boxes = torch.as_tensor(boxes, dtype=torch.float32)
+    if skip_empty:
+        lo = torch.clamp(boxes.min(dim=0).values.floor()[:2] - 1, min=0).to(torch.int32)
+        x_lo, y_lo = int(lo[0]), int(lo[1])
+        x_hi = int(torch.clamp(boxes[:, 2].max().ceil() + 1, max=img_w).to(torch.int32))
+        y_hi = int(torch.clamp(boxes[:, 3].max().ceil() + 1, max=img_h).to(torch.int32))
+    else:
+        x_lo, y_lo, x_hi, y_hi = 0, 0, int(img_w), int(img_h)
+    bx0, by0, bx1, by1 = torch.split(boxes, 1, dim=1)
+    n = masks.shape[0]
+    ys = torch.arange(y_lo, y_hi, dtype=torch.float32) + 0.5
+    xs = torch.arange(x_lo, x_hi, dtype=torch.float32) + 0.5
+    ys = (ys - by0) / (by1 - by0) * 2 - 1
+    xs = (xs - bx0) / (bx1 - bx0) * 2 - 1
+    xs[torch.isinf(xs)] = 0
+    ys[torch.isinf(ys)] = 0
+    gx = xs[:, None, :].expand(n, ys.size(1), xs.size(1))
+    gy = ys[:, :, None].expand(n, ys.size(1), xs.size(1))
+    out = F.grid_sample(masks, torch.stack([gx, gy], dim=3), align_corners=False)
+    if skip_empty:
+        return out[:, 0], (slice(y_lo, y_hi), slice(x_lo, x_hi))
+    return out[:, 0], ()
+
+
+def get_seg_masks(mask_pred, det_bboxes, det_labels, mask_thr_binary, ori_shape, scale_factor,
+                  rescale):
+    """DynaMaskHead.get_seg_masks on CPU: list of N numpy [img_h,img_w] (bool, or uint8 if thr<0)."""
+    prob = torch.as_tensor(mask_pred, dtype=torch.float32).sigmoid()
+    det_bboxes = torch.as_tensor(det_bboxes, dtype=torch.float32)
+    boxes = det_bboxes[:, :4]
+    if rescale:
+        img_h, img_w = int(ori_shape[0]), int(ori_shape[1])
+    else:
+        img_h = int(np.round(ori_shape[0] * scale_factor).astype(np.int32))
+        img_w = int(np.round(ori_shape[1] * scale_factor).astype(np.int32))
+        scale_factor = 1.0
+    if not isinstance(scale_factor, (float, torch.Tensor)):
+        scale_factor = boxes.new_tensor(scale_factor)
+    boxes = boxes / scale_factor
+    n = prob.shape[0]
+    if prob.shape[1] > 1:
+        prob = prob[range(n), torch.as_tensor(det_labels)][:, None]
+    thr = mask_thr_binary
+    canvas = torch.zeros(n, img_h, img_w, dtype=torch.bool if thr >= 0 else torch.uint8)
+    for i in range(n):  # CPU mode of the reference: one instance per chunk, skip_empty=True
+        chunk, sl = do_paste_mask(prob[i:i + 1], boxes[i:i + 1], img_h, img_w, skip_empty=True)
+        if thr >= 0:
+            chunk = (chunk >= thr).to(torch.bool)
+        else:
+            chunk = (chunk * 255).to(torch.uint8)
+        canvas[(torch.tensor([i]),) + sl] = chunk
+    return [canvas[i].numpy() for i in range(n)]
