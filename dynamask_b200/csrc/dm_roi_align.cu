@@ -1,0 +1,821 @@
+// Stage 2: aligned avg-pool multi-level RoIAlign, forward and backward, for sm_100a.
+//
+// Replaces mmcv._ext.roi_align_forward / roi_align_backward as reached from
+// mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:52-54 together with the per-level
+// select / align / scatter loop of SingleRoIExtractor.forward
+// (mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:53-81).
+//
+// Formulation.  For one RoI and one channel, bilinear sampling followed by the sampling-grid
+// average is a separable linear map
+//        out[ph][pw] = sum_y sum_x  Ay[ph][y] * Ax[pw][x] * feat[y][x]
+// where Ax / Ay are banded: bin pw touches the pixels xs[pw] .. xs[pw]+JX-1 only.  The kernel
+//   1. folds the g_w (g_h) sample weights of every bin into the banded tables Ax, Ay and stages
+//      them in shared memory once per work unit (they are shared by all channels),
+//   2. stages the RoI's feature patch (rows Y0..Y1, columns X0..X1) for a group of channels,
+//   3. X pass:  V[y][pw]  = sum_j Ax[pw][j] * patch[y][xs[pw]+j]          (shared -> shared)
+//   4. Y pass:  out[ph][pw] = sum_j Ay[ph][j] * V[ys[ph]+j][pw]           (shared -> 16-B streaming stores)
+// so HBM sees each patch element once and each output element once.  Backward is the transpose:
+// a column pass that walks grad_out down each column with a register window of band rows
+// (grad_out is read once, straight into registers), a row pass that gathers the patch gradient,
+// and one global reduction (RED.ADD.F32) per touched feature pixel -- i.e. the atomics are
+// aggregated per CTA in shared memory before they reach L2.
+//
+// Scheduling.  All resolution buckets run in ONE persistent launch: grid = SMs x resident CTAs,
+// work units = (RoI, channel slab) enumerated bucket by bucket from the largest output size to the
+// smallest, static round-robin over CTAs.  Bucket membership comes from device memory
+// (dm_assign's perm / seg_offsets), so no host synchronisation is needed.
+//
+// Summation order differs from the sample-by-sample order of the reference; the contract for
+// feature RoIAlign is 1e-5 relative (forward) / 1e-4 (backward), see tests/test_roi_align_gpu.py.
+#include <climits>
+#include <cstdlib>
+
+#include "dm_common.cuh"
+
+namespace dm {
+
+constexpr int kRaThreads = 256;
+constexpr int kRaWarps = kRaThreads / 32;
+
+struct LevelDesc {
+    float* ptr;  // const for forward, accumulated into for backward
+    int N, C, H, W;
+    long long sN, sC, sH, sW;
+    float scale;
+};
+
+struct BucketDesc {
+    float* ptr;  // written by forward, read by backward
+    int ph, pw;
+    long long sN, sC, sH, sW;
+    int cg;     // channels per work unit
+    int nslab;  // ceil(C / cg)
+    int vec;    // vector width of the pooled-row accesses (4, 2 or 1)
+};
+
+struct RaParams {
+    LevelDesc lv[DM_MAX_LEVELS];
+    BucketDesc bk[DM_MAX_BUCKETS];
+    int order[DM_MAX_BUCKETS];
+    int L, nb, K, C;
+    const float* rois;
+    const int32_t* lvl;
+    const int32_t* perm;
+    const int32_t* seg;
+    int sampling_ratio, aligned;
+    int smem_floats;
+};
+
+// exact n / d for n, d < 2^20
+struct FastDiv {
+    unsigned long long m;
+    __device__ __forceinline__ void init(unsigned d) { m = ((1ull << 40) + d - 1) / d; }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return (unsigned)((n * m) >> 40); }
+};
+
+__device__ __forceinline__ int pow2_shift_ge(int n) {  // smallest s with (1 << s) >= n
+    return n <= 1 ? 0 : 32 - __clz(n - 1);
+}
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* p, float (&a)[VEC]) {
+    if (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        a[0] = v.x; a[1 % VEC] = v.y; a[2 % VEC] = v.z; a[3 % VEC] = v.w;
+    } else if (VEC == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        a[0] = v.x; a[1 % VEC] = v.y;
+    } else {
+        a[0] = *p;
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void ldg_stream_vec(const float* p, float (&a)[VEC]) {
+    if (VEC == 4) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        a[0] = v.x; a[1 % VEC] = v.y; a[2 % VEC] = v.z; a[3 % VEC] = v.w;
+    } else if (VEC == 2) {
+        const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+        a[0] = v.x; a[1 % VEC] = v.y;
+    } else {
+        a[0] = __ldcs(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_stream_vec(float* p, const float (&a)[VEC]) {
+    if (VEC == 4) st_stream(reinterpret_cast<float4*>(p), make_float4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]));
+    else if (VEC == 2) st_stream(reinterpret_cast<float2*>(p), make_float2(a[0], a[1 % VEC]));
+    else st_stream(p, a[0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Banded weight tables of one RoI, staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+enum { ST_JX = 0, ST_X0, ST_X1, ST_PA, ST_PB, ST_JY, ST_Y0, ST_Y1, ST_QA, ST_QB, ST_N };
+
+struct Tables {
+    int* xs;    // [pw]  first feature column touched by bin pw
+    int* ys;    // [ph]
+    float* wx;  // [JX][pw] folded weights (already divided by g_w)
+    float* wy;  // [JY][ph]
+    int JX, JY, X0, X1, Y0, Y1;
+    int floats;  // shared-memory floats consumed (multiple of 4)
+};
+
+__device__ __forceinline__ void axis_scan(int P, int size, float start, float bin, int grid,
+                                          int* s_start, int* stat) {
+    for (int p = threadIdx.x; p < P; p += kRaThreads) {
+        int first = INT_MAX, last = -1;
+        for (int i = 0; i < grid; ++i) {
+            int lo, hi;
+            float l, h;
+            if (axis_tap(sample_coord(start, bin, grid, p, i), size, lo, hi, l, h)) {
+                first = min(first, lo);
+                last = max(last, hi);
+            }
+        }
+        s_start[p] = first;
+        if (last >= 0) {
+            atomicMax(&stat[0], last - first + 1);
+            atomicMin(&stat[1], first);
+            atomicMax(&stat[2], last);
+            atomicMin(&stat[3], p);
+            atomicMax(&stat[4], p);
+        }
+    }
+}
+
+__device__ __forceinline__ void axis_fill(int P, int size, float start, float bin, int grid,
+                                          const int* s_start, float* w) {
+    const float inv = 1.0f / (float)grid;
+    for (int p = threadIdx.x; p < P; p += kRaThreads) {
+        const int st = s_start[p];
+        for (int i = 0; i < grid; ++i) {
+            int lo, hi;
+            float l, h;
+            if (axis_tap(sample_coord(start, bin, grid, p, i), size, lo, hi, l, h)) {
+                w[(lo - st) * P + p] += h * inv;
+                w[(hi - st) * P + p] += l * inv;
+            }
+        }
+    }
+}
+
+// Returns false (uniformly) when the RoI has no valid sample at all -> output is all zeros.
+// `fits` is set false when the tables alone exceed the shared-memory budget.
+__device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, float* smem,
+                             int smem_floats, int* stat, Tables& t, bool& fits) {
+    fits = true;
+    if (threadIdx.x < ST_N) {
+        const int k = threadIdx.x;
+        stat[k] = (k == ST_X0 || k == ST_PA || k == ST_Y0 || k == ST_QA) ? INT_MAX : (k == ST_JX || k == ST_JY ? 0 : -1);
+    }
+    t.xs = reinterpret_cast<int*>(smem);
+    t.ys = t.xs + Pw;
+    __syncthreads();
+    if (g.gw <= 0 || g.gh <= 0) return false;
+    if (Pw + Ph > smem_floats) { fits = false; return true; }
+    axis_scan(Pw, W, g.rsw, g.bw, g.gw, t.xs, stat + ST_JX);
+    axis_scan(Ph, H, g.rsh, g.bh, g.gh, t.ys, stat + ST_JY);
+    __syncthreads();
+    t.JX = stat[ST_JX]; t.X0 = stat[ST_X0]; t.X1 = stat[ST_X1];
+    t.JY = stat[ST_JY]; t.Y0 = stat[ST_Y0]; t.Y1 = stat[ST_Y1];
+    if (t.JX <= 0 || t.JY <= 0) return false;
+    const int pa = stat[ST_PA], pb = stat[ST_PB], qa = stat[ST_QA], qb = stat[ST_QB];
+    const int base = (Pw + Ph + 3) & ~3;
+    const int wfloats = t.JX * Pw + t.JY * Ph;
+    t.floats = (base + wfloats + 3) & ~3;
+    if (t.floats > smem_floats) { fits = false; return true; }
+    t.wx = smem + base;
+    t.wy = t.wx + t.JX * Pw;
+    // bins without any valid sample sit at the two ends; give them a start that keeps xs / ys
+    // monotone (their weights stay zero)
+    const int xs_last = t.xs[pb], ys_last = t.ys[qb];
+    __syncthreads();
+    for (int p = threadIdx.x; p < Pw; p += kRaThreads)
+        if (t.xs[p] == INT_MAX) t.xs[p] = p < pa ? t.X0 : xs_last;
+    for (int p = threadIdx.x; p < Ph; p += kRaThreads)
+        if (t.ys[p] == INT_MAX) t.ys[p] = p < qa ? t.Y0 : ys_last;
+    for (int i = threadIdx.x; i < wfloats; i += kRaThreads) t.wx[i] = 0.0f;
+    __syncthreads();
+    axis_fill(Pw, W, g.rsw, g.bw, g.gw, t.xs, t.wx);
+    axis_fill(Ph, H, g.rsh, g.bh, g.gh, t.ys, t.wy);
+    __syncthreads();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unit bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct Unit {
+    int b;      // bucket
+    int i;      // position inside the bucket (row of the bucket's output tensor)
+    int slab;   // channel slab
+};
+
+__device__ __forceinline__ long long total_units(const RaParams& p, const int* s_seg) {
+    long long tot = 0;
+    for (int j = 0; j < p.nb; ++j) {
+        const int b = p.order[j];
+        tot += (long long)(s_seg[b + 1] - s_seg[b]) * p.bk[b].nslab;
+    }
+    return tot;
+}
+
+__device__ __forceinline__ Unit decode_unit(const RaParams& p, const int* s_seg, long long u) {
+    Unit un;
+    un.b = p.order[p.nb - 1];
+    un.i = 0;
+    un.slab = 0;
+    for (int j = 0; j < p.nb; ++j) {
+        const int b = p.order[j];
+        const long long n = (long long)(s_seg[b + 1] - s_seg[b]) * p.bk[b].nslab;
+        if (u < n) {
+            un.b = b;
+            // slab-major inside a RoI so consecutive CTAs share one RoI's patch in L2
+            un.i = (int)(u / p.bk[b].nslab);
+            un.slab = (int)(u - (long long)un.i * p.bk[b].nslab);
+            return un;
+        }
+        u -= n;
+    }
+    return un;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fallbacks: zero fill, and direct (sample-by-sample) evaluation for geometries whose tables or
+// tiles do not fit in shared memory (e.g. a whole 800x1344 map pooled to 14x14).
+// ---------------------------------------------------------------------------------------------
+__device__ void zero_unit(const BucketDesc& B, int i, int c0, int c1) {
+    const int per_c = B.ph * B.pw;
+    const int n = (c1 - c0) * per_c;
+    for (int e = threadIdx.x; e < n; e += kRaThreads) {
+        const int c = e / per_c, r = e - c * per_c;
+        const int ph = r / B.pw, pw = r - ph * B.pw;
+        B.ptr[(long long)i * B.sN + (long long)(c0 + c) * B.sC + (long long)ph * B.sH + (long long)pw * B.sW] = 0.0f;
+    }
+}
+
+template <bool BWD>
+__device__ void direct_unit(const LevelDesc& Lv, const BucketDesc& B, const RoiGeom& g, int batch,
+                            int i, int c0, int c1) {
+    const int per_c = B.ph * B.pw;
+    const int n = (c1 - c0) * per_c;
+    const int cnt = g.gh * g.gw;
+    const float inv_count = 1.0f / (float)(cnt > 1 ? cnt : 1);
+    for (int e = threadIdx.x; e < n; e += kRaThreads) {
+        const int c = e / per_c, r = e - c * per_c;
+        const int ph = r / B.pw, pw = r - ph * B.pw;
+        float* o = B.ptr + (long long)i * B.sN + (long long)(c0 + c) * B.sC + (long long)ph * B.sH + (long long)pw * B.sW;
+        float* f = Lv.ptr + (long long)batch * Lv.sN + (long long)(c0 + c) * Lv.sC;
+        float acc = 0.0f;
+        const float gv = BWD ? *o * inv_count : 0.0f;
+        for (int iy = 0; iy < g.gh; ++iy) {
+            int yl, yh;
+            float ly, hy;
+            if (!axis_tap(sample_coord(g.rsh, g.bh, g.gh, ph, iy), Lv.H, yl, yh, ly, hy)) continue;
+            for (int ix = 0; ix < g.gw; ++ix) {
+                int xl, xh;
+                float lx, hx;
+                if (!axis_tap(sample_coord(g.rsw, g.bw, g.gw, pw, ix), Lv.W, xl, xh, lx, hx)) continue;
+                float* p1 = f + (long long)yl * Lv.sH + (long long)xl * Lv.sW;
+                float* p2 = f + (long long)yl * Lv.sH + (long long)xh * Lv.sW;
+                float* p3 = f + (long long)yh * Lv.sH + (long long)xl * Lv.sW;
+                float* p4 = f + (long long)yh * Lv.sH + (long long)xh * Lv.sW;
+                if (BWD) {
+                    atomicAdd(p1, gv * hy * hx);
+                    atomicAdd(p2, gv * hy * lx);
+                    atomicAdd(p3, gv * ly * hx);
+                    atomicAdd(p4, gv * ly * lx);
+                } else {
+                    acc += hy * hx * __ldg(p1) + hy * lx * __ldg(p2) + ly * hx * __ldg(p3) + ly * lx * __ldg(p4);
+                }
+            }
+        }
+        if (!BWD) *o = acc * inv_count;
+    }
+}
+
+// Rows of the feature map needed by pooled rows [p0, p1): ys[p0] .. min(ys[p1-1]+JY-1, Y1)
+__device__ __forceinline__ int band_rows(const Tables& t, int p0, int p1) {
+    return min(t.ys[p1 - 1] + t.JY - 1, t.Y1) - t.ys[p0] + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward unit
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, float* tile,
+                         int batch, int i, int c0, int cs, int p0, int p1) {
+    const int Pw = B.pw;
+    const int fw = t.X1 - t.X0 + 1;
+    const int Yt0 = t.ys[p0];
+    const int R = band_rows(t, p0, p1);
+    float* V = tile;                    // [cs][R][Pw]
+    float* patch = tile + cs * R * Pw;  // [cs][R][fw]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- stage the patch: one warp per (channel, row), eight rows in flight per warp ----------
+    {
+        const float* src = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Yt0 * Lv.sH + (long long)t.X0 * Lv.sW;
+        const int nrows = cs * R;
+        FastDiv fdR;
+        fdR.init(R);
+        constexpr int PF = 8;  // rows in flight per warp
+        for (int r0 = warp; r0 < nrows; r0 += PF * kRaWarps) {
+            for (int x = lane; x < fw; x += 32) {
+                float v[PF];
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    const int row = r0 + q * kRaWarps;
+                    v[q] = 0.0f;
+                    if (row < nrows) {
+                        const int c = fdR.div(row), r = row - c * R;
+                        v[q] = __ldg(src + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    const int row = r0 + q * kRaWarps;
+                    if (row < nrows) patch[row * fw + x] = v[q];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- X pass: V[c][r][pw] = sum_j wx[j][pw] * patch[c][r][xs[pw]-X0+j] ---------------------
+    {
+        const int sh = pow2_shift_ge(Pw);
+        const int nrows = cs * R;
+        const int items = nrows << sh;
+        const int JX = t.JX;
+        for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
+            const int row = vi >> sh, pw = vi & ((1 << sh) - 1);
+            if (pw >= Pw) continue;
+            const float* prow = patch + row * fw;
+            const int x0 = t.xs[pw] - t.X0;
+            float acc = 0.0f;
+            for (int j = 0; j < JX; ++j) acc += t.wx[j * Pw + pw] * prow[min(x0 + j, fw - 1)];
+            V[row * Pw + pw] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- Y pass: out[c][ph][pw..pw+VEC) = sum_j wy[j][ph] * V[c][ys[ph]-Yt0+j][pw..] ----------
+    {
+        const int PwV = Pw / VEC;
+        const int sh = pow2_shift_ge(PwV);
+        const int nph = p1 - p0;
+        const int nrows = cs * nph;
+        const int items = nrows << sh;
+        const int JY = t.JY;
+        FastDiv fdP;
+        fdP.init(nph);
+        float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+        for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
+            const int row = vi >> sh, pv = vi & ((1 << sh) - 1);
+            if (pv >= PwV) continue;
+            const int c = fdP.div(row), ph = p0 + (row - c * nph);
+            const int r0 = t.ys[ph] - Yt0;
+            const float* vc = V + c * R * Pw + pv * VEC;
+            float acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+            for (int j = 0; j < JY; ++j) {
+                const float w = t.wy[j * B.ph + ph];
+                float v[VEC];
+                ld_vec<VEC>(vc + min(r0 + j, R - 1) * Pw, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += w * v[e];
+            }
+            float* o = obase + (long long)c * B.sC + (long long)ph * B.sH + (long long)(pv * VEC) * B.sW;
+            if (VEC == 1) __stcs(o, acc[0]);
+            else st_stream_vec<VEC>(o, acc);
+        }
+    }
+}
+
+template <int VEC>
+__device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, float* smem, int* stat) {
+    const BucketDesc& B = p.bk[un.b];
+    const int pos = s_seg[un.b] + un.i;
+    const int k = p.perm ? p.perm[pos] : pos;
+    const int c0 = un.slab * B.cg, c1 = min(c0 + B.cg, p.C);
+    const float* roi = p.rois + 5 * (size_t)k;
+    const int lv = p.lvl ? p.lvl[k] : 0;
+    const int batch = (int)roi[0];
+    if (lv < 0 || lv >= p.L || batch < 0 || batch >= p.lv[lv < 0 || lv >= p.L ? 0 : lv].N) {
+        zero_unit(B, un.i, c0, c1);
+        return;
+    }
+    const LevelDesc& Lv = p.lv[lv];
+    const RoiGeom g = roi_geom(roi, Lv.scale, B.ph, B.pw, p.sampling_ratio, p.aligned);
+    Tables t;
+    bool fits;
+    if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) {
+        zero_unit(B, un.i, c0, c1);
+        return;
+    }
+    const int fw = fits ? t.X1 - t.X0 + 1 : 0;
+    const int avail = p.smem_floats - (fits ? t.floats : 0);
+    // smallest possible tile: one channel, one pooled row
+    if (!fits || (long long)t.JY * (fw + B.pw) > avail) {
+        direct_unit<false>(Lv, B, g, batch, un.i, c0, c1);
+        return;
+    }
+    float* tile = smem + t.floats;
+    const int per_row = fw + B.pw;
+    const int Rfull = t.Y1 - t.Y0 + 1;
+    if ((long long)Rfull * per_row <= avail) {
+        const int cs_max = min(c1 - c0, avail / (Rfull * per_row));
+        for (int c = c0; c < c1; c += cs_max) {
+            fwd_tile<VEC>(Lv, B, t, tile, batch, un.i, c, min(cs_max, c1 - c), 0, B.ph);
+            __syncthreads();
+        }
+    } else {
+        // tall RoI: one channel at a time, pooled rows in tiles whose band fits
+        for (int c = c0; c < c1; ++c) {
+            int q0 = 0;
+            while (q0 < B.ph) {
+                int q1 = q0 + 1;
+                while (q1 < B.ph && (long long)band_rows(t, q0, q1 + 1) * per_row <= avail) ++q1;
+                fwd_tile<VEC>(Lv, B, t, tile, batch, un.i, c, 1, q0, q1);
+                __syncthreads();
+                q0 = q1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward unit
+// ---------------------------------------------------------------------------------------------
+// Column pass: every thread owns (channel, column vector, run of pooled rows) and walks its run
+// top to bottom keeping the JYW band rows it is currently touching in registers.  Completed band
+// rows are added to the shared accumulator U[c][r][pw] (shared-memory reductions; runs of the
+// same column overlap in at most JY-1 rows).
+template <int VEC, int JYW>
+__device__ void bwd_column_pass(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
+    const int Pw = B.pw, Ph = B.ph;
+    const int PwV = Pw / VEC;
+    const int R = t.Y1 - t.Y0 + 1;
+    const int nstrips = cs * PwV;
+    // split the pooled rows into runs so that there are >= 2 items per thread when possible
+    int nseg = (2 * kRaThreads + nstrips - 1) / nstrips;
+    nseg = max(1, min(nseg, Ph / 8 > 0 ? Ph / 8 : 1));
+    const int seg_len = (Ph + nseg - 1) / nseg;
+    const int items = nstrips * nseg;
+    FastDiv fdS, fdV;
+    fdS.init(nstrips);
+    fdV.init(PwV);
+    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+    const int JY = t.JY;
+    for (int it = threadIdx.x; it < items; it += kRaThreads) {
+        const int sg = fdS.div(it), strip = it - sg * nstrips;
+        const int c = fdV.div(strip), pv = strip - c * PwV;
+        const int q0 = sg * seg_len, q1 = min(q0 + seg_len, Ph);
+        if (q0 >= q1) continue;
+        const float* gp = gbase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW;
+        float* uc = U + c * R * Pw + pv * VEC;
+        float acc[JYW][VEC];
+#pragma unroll
+        for (int j = 0; j < JYW; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
+        int base = t.ys[q0];
+        constexpr int PF = 8;  // pooled rows loaded ahead of use
+        for (int ph0 = q0; ph0 < q1; ph0 += PF) {
+            float gv[PF][VEC];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                if (ph0 + u < q1) ldg_stream_vec<VEC>(gp + (long long)(ph0 + u) * B.sH, gv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int ph = ph0 + u;
+                if (ph >= q1) break;
+                const int y0 = t.ys[ph];
+                while (base < y0) {
+                    const int r = base - t.Y0;
+                    if (r < R) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e)
+                            if (acc[0][e] != 0.0f) atomicAdd(uc + r * Pw + e, acc[0][e]);
+                    }
+#pragma unroll
+                    for (int j = 0; j + 1 < JYW; ++j)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[JYW - 1][e] = 0.0f;
+                    ++base;
+                }
+#pragma unroll
+                for (int j = 0; j < JYW; ++j) {
+                    if (j < JY) {
+                        const float w = t.wy[j * Ph + ph];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[j][e] += w * gv[u][e];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < JYW; ++j) {
+            const int r = base + j - t.Y0;
+            if (r < R) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    if (acc[j][e] != 0.0f) atomicAdd(uc + r * Pw + e, acc[j][e]);
+            }
+        }
+    }
+}
+
+// Generic column pass for very tall bands (JY > 8): straight shared-memory reductions.
+template <int VEC>
+__device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
+    const int Pw = B.pw, Ph = B.ph;
+    const int PwV = Pw / VEC;
+    const int R = t.Y1 - t.Y0 + 1;
+    const int per_c = Ph * PwV;
+    const int items = cs * per_c;
+    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+    for (int it = threadIdx.x; it < items; it += kRaThreads) {
+        const int c = it / per_c, rem = it - c * per_c;
+        const int ph = rem / PwV, pv = rem - ph * PwV;
+        float gv[VEC];
+        ldg_stream_vec<VEC>(gbase + (long long)c * B.sC + (long long)ph * B.sH + (long long)(pv * VEC) * B.sW, gv);
+        float* uc = U + c * R * Pw + pv * VEC;
+        const int r0 = t.ys[ph] - t.Y0;
+        for (int j = 0; j < t.JY; ++j) {
+            const float w = t.wy[j * Ph + ph];
+            const int r = r0 + j;
+            if (w != 0.0f && r < R) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) atomicAdd(uc + r * Pw + e, w * gv[e]);
+            }
+        }
+    }
+}
+
+// Row pass + flush: grad_patch[c][r][x] = sum_{pw : xs[pw] <= x < xs[pw]+JX} wx[x-xs[pw]][pw] * U[c][r][pw],
+// one global reduction per touched feature element.
+__device__ void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, const float* U,
+                             const int* plo, const int* phi, int batch, int c0, int cs) {
+    const int Pw = B.pw;
+    const int fw = t.X1 - t.X0 + 1;
+    const int R = t.Y1 - t.Y0 + 1;
+    const int sh = pow2_shift_ge(fw);
+    const int nrows = cs * R;
+    const int items = nrows << sh;
+    FastDiv fdR;
+    fdR.init(R);
+    float* dst = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + (long long)t.X0 * Lv.sW;
+    for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
+        const int row = vi >> sh, x = vi & ((1 << sh) - 1);
+        if (x >= fw) continue;
+        const float* urow = U + row * Pw;
+        const int lo = plo[x], hi = phi[x];
+        float acc = 0.0f;
+        for (int pw = lo; pw <= hi; ++pw) {
+            const int j = x + t.X0 - t.xs[pw];
+            acc += t.wx[j * Pw + pw] * urow[pw];
+        }
+        if (acc != 0.0f) {
+            const int c = fdR.div(row), r = row - c * R;
+            atomicAdd(dst + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW, acc);
+        }
+    }
+}
+
+template <int VEC>
+__device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, float* smem, int* stat) {
+    const BucketDesc& B = p.bk[un.b];
+    const int pos = s_seg[un.b] + un.i;
+    const int k = p.perm ? p.perm[pos] : pos;
+    const int c0 = un.slab * B.cg, c1 = min(c0 + B.cg, p.C);
+    const float* roi = p.rois + 5 * (size_t)k;
+    const int lv = p.lvl ? p.lvl[k] : 0;
+    const int batch = (int)roi[0];
+    if (lv < 0 || lv >= p.L) return;
+    const LevelDesc& Lv = p.lv[lv];
+    if (batch < 0 || batch >= Lv.N) return;
+    const RoiGeom g = roi_geom(roi, Lv.scale, B.ph, B.pw, p.sampling_ratio, p.aligned);
+    Tables t;
+    bool fits;
+    if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) return;
+    const int fw = fits ? t.X1 - t.X0 + 1 : 0;
+    const int R = fits ? t.Y1 - t.Y0 + 1 : 0;
+    // extra tables: pooled-column range touching each feature column
+    const int extra = (2 * fw + 3) & ~3;
+    const long long avail = (long long)p.smem_floats - (fits ? t.floats : 0) - extra;
+    if (!fits || (long long)R * B.pw > avail) {
+        direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
+        return;
+    }
+    int* plo = reinterpret_cast<int*>(smem + t.floats);
+    int* phi = plo + fw;
+    for (int x = threadIdx.x; x < fw; x += kRaThreads) {
+        const int xa = x + t.X0;
+        // first bin whose band reaches xa, last bin whose band starts at or before xa (xs is monotone)
+        int lo = 0, hi = B.pw - 1;
+        while (lo < B.pw && t.xs[lo] + t.JX - 1 < xa) ++lo;
+        while (hi >= 0 && t.xs[hi] > xa) --hi;
+        plo[x] = lo;
+        phi[x] = hi;
+    }
+    float* U = smem + t.floats + extra;
+    const int per_c = R * B.pw;
+    const int cs_max = min(c1 - c0, (int)(avail / per_c));
+    for (int c = c0; c < c1; c += cs_max) {
+        const int cs = min(cs_max, c1 - c);
+        for (int e = threadIdx.x; e < cs * per_c; e += kRaThreads) U[e] = 0.0f;
+        __syncthreads();
+        if (t.JY <= 4) bwd_column_pass<VEC, 4>(B, t, U, un.i, c, cs);
+        else if (t.JY <= 8) bwd_column_pass<VEC, 8>(B, t, U, un.i, c, cs);
+        else bwd_column_pass_generic<VEC>(B, t, U, un.i, c, cs);
+        __syncthreads();
+        bwd_row_pass(Lv, B, t, U, plo, phi, batch, c, cs);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent kernel
+// ---------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kRaThreads, 2) ra_kernel(const __grid_constant__ RaParams p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_seg[DM_MAX_BUCKETS + 1];
+    __shared__ int s_stat[ST_N];
+    if (threadIdx.x <= p.nb) s_seg[threadIdx.x] = p.seg ? p.seg[threadIdx.x] : (threadIdx.x == 0 ? 0 : p.K);
+    __syncthreads();
+    const long long total = total_units(p, s_seg);
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const Unit un = decode_unit(p, s_seg, u);
+        const int vec = p.bk[un.b].vec;
+        if (BWD) {
+            if (vec == 4) bwd_unit<4>(p, un, s_seg, smem, s_stat);
+            else if (vec == 2) bwd_unit<2>(p, un, s_seg, smem, s_stat);
+            else bwd_unit<1>(p, un, s_seg, smem, s_stat);
+        } else {
+            if (vec == 4) fwd_unit<4>(p, un, s_seg, smem, s_stat);
+            else if (vec == 2) fwd_unit<2>(p, un, s_seg, smem, s_stat);
+            else fwd_unit<1>(p, un, s_seg, smem, s_stat);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat_shapes,
+                       const int64_t* feat_strides, const float* spatial_scales, int L,
+                       const float* rois, int K, const int32_t* lvl, const int32_t* perm,
+                       const int32_t* seg, int nb, const int32_t* out_hw, float* const* out_ptrs,
+                       const int64_t* out_strides, int sampling_ratio, int aligned) {
+    if (L < 1 || L > DM_MAX_LEVELS || nb < 1 || nb > DM_MAX_BUCKETS || K < 0) return DM_EINVAL;
+    if (!feat_ptrs || !feat_shapes || !feat_strides || !spatial_scales || !out_hw || !out_ptrs || !out_strides)
+        return DM_EINVAL;
+    if ((perm == nullptr) != (seg == nullptr)) return DM_EINVAL;
+    if (nb > 1 && !seg) return DM_EINVAL;
+    if (K > 0 && !rois) return DM_EINVAL;
+    if (L > 1 && !lvl) return DM_EINVAL;
+    if (sampling_ratio < 0) return DM_EINVAL;
+    p.L = L;
+    p.nb = nb;
+    p.K = K;
+    p.C = feat_shapes[1];
+    for (int l = 0; l < L; ++l) {
+        LevelDesc& d = p.lv[l];
+        d.ptr = feat_ptrs[l];
+        d.N = feat_shapes[4 * l + 0];
+        d.C = feat_shapes[4 * l + 1];
+        d.H = feat_shapes[4 * l + 2];
+        d.W = feat_shapes[4 * l + 3];
+        d.sN = feat_strides[4 * l + 0];
+        d.sC = feat_strides[4 * l + 1];
+        d.sH = feat_strides[4 * l + 2];
+        d.sW = feat_strides[4 * l + 3];
+        d.scale = spatial_scales[l];
+        if (!d.ptr || d.N < 1 || d.C != p.C || d.H < 1 || d.W < 1) return DM_EINVAL;
+    }
+    if (p.C < 1) return DM_EINVAL;
+    for (int b = 0; b < nb; ++b) {
+        BucketDesc& d = p.bk[b];
+        d.ptr = out_ptrs[b];
+        d.ph = out_hw[2 * b];
+        d.pw = out_hw[2 * b + 1];
+        d.sN = out_strides[4 * b + 0];
+        d.sC = out_strides[4 * b + 1];
+        d.sH = out_strides[4 * b + 2];
+        d.sW = out_strides[4 * b + 3];
+        if (d.ph < 1 || d.pw < 1 || d.ph >= (1 << 15) || d.pw >= (1 << 15)) return DM_EINVAL;
+        // ~256 KB of pooled output per work unit
+        int cg = 65536 / (d.ph * d.pw);
+        int pw2 = 1;
+        while (pw2 * 2 <= cg) pw2 *= 2;
+        cg = cg < 1 ? 1 : pw2;
+        cg = cg < 4 ? 4 : (cg > 64 ? 64 : cg);
+        cg = env_int("DM_RA_CG", 0) > 0 ? env_int("DM_RA_CG", 0) : cg;
+        if (cg > p.C) cg = p.C;
+        d.cg = cg;
+        d.nslab = (p.C + cg - 1) / cg;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(d.ptr);
+        int vec = 1;
+        if (d.sW == 1) {
+            if (d.pw % 4 == 0 && d.sH % 4 == 0 && d.sC % 4 == 0 && d.sN % 4 == 0 && a % 16 == 0) vec = 4;
+            else if (d.pw % 2 == 0 && d.sH % 2 == 0 && d.sC % 2 == 0 && d.sN % 2 == 0 && a % 8 == 0) vec = 2;
+        }
+        d.vec = vec;
+    }
+    // largest outputs first
+    for (int b = 0; b < nb; ++b) p.order[b] = b;
+    for (int a = 0; a < nb; ++a)
+        for (int b = a + 1; b < nb; ++b)
+            if (p.bk[p.order[b]].ph * p.bk[p.order[b]].pw > p.bk[p.order[a]].ph * p.bk[p.order[a]].pw) {
+                const int tmp = p.order[a];
+                p.order[a] = p.order[b];
+                p.order[b] = tmp;
+            }
+    p.rois = rois;
+    p.lvl = lvl;
+    p.perm = perm;
+    p.seg = seg;
+    p.sampling_ratio = sampling_ratio;
+    p.aligned = aligned ? 1 : 0;
+    return DM_OK;
+}
+
+template <bool BWD>
+static int launch(RaParams& p, cudaStream_t st, const char* where) {
+    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", 100);
+    const int smem_bytes = smem_kb * 1024;
+    p.smem_floats = smem_bytes / 4;
+    DM_CUDA_CHECK(cudaFuncSetAttribute(ra_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
+    int occ = 0;
+    DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_kernel<BWD>, kRaThreads, smem_bytes), where);
+    if (occ < 1) return DM_EUNSUPPORTED;
+    const int grid = sm_count() * occ;
+    ra_kernel<BWD><<<grid, kRaThreads, smem_bytes, st>>>(p);
+    DM_LAUNCH_CHECK(where);
+    return DM_OK;
+}
+
+}  // namespace dm
+
+extern "C" int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* feat_shapes,
+                                const int64_t* feat_strides, const float* spatial_scales,
+                                int num_levels, const float* rois, int K, const int32_t* lvl,
+                                const int32_t* perm, const int32_t* seg_offsets, int num_buckets,
+                                const int32_t* out_hw, float* const* out_ptrs,
+                                const int64_t* out_strides, int sampling_ratio, int aligned,
+                                dm_stream_t stream) {
+    dm::RaParams p;
+    const int rc = dm::fill_params(p, const_cast<float* const*>(feat_ptrs), feat_shapes, feat_strides,
+                                   spatial_scales, num_levels, rois, K, lvl, perm, seg_offsets,
+                                   num_buckets, out_hw, out_ptrs, out_strides, sampling_ratio, aligned);
+    if (rc != DM_OK) return rc;
+    if (K == 0) return DM_OK;
+    for (int b = 0; b < num_buckets; ++b)
+        if (!out_ptrs[b] && !seg_offsets) return DM_EINVAL;
+    return dm::launch<false>(p, (cudaStream_t)stream, "dm_roi_align_fwd");
+}
+
+extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* feat_shapes,
+                                const int64_t* feat_strides, const float* spatial_scales,
+                                int num_levels, const float* rois, int K, const int32_t* lvl,
+                                const int32_t* perm, const int32_t* seg_offsets, int num_buckets,
+                                const int32_t* out_hw, const float* const* grad_out_ptrs,
+                                const int64_t* grad_out_strides, int sampling_ratio, int aligned,
+                                int zero_init, dm_stream_t stream) {
+    dm::RaParams p;
+    const int rc = dm::fill_params(p, grad_feat_ptrs, feat_shapes, feat_strides, spatial_scales,
+                                   num_levels, rois, K, lvl, perm, seg_offsets, num_buckets, out_hw,
+                                   const_cast<float* const*>(grad_out_ptrs), grad_out_strides,
+                                   sampling_ratio, aligned);
+    if (rc != DM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (zero_init) {
+        for (int l = 0; l < num_levels; ++l) {
+            const dm::LevelDesc& d = p.lv[l];
+            // dense map: the four strides address exactly N*C*H*W distinct elements
+            const long long n = (long long)d.N * d.C * d.H * d.W;
+            const long long span = (d.N - 1) * d.sN + (d.C - 1) * d.sC + (d.H - 1) * d.sH + (d.W - 1) * d.sW + 1;
+            if (span != n) return DM_EINVAL;
+            DM_CUDA_CHECK(cudaMemsetAsync(d.ptr, 0, sizeof(float) * (size_t)n, st), "dm_roi_align_bwd/memset");
+        }
+    }
+    if (K == 0) return DM_OK;
+    return dm::launch<true>(p, st, "dm_roi_align_bwd");
+}

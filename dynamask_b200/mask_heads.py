@@ -1,0 +1,108 @@
+"""Mask-head entry points of the hot path: paste-back and target generation.
+
+Reference: ``_do_paste_mask`` (``mmdet/models/roi_heads/mask_heads/fcn_mask_head.py:240-308``),
+``DynaMaskHead.get_seg_masks`` / ``get_targets``
+(``mmdet/models/roi_heads/mask_heads/dynamask_head.py:279-342`` / ``:246-271``).  The dense
+convolutions of the head (``DynaMaskHead.forward``, ``SFMStage``) stay PyTorch and are out of
+scope; :class:`DynaMaskHeadMixin` carries the two methods a maintainer mixes into the
+reference head.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .mask_target import multi_size_mask_targets
+
+BYTES_PER_FLOAT = 4
+# Kept for signature / behaviour parity with fcn_mask_head.py:13-16.  The fused kernel writes
+# one byte per pixel and never materialises the fp32 sampling grid, so it does not chunk.
+GPU_MEM_LIMIT = 1024**3
+
+
+def _do_paste_mask(masks, boxes, img_h, img_w, skip_empty=True):
+    """Paste instance masks according to boxes.
+
+    Args:
+        masks (Tensor): N, 1, H, W probabilities.
+        boxes (Tensor): N, 4.
+        img_h, img_w (int): canvas size.
+        skip_empty (bool): paste only the window that tightly bounds all boxes.
+
+    Returns:
+        tuple: (Tensor[N, h', w'] float32, slices) exactly like the reference: the full canvas and
+        ``()`` when ``skip_empty`` is False, else the window and its ``(slice_y, slice_x)``.
+    """
+    if skip_empty:
+        # one 16-byte readback: the window decides the *shape* of the returned tensor
+        lo = torch.clamp(boxes.min(dim=0).values.floor()[:2] - 1, min=0)
+        hi = torch.stack([torch.clamp(boxes[:, 2].max().ceil() + 1, max=img_w),
+                          torch.clamp(boxes[:, 3].max().ceil() + 1, max=img_h)])
+        x0_int, y0_int, x1_int, y1_int = torch.cat([lo, hi]).to(torch.int32).tolist()
+    else:
+        x0_int, y0_int = 0, 0
+        x1_int, y1_int = int(img_w), int(img_h)
+    out = ops.paste_masks(masks.to(torch.float32), boxes, None, int(img_h), int(img_w),
+                          [x0_int, y0_int, x1_int, y1_int], False, 0.0, ops.PASTE_F32)
+    if skip_empty:
+        return out, (slice(y0_int, y1_int), slice(x0_int, x1_int))
+    return out, ()
+
+
+def paste_masks_in_image(mask_pred, det_bboxes, det_labels, mask_thr_binary, ori_shape,
+                         scale_factor, rescale):
+    """Device-side body of ``get_seg_masks``: logits -> ``[N, img_h, img_w]`` bool (or uint8)."""
+    bboxes = det_bboxes[:, :4]
+    if rescale:
+        img_h, img_w = ori_shape[:2]
+    else:
+        img_h = np.round(ori_shape[0] * scale_factor).astype(np.int32)
+        img_w = np.round(ori_shape[1] * scale_factor).astype(np.int32)
+        scale_factor = 1.0
+    if not isinstance(scale_factor, (float, torch.Tensor)):
+        scale_factor = bboxes.new_tensor(scale_factor)
+    bboxes = bboxes / scale_factor
+    img_h, img_w = int(img_h), int(img_w)
+    labels = det_labels if mask_pred.shape[1] > 1 else None
+    if mask_thr_binary >= 0:
+        mode, thr = ops.PASTE_BOOL, float(mask_thr_binary)
+    else:
+        mode, thr = ops.PASTE_U8, 0.0  # for visualization and debugging
+    return ops.paste_masks(mask_pred.to(torch.float32), bboxes, labels, img_h, img_w,
+                           [0, 0, img_w, img_h], True, thr, mode)
+
+
+def get_seg_masks(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape, scale_factor,
+                  rescale):
+    """Get segmentation masks from mask_pred and bboxes.
+
+    Args:
+        mask_pred (Tensor): (n, #class or 1, h, w) mask logits.
+        det_bboxes (Tensor): (n, 4/5).
+        det_labels (Tensor): (n, ).
+        rcnn_test_cfg: config with ``mask_thr_binary``.
+        ori_shape: original image size.
+        scale_factor (float | ndarray | Tensor), rescale (bool): as in the reference.
+
+    Returns:
+        list[ndarray]: n masks of shape (img_h, img_w), bool (uint8 if ``mask_thr_binary < 0``).
+        One device->host copy for the whole batch instead of one per instance.
+    """
+    im_mask = paste_masks_in_image(mask_pred, det_bboxes, det_labels,
+                                   rcnn_test_cfg.mask_thr_binary, ori_shape, scale_factor, rescale)
+    host = im_mask.cpu().numpy()
+    return [host[i] for i in range(host.shape[0])]
+
+
+class DynaMaskHeadMixin(object):
+    """``get_targets`` / ``get_seg_masks`` with the reference ``DynaMaskHead`` signatures."""
+
+    stage_sup_size = [14, 28, 56, 112]
+
+    def get_targets(self, pos_bboxes_list, pos_assigned_gt_inds_list, gt_masks_list):
+        return multi_size_mask_targets(pos_bboxes_list, pos_assigned_gt_inds_list, gt_masks_list,
+                                       self.stage_sup_size)
+
+    def get_seg_masks(self, mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape,
+                      scale_factor, rescale):
+        return get_seg_masks(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape,
+                             scale_factor, rescale)

@@ -1,0 +1,314 @@
+"""torch custom ops over the C ABI of ``libdynamask_sm100.so``.
+
+Each op allocates its outputs with the PyTorch caching allocator, passes raw device pointers,
+sizes and the current CUDA stream across ``extern "C"`` and returns immediately (no host
+synchronisation).  Ops are registered for CUDA tensors only: a CPU tensor raises
+``NotImplementedError`` from the dispatcher -- there is no CPU or eager-PyTorch fallback.
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+__all__ = ['assign', 'roi_align_forward', 'roi_align_backward', 'paste_masks', 'mask_target',
+           'multilevel_roi_align']
+
+PASTE_BOOL, PASTE_U8, PASTE_F32 = 0, 1, 2
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _arr(ctype, vals):
+    return (ctype * max(len(vals), 1))(*vals)
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError('%s must be float32, got %s' % (name, t.dtype))
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# dm_assign
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op('dynamask::assign', mutates_args=(), device_types='cuda')
+def assign(rois: Tensor, onehot: Optional[Tensor], num_levels: int, finest_scale: float,
+           num_buckets: int) -> List[Tensor]:
+    """-> [lvl int32 [K], bucket int32 [K], perm int32 [K], seg_offsets int32 [num_buckets+1]]."""
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError('rois must be [K,5]')
+    rois = _f32c(rois, 'rois').contiguous()
+    K = rois.size(0)
+    dev = rois.device
+    if onehot is not None:
+        onehot = _f32c(onehot, 'onehot').contiguous()
+        if onehot.dim() != 2 or onehot.size(0) != K or onehot.size(1) != num_buckets:
+            raise ValueError('onehot must be [K,num_buckets]')
+    lvl = torch.empty(K, dtype=torch.int32, device=dev)
+    bucket = torch.empty(K, dtype=torch.int32, device=dev)
+    perm = torch.empty(K, dtype=torch.int32, device=dev)
+    seg = torch.empty(num_buckets + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_assign(_ptr(rois), K, _ptr(onehot), num_buckets, num_levels,
+                                   float(finest_scale), _ptr(lvl), _ptr(bucket), _ptr(perm),
+                                   _ptr(seg), _stream(dev))
+    _lib.check(rc, 'dm_assign')
+    return [lvl, bucket, perm, seg]
+
+
+@assign.register_fake
+def _(rois, onehot, num_levels, finest_scale, num_buckets):
+    K = rois.size(0)
+    i32 = dict(dtype=torch.int32, device=rois.device)
+    return [torch.empty(K, **i32), torch.empty(K, **i32), torch.empty(K, **i32),
+            torch.empty(num_buckets + 1, **i32)]
+
+
+# --------------------------------------------------------------------------------------------
+# dm_roi_align_fwd / dm_roi_align_bwd
+# --------------------------------------------------------------------------------------------
+def _level_arrays(feats):
+    L = len(feats)
+    ptrs = _arr(ctypes.c_void_p, [f.data_ptr() for f in feats])
+    shapes, strides = [], []
+    for f in feats:
+        if f.dim() != 4:
+            raise ValueError('feature maps must be [N,C,H,W]')
+        _f32c(f, 'feats')
+        shapes += list(f.shape)
+        strides += list(f.stride())
+    return L, ptrs, _arr(ctypes.c_int32, shapes), _arr(ctypes.c_int64, strides)
+
+
+def _bucket_arrays(tensors, out_hw):
+    ptrs = _arr(ctypes.c_void_p, [t.data_ptr() for t in tensors])
+    strides = []
+    for t in tensors:
+        strides += list(t.stride())
+    return ptrs, _arr(ctypes.c_int32, list(out_hw)), _arr(ctypes.c_int64, strides)
+
+
+@torch.library.custom_op('dynamask::roi_align_forward', mutates_args=(), device_types='cuda')
+def roi_align_forward(feats: Sequence[Tensor], rois: Tensor, lvl: Optional[Tensor],
+                      perm: Optional[Tensor], seg: Optional[Tensor], counts: Sequence[int],
+                      out_hw: Sequence[int], spatial_scales: Sequence[float], sampling_ratio: int,
+                      aligned: bool, channels_last: bool) -> List[Tensor]:
+    """Multi-level, multi-bucket RoIAlign forward.
+
+    ``counts[b]`` RoIs of bucket b (host ints), pooled size ``out_hw[2b:2b+2]``.  Returns one
+    ``[counts[b], C, h, w]`` tensor per bucket (NCHW-contiguous, or channels_last on request).
+    """
+    nb = len(counts)
+    if len(out_hw) != 2 * nb or len(spatial_scales) != len(feats):
+        raise ValueError('inconsistent bucket / level arguments')
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError('rois must be [K,5]')
+    rois = _f32c(rois, 'rois').contiguous()
+    dev = rois.device
+    K = rois.size(0)
+    C = feats[0].size(1)
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    outs = [torch.empty((int(counts[b]), C, int(out_hw[2 * b]), int(out_hw[2 * b + 1])),
+                        dtype=torch.float32, device=dev, memory_format=fmt) for b in range(nb)]
+    if K == 0:
+        return outs
+    L, fptrs, fshapes, fstrides = _level_arrays(feats)
+    optrs, ohw, ostrides = _bucket_arrays(outs, out_hw)
+    scales = _arr(ctypes.c_float, [float(s) for s in spatial_scales])
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_roi_align_fwd(fptrs, fshapes, fstrides, scales, L, _ptr(rois), K,
+                                          _ptr(lvl), _ptr(perm), _ptr(seg), nb, ohw, optrs,
+                                          ostrides, int(sampling_ratio), int(bool(aligned)),
+                                          _stream(dev))
+    _lib.check(rc, 'dm_roi_align_fwd')
+    return outs
+
+
+@roi_align_forward.register_fake
+def _(feats, rois, lvl, perm, seg, counts, out_hw, spatial_scales, sampling_ratio, aligned,
+      channels_last):
+    C = feats[0].size(1)
+    return [torch.empty((counts[b], C, out_hw[2 * b], out_hw[2 * b + 1]), dtype=torch.float32,
+                        device=rois.device) for b in range(len(counts))]
+
+
+@torch.library.custom_op('dynamask::roi_align_backward', mutates_args=(), device_types='cuda')
+def roi_align_backward(grad_outs: Sequence[Tensor], rois: Tensor, lvl: Optional[Tensor],
+                       perm: Optional[Tensor], seg: Optional[Tensor],
+                       feat_shapes: Sequence[int], feat_channels_last: Sequence[bool],
+                       out_hw: Sequence[int], spatial_scales: Sequence[float], sampling_ratio: int,
+                       aligned: bool) -> List[Tensor]:
+    """Gradient w.r.t. every level's feature map (zero-initialised here, then reduced into)."""
+    nb = len(grad_outs)
+    L = len(spatial_scales)
+    dev = rois.device
+    rois = _f32c(rois, 'rois').contiguous()
+    K = rois.size(0)
+    grads = []
+    for l in range(L):
+        shp = [int(v) for v in feat_shapes[4 * l:4 * l + 4]]
+        fmt = torch.channels_last if feat_channels_last[l] else torch.contiguous_format
+        grads.append(torch.empty(shp, dtype=torch.float32, device=dev, memory_format=fmt))
+    gos = [_f32c(g, 'grad_out') for g in grad_outs]
+    _, gptrs, gshapes, gstrides = _level_arrays(grads)
+    optrs, ohw, ostrides = _bucket_arrays(gos, out_hw)
+    scales = _arr(ctypes.c_float, [float(s) for s in spatial_scales])
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_roi_align_bwd(gptrs, gshapes, gstrides, scales, L, _ptr(rois), K,
+                                          _ptr(lvl), _ptr(perm), _ptr(seg), nb, ohw, optrs,
+                                          ostrides, int(sampling_ratio), int(bool(aligned)), 1,
+                                          _stream(dev))
+    _lib.check(rc, 'dm_roi_align_bwd')
+    return grads
+
+
+@roi_align_backward.register_fake
+def _(grad_outs, rois, lvl, perm, seg, feat_shapes, feat_channels_last, out_hw, spatial_scales,
+      sampling_ratio, aligned):
+    L = len(spatial_scales)
+    return [torch.empty([int(v) for v in feat_shapes[4 * l:4 * l + 4]], dtype=torch.float32,
+                        device=rois.device) for l in range(L)]
+
+
+def _ra_setup_context(ctx, inputs, output):
+    (feats, rois, lvl, perm, seg, counts, out_hw, spatial_scales, sampling_ratio, aligned,
+     channels_last) = inputs
+    ctx.save_for_backward(rois, *[t for t in (lvl, perm, seg) if t is not None])
+    ctx.has = (lvl is not None, perm is not None, seg is not None)
+    ctx.feat_shapes = [int(v) for f in feats for v in f.shape]
+    ctx.feat_cl = [bool(f.dim() == 4 and not f.is_contiguous()
+                        and f.is_contiguous(memory_format=torch.channels_last)) for f in feats]
+    ctx.n_feats = len(feats)
+    ctx.counts = list(counts)
+    ctx.out_hw = list(out_hw)
+    ctx.scales = list(spatial_scales)
+    ctx.sr = sampling_ratio
+    ctx.aligned = aligned
+    ctx.needs = [f.requires_grad for f in feats]
+
+
+def _ra_backward(ctx, grad_outs):
+    saved = list(ctx.saved_tensors)
+    rois = saved.pop(0)
+    lvl = saved.pop(0) if ctx.has[0] else None
+    perm = saved.pop(0) if ctx.has[1] else None
+    seg = saved.pop(0) if ctx.has[2] else None
+    C = ctx.feat_shapes[1]
+    gos = []
+    for b, g in enumerate(grad_outs):
+        if g is None:
+            g = torch.zeros((ctx.counts[b], C, ctx.out_hw[2 * b], ctx.out_hw[2 * b + 1]),
+                            dtype=torch.float32, device=rois.device)
+        gos.append(g)
+    grads = roi_align_backward(gos, rois, lvl, perm, seg, ctx.feat_shapes, ctx.feat_cl,
+                               ctx.out_hw, ctx.scales, ctx.sr, ctx.aligned)
+    grads = [g if need else None for g, need in zip(grads, ctx.needs)]
+    return (grads, None, None, None, None, None, None, None, None, None, None)
+
+
+roi_align_forward.register_autograd(_ra_backward, setup_context=_ra_setup_context)
+
+
+def multilevel_roi_align(feats, rois, out_sizes, spatial_scales, lvl=None, perm=None, seg=None,
+                         counts=None, sampling_ratio=0, aligned=True, channels_last=False):
+    """Convenience wrapper: ``out_sizes`` is a list of (h, w) per bucket."""
+    out_hw = [int(v) for hw in out_sizes for v in hw]
+    if counts is None:
+        if len(out_sizes) != 1:
+            raise ValueError('counts is required with more than one bucket')
+        counts = [rois.size(0)]
+    return roi_align_forward(list(feats), rois, lvl, perm, seg, [int(c) for c in counts], out_hw,
+                             [float(s) for s in spatial_scales], int(sampling_ratio),
+                             bool(aligned), bool(channels_last))
+
+
+# --------------------------------------------------------------------------------------------
+# dm_paste_masks
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op('dynamask::paste_masks', mutates_args=(), device_types='cuda')
+def paste_masks(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,
+                region: Sequence[int], apply_sigmoid: bool, thr: float, mode: int) -> Tensor:
+    """masks [N,C,S_h,S_w] fp32, boxes [N,4]; region = (x_lo, y_lo, x_hi, y_hi).
+
+    mode 0 -> bool [N,h,w] (value >= thr); 1 -> uint8 (value*255); 2 -> float32 raw value."""
+    if masks.dim() != 4:
+        raise ValueError('masks must be [N,C,S_h,S_w]')
+    masks = _f32c(masks, 'masks')
+    if masks.stride(3) != 1 or masks.stride(2) != masks.size(3):
+        masks = masks.contiguous()
+    N, _, sh, sw = masks.shape
+    dev = masks.device
+    boxes = _f32c(boxes, 'boxes')[:, :4].contiguous()
+    if boxes.size(0) != N:
+        raise ValueError('boxes must be [N,4]')
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    x_lo, y_lo, x_hi, y_hi = [int(v) for v in region]
+    dt = {PASTE_BOOL: torch.bool, PASTE_U8: torch.uint8, PASTE_F32: torch.float32}[mode]
+    out = torch.empty((N, y_hi - y_lo, x_hi - x_lo), dtype=dt, device=dev)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_paste_masks(_ptr(masks), masks.stride(0), masks.stride(1),
+                                        _ptr(labels), N, sh, sw, int(bool(apply_sigmoid)),
+                                        _ptr(boxes), int(img_h), int(img_w), x_lo, y_lo, x_hi,
+                                        y_hi, float(thr), int(mode), _ptr(out), _stream(dev))
+    _lib.check(rc, 'dm_paste_masks')
+    return out
+
+
+@paste_masks.register_fake
+def _(masks, boxes, labels, img_h, img_w, region, apply_sigmoid, thr, mode):
+    dt = {PASTE_BOOL: torch.bool, PASTE_U8: torch.uint8, PASTE_F32: torch.float32}[mode]
+    return torch.empty((masks.size(0), region[3] - region[1], region[2] - region[0]), dtype=dt,
+                       device=masks.device)
+
+
+# --------------------------------------------------------------------------------------------
+# dm_mask_target
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op('dynamask::mask_target', mutates_args=(), device_types='cuda')
+def mask_target(gt_blob: Tensor, img_offsets: Tensor, img_ghw: Tensor, boxes: Tensor,
+                inds: Tensor, roi_img: Optional[Tensor], clip: bool,
+                sizes_hw: Sequence[int]) -> List[Tensor]:
+    """gt_blob uint8 (all images' [G,H,W] bitmaps back to back); -> one [K,h,w] fp32 per size."""
+    if gt_blob.dtype != torch.uint8:
+        raise TypeError('gt_blob must be uint8')
+    dev = boxes.device
+    boxes = _f32c(boxes, 'boxes')[:, :4].contiguous()
+    K = boxes.size(0)
+    inds = inds.to(torch.int64).contiguous()
+    n_sizes = len(sizes_hw) // 2
+    outs = [torch.empty((K, int(sizes_hw[2 * s]), int(sizes_hw[2 * s + 1])), dtype=torch.float32,
+                        device=dev) for s in range(n_sizes)]
+    if K == 0:
+        return outs
+    B = img_offsets.numel()
+    if img_offsets.dtype != torch.int64 or img_ghw.dtype != torch.int32:
+        raise TypeError('img_offsets must be int64 and img_ghw int32')
+    if roi_img is not None and roi_img.dtype != torch.int32:
+        raise TypeError('roi_img must be int32')
+    optrs = _arr(ctypes.c_void_p, [o.data_ptr() for o in outs])
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_mask_target(_ptr(gt_blob), _ptr(img_offsets), _ptr(img_ghw), B,
+                                        _ptr(boxes), _ptr(inds), _ptr(roi_img), K, int(bool(clip)),
+                                        _arr(ctypes.c_int32, [int(v) for v in sizes_hw]), n_sizes,
+                                        optrs, _stream(dev))
+    _lib.check(rc, 'dm_mask_target')
+    return outs
+
+
+@mask_target.register_fake
+def _(gt_blob, img_offsets, img_ghw, boxes, inds, roi_img, clip, sizes_hw):
+    K = boxes.size(0)
+    return [torch.empty((K, sizes_hw[2 * s], sizes_hw[2 * s + 1]), dtype=torch.float32,
+                        device=boxes.device) for s in range(len(sizes_hw) // 2)]

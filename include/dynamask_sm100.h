@@ -1,0 +1,143 @@
+/*
+ * dynamask_sm100.h -- C ABI of libdynamask_sm100.so, the B200 (sm_100a) implementation of the
+ * DynaMask per-instance mask hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device
+ * pointers, sizes and a CUDA stream; no torch / ATen types cross it.  The library owns no
+ * memory and holds no mutable global state: every buffer (inputs, outputs, scratch) belongs to
+ * the caller, every call is asynchronous on `stream` and re-entrant across streams.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree, lslrh/DynaMask):
+ *   dm_assign          <- SingleRoIExtractor.map_roi_levels
+ *                           mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:32-51
+ *                         + argmax of the mask-switch one-hot,
+ *                           mmdet/models/roi_heads/dynamask_roi_head.py:84-114 (use at :197-203)
+ *   dm_roi_align_fwd   <- mmcv._ext.roi_align_forward as reached from
+ *                           mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:52-54 and the
+ *                           per-level select/scatter loop single_level_roi_extractor.py:53-81
+ *   dm_roi_align_bwd   <- mmcv._ext.roi_align_backward (autograd of the above)
+ *   dm_paste_masks     <- _do_paste_mask, mmdet/models/roi_heads/mask_heads/fcn_mask_head.py:240-308
+ *                         + sigmoid / class select / threshold of DynaMaskHead.get_seg_masks,
+ *                           mmdet/models/roi_heads/mask_heads/dynamask_head.py:279-342
+ *   dm_mask_target     <- BitmapMasks.crop_and_resize, mmdet/core/mask/structures.py:256-286
+ *                         + clip of mask_target_single, mmdet/core/mask/mask_target.py:49-51
+ *                         + the four-size loop of DynaMaskHead.get_targets, dynamask_head.py:246-271
+ *
+ * All functions return DM_OK (0) or a negative DM_E* code and never throw.
+ */
+#ifndef DYNAMASK_SM100_H_
+#define DYNAMASK_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_MAX_LEVELS 8
+#define DM_MAX_BUCKETS 8
+
+#define DM_OK 0
+#define DM_EINVAL (-1)       /* bad argument (null pointer, size, stride) */
+#define DM_ECUDA (-2)        /* a CUDA runtime call or launch failed; see dm_last_cuda_error() */
+#define DM_EUNSUPPORTED (-3) /* valid request this build does not implement */
+
+/* output modes of dm_paste_masks */
+#define DM_PASTE_BOOL 0  /* uint8 {0,1}: (value >= thr) */
+#define DM_PASTE_U8 1    /* uint8: (uint8)(value * 255)  (reference thr < 0 branch) */
+#define DM_PASTE_F32 2   /* float: raw interpolated value (the _do_paste_mask return) */
+
+typedef void* dm_stream_t; /* cudaStream_t */
+
+int dm_version(void);
+const char* dm_error_string(int code);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char* dm_last_cuda_error(void);
+/* Number of kernels launched by this library from the calling process so far. */
+int64_t dm_launch_count(void);
+
+/*
+ * Stage 1: per-RoI FPN level + resolution bucket + stable grouping by bucket.
+ *   rois        device [K,5] fp32 (batch_idx, x1, y1, x2, y2), row stride 5
+ *   onehot      device [K,num_buckets] fp32 mask-switch output, or NULL (every RoI -> bucket 0)
+ *   lvl         device [K] int32 out: clamp(floor(log2(sqrt(w*h)/finest_scale + 1e-6)), 0, L-1);
+ *               -1 when the expression is NaN (negative area: the reference matches no level)
+ *   bucket      device [K] int32 out: first argmax of the one-hot row
+ *   perm        device [K] int32 out: RoI indices grouped by bucket, original order inside a bucket
+ *   seg_offsets device [num_buckets+1] int32 out: bucket b owns perm[seg[b] .. seg[b+1])
+ * Any of lvl / bucket / perm / seg_offsets may be NULL when not wanted (perm and seg_offsets
+ * must be given together).  One single-CTA launch, no host synchronisation.
+ */
+int dm_assign(const float* rois, int K, const float* onehot, int num_buckets, int num_levels,
+              float finest_scale, int32_t* lvl, int32_t* bucket, int32_t* perm,
+              int32_t* seg_offsets, dm_stream_t stream);
+
+/*
+ * Stage 2 forward: aligned / avg-pool multi-level RoIAlign, all buckets in one persistent launch.
+ *   feat_ptrs      host array [L] of device pointers, one fp32 map per FPN level
+ *   feat_shapes    host [L*4]  (N, C, H, W) per level (C equal on all levels)
+ *   feat_strides   host [L*4]  element strides (n, c, h, w) per level; any layout
+ *   spatial_scales host [L]    1 / stride
+ *   rois           device [K,5]
+ *   lvl            device [K] int32 from dm_assign, or NULL (every RoI reads level 0)
+ *   perm, seg_offsets  device, from dm_assign, or both NULL (one bucket holding RoIs 0..K-1)
+ *   out_hw         host [num_buckets*2] pooled (h, w) of each bucket
+ *   out_ptrs       host [num_buckets] device pointers, bucket b is [seg[b+1]-seg[b], C, h, w]
+ *   out_strides    host [num_buckets*4] element strides (n, c, h, w) of each bucket's output
+ *   sampling_ratio 0 = adaptive ceil(roi_size / out_size);  aligned 1 = half-pixel shift
+ * Every output element of every listed RoI is written (zeros where the reference yields zeros).
+ */
+int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* feat_shapes,
+                     const int64_t* feat_strides, const float* spatial_scales, int num_levels,
+                     const float* rois, int K, const int32_t* lvl, const int32_t* perm,
+                     const int32_t* seg_offsets, int num_buckets, const int32_t* out_hw,
+                     float* const* out_ptrs, const int64_t* out_strides, int sampling_ratio,
+                     int aligned, dm_stream_t stream);
+
+/*
+ * Stage 2 backward: scatters grad_out of every bucket into the per-level gradient maps.
+ * Arguments mirror dm_roi_align_fwd.  zero_init != 0 clears every grad map first (the maps must
+ * then be dense: each level's storage is the N*C*H*W elements its strides span).
+ */
+int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* feat_shapes,
+                     const int64_t* feat_strides, const float* spatial_scales, int num_levels,
+                     const float* rois, int K, const int32_t* lvl, const int32_t* perm,
+                     const int32_t* seg_offsets, int num_buckets, const int32_t* out_hw,
+                     const float* const* grad_out_ptrs, const int64_t* grad_out_strides,
+                     int sampling_ratio, int aligned, int zero_init, dm_stream_t stream);
+
+/*
+ * Stage 3: paste N instance masks into image canvases, fused sigmoid + bilinear + threshold.
+ *   masks          device fp32; instance n, class c plane at masks + n*stride_n + c*stride_c, [S_h,S_w] dense
+ *   labels         device [N] int64 class per instance, or NULL (class 0)
+ *   apply_sigmoid  1: masks hold logits;  0: masks hold probabilities
+ *   boxes          device [N,4] fp32 xyxy in canvas pixels
+ *   region         paste window [y_lo,y_hi) x [x_lo,x_hi) of the img_h x img_w canvas
+ *   out            device [N, y_hi-y_lo, x_hi-x_lo] dense; element type per out_mode
+ */
+int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                   const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                   const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                   int y_hi, float thr, int out_mode, void* out, dm_stream_t stream);
+
+/*
+ * Stage 4: training mask targets for every positive RoI of a batch at several sizes, one launch.
+ *   gt_blob      device uint8: the ground-truth bitmaps of all images, image b at gt_blob + img_offsets[b],
+ *                laid out [G_b, H_b, W_b] dense
+ *   img_offsets  device [B] int64 byte offsets;  img_ghw device [B*3] int32 (G_b, H_b, W_b)
+ *   boxes        device [K,4] fp32 xyxy in image pixels; inds device [K] int64 assigned gt index
+ *   roi_img      device [K] int32 image of each RoI, or NULL (all image 0)
+ *   clip         1: clip x to [0,W_b], y to [0,H_b] first (mask_target_single); 0: as given
+ *   sizes_hw     host [n_sizes*2]; out_ptrs host [n_sizes] device pointers, each [K, h, w] fp32 in {0,1}
+ * Bit-exact with the reference's fp32 operation order (no FMA contraction, serial accumulation).
+ */
+int dm_mask_target(const uint8_t* gt_blob, const int64_t* img_offsets, const int32_t* img_ghw,
+                   int B, const float* boxes, const int64_t* inds, const int32_t* roi_img, int K,
+                   int clip, const int32_t* sizes_hw, int n_sizes, float* const* out_ptrs,
+                   dm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNAMASK_SM100_H_ */

@@ -1,0 +1,447 @@
+"""GPU parity tests: the CUDA path, called through the plugin surface and the C ABI, against the
+CPU oracle on the same seeded inputs.  Bars (BASELINE.json): level / bucket assignment bit-exact,
+RoIAlign forward 1e-5 relative, backward 1e-4, pasted masks >= 99.99 % pixel agreement, mask
+targets bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_RTOL, FWD_ATOL = 1e-5, 1e-5   # 1e-5 relative; atol covers cancellation around zero (|feat| ~ 1)
+BWD_RTOL, BWD_ATOL = 1e-4, 1e-4
+
+
+def dm():
+    import dynamask_b200
+    return dynamask_b200
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def assert_close(a, b, rtol, atol, what):
+    a = a.detach().cpu().float()
+    b = b.detach().cpu().float()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.numel() == 0:
+        return
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bool(bad.any()), '%s: %d / %d outside tolerance, max err %.3e (ref max %.3e)' % (
+        what, int(bad.sum()), a.numel(), float(err.max()), float(b.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------
+# stage 1: level / bucket assignment
+# ------------------------------------------------------------------------------------------
+def test_assign_matches_oracle_on_seeded_rois():
+    g = gen(1234)
+    rois = synth.make_rois(4, 2048, 800, 1344, g)
+    onehot = synth.make_onehot(rois.size(0), g)
+    lvl_o, bucket_o, perm_o, seg_o = O.assign(rois, onehot, 4, 56)
+    lvl, bucket, perm, seg = dm().ops.assign(rois.cuda(), onehot.cuda(), 4, 56.0, 4)
+    assert torch.equal(lvl.cpu().long(), torch.from_numpy(lvl_o))
+    assert torch.equal(bucket.cpu().long(), torch.from_numpy(bucket_o))
+    assert torch.equal(perm.cpu().long(), torch.from_numpy(perm_o))
+    assert torch.equal(seg.cpu().long(), torch.from_numpy(seg_o))
+
+
+def test_assign_levels_match_reference_expression_on_cuda():
+    """Authoritative check for A2: the reference expression evaluated by torch on CUDA tensors,
+    including values a few ulp around every level boundary and degenerate boxes."""
+    vals = []
+    for k in range(0, 6):
+        edge = np.float32(56.0 * 2 ** k)
+        v = edge
+        for _ in range(12):
+            v = np.nextafter(v, np.float32(0), dtype=np.float32)
+        for _ in range(25):
+            vals.append(float(v))
+            v = np.nextafter(v, np.float32(1e9), dtype=np.float32)
+    vals = np.array(vals, np.float32)
+    rois = np.zeros((len(vals) * 3 + 4, 5), np.float32)
+    n = len(vals)
+    rois[:n, 3] = vals; rois[:n, 4] = vals                      # squares of side v
+    rois[n:2 * n, 1] = 3.25; rois[n:2 * n, 2] = 7.5
+    rois[n:2 * n, 3] = 3.25 + vals * 2; rois[n:2 * n, 4] = 7.5 + vals / 2   # 2v x v/2
+    rois[2 * n:3 * n, 3] = vals * vals; rois[2 * n:3 * n, 4] = 1.0         # v^2 x 1
+    rois[3 * n + 0] = (0, 5, 5, 5, 5)         # zero area
+    rois[3 * n + 1] = (0, 5, 5, 4, 9)         # negative width -> NaN level
+    rois[3 * n + 2] = (0, 9, 9, 3, 2)         # both negative -> positive area
+    rois[3 * n + 3] = (0, 0, 0, 1e4, 1e4)     # huge
+    g = gen(7)
+    rnd = synth.make_rois(1, 200000, 800, 1344, g).numpy()
+    rois = np.concatenate([rois, rnd], 0)
+    r = torch.from_numpy(rois).cuda()
+    ref = O.map_roi_levels(r, 4, 56)          # same torch expression, on the CUDA tensor
+    lvl = dm().ops.assign(r, None, 4, 56.0, 1)[0].long()
+    nan = torch.isnan(torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2])))
+    assert int(nan.sum()) == 1
+    assert torch.equal(lvl[~nan], ref[~nan])
+    assert int(lvl[nan][0]) == -1
+    mod = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=0), 8, [4, 8, 16, 32])
+    assert torch.equal(mod.map_roi_levels(r, 4)[~nan], ref[~nan])
+
+
+def test_assign_stable_grouping_many_rois():
+    g = gen(5)
+    K = 5000
+    rois = synth.make_rois(1, K, 800, 1344, g)
+    onehot = synth.make_onehot(K, g, probs=(0.4, 0.3, 0.2, 0.1))
+    _, bucket_o, perm_o, seg_o = O.assign(rois, onehot, 4, 56)
+    _, bucket, perm, seg = dm().ops.assign(rois.cuda(), onehot.cuda(), 4, 56.0, 4)
+    assert torch.equal(perm.cpu().long(), torch.from_numpy(perm_o))
+    assert torch.equal(seg.cpu().long(), torch.from_numpy(seg_o))
+    assert sorted(perm.cpu().tolist()) == list(range(K))
+
+
+# ------------------------------------------------------------------------------------------
+# stage 2: RoIAlign forward
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('out_size', [7, 14, 28, (5, 3), (4, 12)])
+@pytest.mark.parametrize('sampling_ratio', [0, 2])
+def test_roi_align_single_level_matches_oracle(out_size, sampling_ratio):
+    g = gen(11)
+    feat = torch.randn(2, 6, 37, 53, generator=g)
+    K = 40
+    x1 = torch.rand(K, generator=g) * 240 - 20
+    y1 = torch.rand(K, generator=g) * 170 - 20
+    w = torch.rand(K, generator=g) * 150
+    h = torch.rand(K, generator=g) * 110
+    rois = torch.stack([torch.randint(0, 2, (K, ), generator=g).float(), x1, y1, x1 + w, y1 + h], 1)
+    for scale in (0.25, 1.0 / 3):
+        ref = O.roi_align(feat, rois, out_size, scale, sampling_ratio, True)
+        out = dm().roi_align(feat.cuda(), rois.cuda(), out_size, scale, sampling_ratio, 'avg', True)
+        assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'roi_align %s sr=%d' % (str(out_size), sampling_ratio))
+
+
+def test_roi_align_not_aligned_mode():
+    g = gen(12)
+    feat = torch.randn(1, 4, 30, 30, generator=g)
+    rois = torch.tensor([[0, 2.0, 3.0, 2.2, 3.1], [0, 5.0, 5.0, 25.0, 18.0], [0, -4.0, -4.0, 40.0, 40.0]])
+    ref = O.roi_align(feat, rois, 7, 1.0, 2, False)
+    out = dm().roi_align(feat.cuda(), rois.cuda(), 7, 1.0, 2, 'avg', False)
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'aligned=False')
+
+
+def test_roi_align_edge_rois():
+    g = gen(13)
+    feat = torch.randn(2, 5, 25, 42, generator=g)
+    rois = torch.tensor([
+        [0, 10.0, 10.0, 10.0, 10.0],      # zero area
+        [0, 30.0, 30.0, 20.0, 40.0],      # negative width
+        [1, -500.0, -500.0, -300.0, -300.0],  # entirely outside
+        [1, 5000.0, 100.0, 6000.0, 300.0],    # entirely outside (right)
+        [0, -100.0, -100.0, 2000.0, 1500.0],  # covers everything
+        [1, 0.0, 0.0, 1344.0, 800.0],
+        [0, 1300.0, 700.0, 1400.0, 900.0],    # straddles the corner
+        [3, 10.0, 10.0, 100.0, 100.0],        # batch index out of range -> zeros
+    ])
+    ref = O.roi_align(feat, rois, 14, 1 / 32, 0, True)
+    out = dm().roi_align(feat.cuda(), rois.cuda(), 14, 1 / 32, 0, 'avg', True)
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'edge rois')
+    empty = dm().roi_align(feat.cuda(), torch.zeros(0, 5).cuda(), 14, 1 / 32, 0, 'avg', True)
+    assert tuple(empty.shape) == (0, 5, 14, 14)
+
+
+def test_roi_align_huge_bins_take_direct_path():
+    """Whole-map RoI pooled to a tiny output at stride 1: bands do not fit shared memory."""
+    g = gen(14)
+    feat = torch.randn(1, 2, 300, 600, generator=g)
+    rois = torch.tensor([[0, 0.0, 0.0, 600.0, 300.0], [0, 20.0, 10.0, 580.0, 290.0]])
+    ref = O.roi_align(feat, rois, 2, 1.0, 0, True)
+    out = dm().roi_align(feat.cuda(), rois.cuda(), 2, 1.0, 0, 'avg', True)
+    assert_close(out, ref, 1e-4, 1e-5, 'huge bins')   # 45 000 samples per bin: looser sum order tolerance
+    fcuda = feat.cuda().requires_grad_()
+    o = dm().roi_align(fcuda, rois.cuda(), 2, 1.0, 0, 'avg', True)
+    go = torch.randn(o.shape, generator=g)
+    o.backward(go.cuda())
+    gref = O.roi_align_backward(go, rois, feat.shape, 1.0, 0, True)
+    assert_close(fcuda.grad, gref, BWD_RTOL, BWD_ATOL, 'huge bins bwd')
+
+
+def test_roi_align_tall_roi_is_tiled():
+    """Single-level stride-4 extractor on a big RoI (the 56x56 semantic extractor case)."""
+    g = gen(15)
+    feat = torch.randn(1, 3, 200, 336, generator=g)
+    rois = torch.tensor([[0, 4.0, 4.0, 1330.0, 790.0], [0, 100.0, 50.0, 700.0, 780.0]])
+    for p in (56, 112):
+        ref = O.roi_align(feat, rois, p, 0.25, 0, True)
+        out = dm().roi_align(feat.cuda(), rois.cuda(), p, 0.25, 0, 'avg', True)
+        assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'tall roi P=%d' % p)
+
+
+def _c2_like(batch, per_img, channels, seed):
+    g = gen(seed)
+    feats = synth.make_features(batch, channels, 800, 1344, g)
+    rois = synth.make_rois(batch, per_img, 800, 1344, g)
+    return feats, rois, g
+
+
+@pytest.mark.parametrize('out_size', [7, 14])
+def test_single_roi_extractor_matches_oracle(out_size):
+    feats, rois, _ = _c2_like(2, 64, 16, 21)
+    ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=out_size, sampling_ratio=0), 16,
+                                  [4, 8, 16, 32])
+    out = ext([f.cuda() for f in feats], rois.cuda())
+    ref = O.single_roi_extractor(feats, rois, out_size, [4, 8, 16, 32])
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'SingleRoIExtractor')
+    out2 = ext([f.cuda() for f in feats], rois.cuda(), roi_scale_factor=1.3)
+    ref2 = O.single_roi_extractor(feats, rois, out_size, [4, 8, 16, 32], roi_scale_factor=1.3)
+    assert_close(out2, ref2, FWD_RTOL, FWD_ATOL, 'SingleRoIExtractor rescaled')
+
+
+def test_single_level_extractor_56():
+    feats, rois, _ = _c2_like(1, 24, 8, 22)
+    ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=56, sampling_ratio=0), 8, [4])
+    out = ext([feats[0].cuda()], rois.cuda())
+    ref = O.single_roi_extractor([feats[0]], rois, 56, [4])
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'semantic extractor')
+    assert ext([feats[0].cuda()], rois[:0].cuda()).shape == (0, 8, 56, 56)
+
+
+def test_extractor_fp16_guard():
+    feats, rois, _ = _c2_like(1, 16, 8, 23)
+    ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=0), 8, [4, 8, 16, 32])
+    ext.fp16_enabled = True
+    out = ext([f.cuda().half() for f in feats], rois.cuda())
+    assert out.dtype == torch.float16
+    ref = O.single_roi_extractor([f.half().float() for f in feats], rois, 7, [4, 8, 16, 32])
+    assert_close(out.float(), ref, 2e-3, 2e-3, 'fp16 guard')
+
+
+@pytest.mark.parametrize('channels_last_in', [False, True])
+def test_bucketed_extractor_matches_oracle(channels_last_in):
+    feats, rois, g = _c2_like(2, 48, 8, 24)
+    onehot = synth.make_onehot(rois.size(0), g)
+    ext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 8,
+                                    [4, 8, 16, 32])
+    fc = [f.cuda() for f in feats]
+    if channels_last_in:
+        fc = [f.contiguous(memory_format=torch.channels_last) for f in fc]
+    res = ext.forward_bucketed(fc, rois.cuda(), onehot.cuda())
+    refs, perm_o, seg_o = O.bucketed_extract(feats, rois, onehot, (14, 28, 56, 112), [4, 8, 16, 32])
+    assert torch.equal(res.perm.cpu().long(), torch.from_numpy(perm_o))
+    assert res.counts == [int(seg_o[i + 1] - seg_o[i]) for i in range(4)]
+    for b in range(4):
+        assert_close(res.feats[b], refs[b], FWD_RTOL, FWD_ATOL, 'bucket %d' % b)
+
+
+def test_bucketed_extractor_channels_last_output_and_empty_bucket():
+    feats, rois, g = _c2_like(1, 20, 8, 25)
+    onehot = torch.zeros(20, 4)
+    onehot[:, 1] = 1
+    onehot[3, 1] = 0
+    onehot[3, 3] = 1
+    ext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 8,
+                                    [4, 8, 16, 32])
+    res = ext.forward_bucketed([f.cuda() for f in feats], rois.cuda(), onehot.cuda(), channels_last=True)
+    refs, _, _ = O.bucketed_extract(feats, rois, onehot, (14, 28, 56, 112), [4, 8, 16, 32])
+    assert res.counts == [0, 19, 0, 1]
+    for b in range(4):
+        assert_close(res.feats[b], refs[b], FWD_RTOL, FWD_ATOL, 'cl bucket %d' % b)
+
+
+# ------------------------------------------------------------------------------------------
+# stage 2: RoIAlign backward
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('out_size', [7, 14, 28])
+def test_extractor_backward_matches_oracle(out_size):
+    feats, rois, g = _c2_like(2, 40, 8, 31)
+    ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=out_size, sampling_ratio=0), 8,
+                                  [4, 8, 16, 32])
+    fc = [f.cuda().requires_grad_() for f in feats]
+    out = ext(fc, rois.cuda())
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go.cuda())
+    refs = O.single_roi_extractor_backward(go, [f.shape for f in feats], rois, [4, 8, 16, 32])
+    for l in range(4):
+        assert_close(fc[l].grad, refs[l], BWD_RTOL, BWD_ATOL, 'grad level %d' % l)
+
+
+def test_bucketed_backward_matches_oracle():
+    feats, rois, g = _c2_like(1, 24, 4, 32)
+    onehot = synth.make_onehot(rois.size(0), g)
+    ext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 4,
+                                    [4, 8, 16, 32])
+    fc = [f.cuda().requires_grad_() for f in feats]
+    res = ext.forward_bucketed(fc, rois.cuda(), onehot.cuda())
+    gos = [torch.randn(o.shape, generator=g) for o in res.feats]
+    torch.autograd.backward(res.feats, [x.cuda() for x in gos])
+    _, _, perm, seg = O.assign(rois, onehot, 4, 56)
+    acc = [torch.zeros_like(f) for f in feats]
+    for b, p in enumerate((14, 28, 56, 112)):
+        idx = torch.from_numpy(perm[seg[b]:seg[b + 1]])
+        gs = O.single_roi_extractor_backward(gos[b], [f.shape for f in feats], rois[idx], [4, 8, 16, 32])
+        for l in range(4):
+            acc[l] += gs[l]
+    for l in range(4):
+        assert_close(fc[l].grad, acc[l], BWD_RTOL, 2e-4, 'bucketed grad level %d' % l)
+
+
+def test_roi_align_backward_sampling_ratio_and_odd_sizes():
+    g = gen(33)
+    feat = torch.randn(2, 3, 37, 53, generator=g)
+    K = 20
+    x1 = torch.rand(K, generator=g) * 200 - 10
+    y1 = torch.rand(K, generator=g) * 140 - 10
+    rois = torch.stack([torch.randint(0, 2, (K, ), generator=g).float(), x1, y1,
+                        x1 + torch.rand(K, generator=g) * 150, y1 + torch.rand(K, generator=g) * 100], 1)
+    for out_size, sr in (((5, 3), 0), (7, 2), ((4, 12), 3)):
+        fcuda = feat.cuda().requires_grad_()
+        o = dm().roi_align(fcuda, rois.cuda(), out_size, 0.25, sr, 'avg', True)
+        go = torch.randn(o.shape, generator=g)
+        o.backward(go.cuda())
+        ref = O.roi_align_backward(go, rois, feat.shape, 0.25, sr, True)
+        assert_close(fcuda.grad, ref, BWD_RTOL, BWD_ATOL, 'bwd %s sr=%d' % (str(out_size), sr))
+
+
+# ------------------------------------------------------------------------------------------
+# stage 3: paste
+# ------------------------------------------------------------------------------------------
+class _Cfg:
+    def __init__(self, thr):
+        self.mask_thr_binary = thr
+
+
+def _dets(n, img_h, img_w, seed):
+    g = gen(seed)
+    boxes = synth.make_boxes(n, img_h, img_w, g, s_lo=8, s_hi=500)
+    logits = synth.make_mask_logits(n, 112, g)
+    return logits, boxes
+
+
+@pytest.mark.parametrize('shape', [(800, 1333), (427, 640)])
+def test_get_seg_masks_pixel_agreement(shape):
+    img_h, img_w = shape
+    logits, boxes = _dets(30, img_h, img_w, 41)
+    det = torch.cat([boxes, torch.ones(30, 1)], 1)
+    labels = torch.zeros(30, dtype=torch.long)
+    ref = O.get_seg_masks(logits, det, labels, 0.5, (img_h, img_w, 3), 1.0, False)
+    out = dm().get_seg_masks(logits.cuda(), det.cuda(), labels.cuda(), _Cfg(0.5), (img_h, img_w, 3), 1.0, False)
+    assert len(out) == 30 and out[0].dtype == np.bool_ and out[0].shape == (img_h, img_w)
+    agree = sum(int((a == b).sum()) for a, b in zip(out, ref))
+    total = 30 * img_h * img_w
+    assert agree / total >= 0.9999, agree / total
+    assert sum(int(a.sum()) for a in out) > 0
+
+
+def test_get_seg_masks_rescale_and_multiclass():
+    img_h, img_w = 480, 640
+    logits, boxes = _dets(12, int(img_h * 1.6), int(img_w * 1.6), 42)
+    logits = torch.cat([logits, -logits, logits * 0.5], 1)          # 3 classes
+    labels = torch.tensor([0, 1, 2] * 4)
+    det = torch.cat([boxes, torch.ones(12, 1)], 1)
+    sf = np.array([1.6, 1.6, 1.6, 1.6], np.float32)
+    ref = O.get_seg_masks(logits, det, labels, 0.5, (img_h, img_w, 3), sf, True)
+    out = dm().get_seg_masks(logits.cuda(), det.cuda(), labels.cuda(), _Cfg(0.5), (img_h, img_w, 3), sf, True)
+    agree = sum(int((a == b).sum()) for a, b in zip(out, ref))
+    assert agree / (12 * img_h * img_w) >= 0.9999
+    # rescale=False with a float scale factor: canvas = round(ori * sf)
+    ref2 = O.get_seg_masks(logits[:, :1], det, labels, 0.5, (img_h, img_w, 3), 1.6, False)
+    out2 = dm().get_seg_masks(logits[:, :1].cuda(), det.cuda(), labels.cuda(), _Cfg(0.5), (img_h, img_w, 3), 1.6, False)
+    assert out2[0].shape == ref2[0].shape == (768, 1024)
+    agree = sum(int((a == b).sum()) for a, b in zip(out2, ref2))
+    assert agree / (12 * 768 * 1024) >= 0.9999
+
+
+def test_get_seg_masks_uint8_mode():
+    logits, boxes = _dets(6, 200, 300, 43)
+    det = torch.cat([boxes, torch.ones(6, 1)], 1)
+    labels = torch.zeros(6, dtype=torch.long)
+    ref = O.get_seg_masks(logits, det, labels, -1, (200, 300, 3), 1.0, False)
+    out = dm().get_seg_masks(logits.cuda(), det.cuda(), labels.cuda(), _Cfg(-1), (200, 300, 3), 1.0, False)
+    assert out[0].dtype == np.uint8
+    diff = np.abs(np.stack(out).astype(np.int32) - np.stack(ref).astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize('skip_empty', [True, False])
+def test_do_paste_mask_values(skip_empty):
+    logits, boxes = _dets(9, 300, 420, 44)
+    boxes[3] = torch.tensor([50.5, 20.0, 50.5, 90.0])       # x1 == x0: the inf -> 0 branch
+    boxes[4] = torch.tensor([-30.0, -20.0, 60.0, 50.0])     # partly outside
+    prob = logits.sigmoid()
+    ref, sl_ref = O.do_paste_mask(prob, boxes, 300, 420, skip_empty=skip_empty)
+    out, sl = dm()._do_paste_mask(prob.cuda(), boxes.cuda(), 300, 420, skip_empty=skip_empty)
+    assert sl == sl_ref
+    out = out.cpu()
+    assert out.shape == ref.shape
+    ok = ~(torch.isnan(ref) | torch.isnan(out))
+    assert float((out[ok] - ref[ok]).abs().max()) < 1e-5
+    assert float(ok.float().mean()) > 0.999
+
+
+# ------------------------------------------------------------------------------------------
+# stage 4: mask targets
+# ------------------------------------------------------------------------------------------
+def _target_case(seed, img_h, img_w, g_n, k):
+    rng = np.random.default_rng(seed)
+    masks = synth.make_gt_masks(g_n, img_h, img_w, rng)
+    boxes, inds = synth.jitter_boxes_from_masks(masks, k, rng)
+    return masks, boxes, inds
+
+
+def test_mask_targets_bit_exact_four_sizes():
+    masks, boxes, inds = _target_case(51, 320, 480, 7, 48)
+    boxes[0] = (-20, -10, 500, 340)         # clipped to the canvas
+    boxes[1] = (10, 10, 10, 10)             # empty box
+    boxes[2] = (0, 0, 480, 320)             # whole image: up to 35x23 samples per bin at S=14
+    bm = dm().BitmapMasks(masks, 320, 480)
+    out = dm().multi_size_mask_targets([torch.from_numpy(boxes).cuda()], [torch.from_numpy(inds).cuda()], [bm])
+    ref = O.dyna_get_targets([boxes], [inds], [masks])
+    for s in range(4):
+        assert out[s].dtype == torch.float32
+        assert torch.equal(out[s].cpu(), ref[s]), 'size %d: %d mismatches' % (
+            s, int((out[s].cpu() != ref[s]).sum()))
+
+
+def test_mask_target_batch_of_images_and_empty_image():
+    cases = [_target_case(52, 200, 304, 5, 20), _target_case(53, 256, 256, 3, 0), _target_case(54, 160, 240, 9, 33)]
+    props = [torch.from_numpy(c[1]).cuda() for c in cases]
+    inds = [torch.from_numpy(c[2]).cuda() for c in cases]
+    bms = [dm().BitmapMasks(c[0], c[0].shape[1], c[0].shape[2]) for c in cases]
+
+    class Cfg:
+        mask_size = 28
+    out = dm().mask_target(props, inds, bms, Cfg)
+    ref = O.mask_target([c[1] for c in cases], [c[2] for c in cases], [c[0] for c in cases], 28)
+    assert torch.equal(out.cpu(), ref)
+    single = dm().mask_target_single(props[1], inds[1], bms[1], Cfg)
+    assert tuple(single.shape) == (0, 28, 28)
+
+
+def test_bitmapmasks_crop_and_resize_matches_oracle():
+    masks, boxes, inds = _target_case(55, 96, 128, 4, 17)
+    bm = dm().BitmapMasks(masks, 96, 128)
+    res = bm.crop_and_resize(boxes, (56, 56), inds, device='cuda')
+    assert isinstance(res, dm().BitmapMasks) and res.masks.dtype == np.bool_
+    assert res.height == 56 and res.width == 56 and len(res) == 17
+    ref = O.crop_and_resize(masks, boxes, (56, 56), inds)
+    assert np.array_equal(res.masks, ref)
+    empty = dm().BitmapMasks(np.zeros((0, 96, 128), np.uint8), 96, 128)
+    e = empty.crop_and_resize(boxes, (56, 56), inds, device='cuda')
+    assert len(e) == 0 and e.height == 56
+
+
+def test_mask_targets_exact_half_ties():
+    """Axis-aligned rectangles produce averages of exactly 0.5; the >= must go the oracle's way."""
+    masks = np.zeros((2, 64, 64), np.uint8)
+    masks[0, 16:48, 16:48] = 1
+    masks[1, :, 32:] = 1
+    boxes = np.array([[0, 0, 64, 64], [16, 16, 48, 48], [8, 8, 40, 40], [0, 0, 32, 64], [15.5, 15.5, 47.5, 47.5],
+                      [16, 0, 48, 64]], np.float32)
+    inds = np.array([0, 0, 0, 1, 0, 1], np.int64)
+    bm = dm().BitmapMasks(masks, 64, 64)
+    out = dm().multi_size_mask_targets([torch.from_numpy(boxes).cuda()], [torch.from_numpy(inds).cuda()], [bm])
+    ref = O.dyna_get_targets([boxes], [inds], [masks])
+    for s in range(4):
+        assert torch.equal(out[s].cpu(), ref[s])
