@@ -1,0 +1,506 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DynaMask per-instance mask hot path on B200.
+
+Workload (BASELINE.json configs[1], "C2"): RoIAlign fwd/bwd microbench, 512 RoIs/img x 256 ch x
+4 FPN levels (800x1344 image), mixed 14/28/56/112 outputs, batch 16 per GPU.  One *step* is one
+pass of the hot path over that batch: dm_assign -> dm_roi_align_fwd (all buckets, one launch) ->
+dm_roi_align_bwd (zero-init of the gradient pyramid + one launch).  `value` is RoIs/s with all
+inputs resident in HBM; `e2e` is the same pass through the plugin surface with HOST buffers
+(pinned host -> device copies of the pyramid / RoIs / labels and device -> host copies of the
+pooled features and the gradient pyramid inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); images are sharded by rank, no collective on
+the data path (NCCL only reduces timings / all-gathers checksums).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import synth  # noqa: E402
+
+IMG_H, IMG_W = 800, 1344
+STRIDES = [4, 8, 16, 32]
+BUCKET_SIZES = (14, 28, 56, 112)
+METRIC = 'rois_per_sec_mask_extract_fwd_bwd'
+UNIT = 'RoIs/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU')
+    ap.add_argument('--rois-per-img', type=int, default=512)
+    ap.add_argument('--channels', type=int, default=256)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--e2e-chunk-images', type=int, default=2)
+    ap.add_argument('--cpu-sample-rois', type=int, default=8, help='RoIs per image in the CPU sample')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ----------------------------------------------------------------------------------------------
+# algorithmic bytes
+# ----------------------------------------------------------------------------------------------
+def footprint_pixels(rois, lvl, shapes):
+    """fp_r: feature pixels in each RoI's bilinear footprint at its level, clipped to the map."""
+    r = rois.double()
+    fp = torch.zeros(r.size(0), dtype=torch.float64)
+    for l, (h, w) in enumerate(shapes):
+        s = 1.0 / STRIDES[l]
+        m = lvl == l
+        if not bool(m.any()):
+            continue
+        x_lo = torch.clamp(torch.floor(r[m, 1] * s - 0.5), min=0)
+        x_hi = torch.clamp(torch.floor(r[m, 3] * s - 0.5) + 1, max=w - 1)
+        y_lo = torch.clamp(torch.floor(r[m, 2] * s - 0.5), min=0)
+        y_hi = torch.clamp(torch.floor(r[m, 4] * s - 0.5) + 1, max=h - 1)
+        fp[m] = torch.clamp(x_hi - x_lo + 1, min=0) * torch.clamp(y_hi - y_lo + 1, min=0)
+    return fp
+
+
+def algorithmic_bytes(rois, lvl, bucket, shapes, batch, channels):
+    p2 = torch.tensor([s * s for s in BUCKET_SIZES], dtype=torch.float64)[bucket]
+    fp = footprint_pixels(rois, lvl, shapes)
+    k = rois.size(0)
+    fwd = float((4.0 * channels * (p2 + fp)).sum()) + 20.0 * k
+    pyramid = 4.0 * batch * channels * sum(h * w for h, w in shapes)
+    bwd = float((4.0 * channels * (p2 + 2 * fp)).sum()) + pyramid
+    return fwd, bwd
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)),
+                'power_w_max': float(max(power)), 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU path (oracle port) used by cpu_baseline and --impl reference
+# ----------------------------------------------------------------------------------------------
+def cpu_extract_fwd_bwd(n_images, rois_per_img, channels, seed, threads):
+    """Reference host path on CPU for a bounded sample of C2: per image, the per-level
+    select / RoIAlign / scatter loop (oracle.single_roi_extractor) at the RoI's selected size, plus
+    autograd backward, with torchvision's CPU roi_align as the stand-in for the absent mmcv kernel.
+    Images are sharded over a thread pool (ATen releases the GIL).  Returns (rois, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(seed)
+    work = []
+    for _ in range(n_images):
+        feats = synth.make_features(1, channels, IMG_H, IMG_W, g)
+        rois = synth.make_rois(1, rois_per_img, IMG_H, IMG_W, g)
+        onehot = synth.make_onehot(rois_per_img, g)
+        work.append((feats, rois, onehot))
+
+    def one(item):
+        torch.set_num_threads(1)
+        feats, rois, onehot = item
+        fr = [f.clone().requires_grad_() for f in feats]
+        outs, _, _ = O.bucketed_extract(fr, rois, onehot, BUCKET_SIZES, STRIDES, kernel=O.roi_align_tv)
+        loss = sum((o * o).sum() for o in outs) * 0.5   # grad_out = out, like the GPU step
+        loss.backward()
+        return float(fr[0].grad.abs().sum())
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, work))
+    dt = time.perf_counter() - t0
+    return n_images * rois_per_img, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference is Python + un-vendored mmcv, nothing compiles into oracle/_ref)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 32))
+    n_img = max(1, min(threads, 16))
+    times, nrois = [], 0
+    for i in range(args.warmup + args.steps):
+        n, dt = cpu_extract_fwd_bwd(n_img, args.cpu_sample_rois, args.channels, 1234 + i, threads)
+        if i >= args.warmup:
+            times.append(dt)
+            nrois = n
+        if sum(times) > 150:
+            break
+    steps_done = max(len(times), 1)
+    ms = 1000.0 * sum(times) / steps_done
+    val = nrois / (ms / 1000.0)
+    sample = '%d images x %d RoIs (uniform 14/28/56/112 mix), C=%d, fwd+bwd, thread pool over images' % (
+        n_img, args.cpu_sample_rois, args.channels)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps_done, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        'workload': 'C2 RoIAlign fwd+bwd microbench: %d RoIs/img x %d ch x 4 FPN levels (800x1344), '
+                    'uniform 14/28/56/112 output mix, batch %d per GPU' % (
+                        args.rois_per_img, args.channels, args.batch),
+        'rois_per_step_per_gpu': args.rois_per_img * args.batch,
+        'layout': 'NCHW fp32 in, NCHW fp32 out (reference layout)',
+        'l2': 'no flush needed: each step streams ~75 GB through a 126 MB L2',
+        'sharding': 'by image, no data-path collective',
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    import dynamask_b200 as dm
+    from dynamask_b200 import _lib, ops
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B, C, R = args.batch, args.channels, args.rois_per_img
+    shapes = synth.pyramid_shapes(IMG_H, IMG_W)
+    g = torch.Generator().manual_seed(1234 + rank)
+    gd = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feats = [torch.randn(B, C, h, w, generator=gd, device=dev) for (h, w) in shapes]
+    rois_h = synth.make_rois(B, R, IMG_H, IMG_W, g)
+    onehot_h = synth.make_onehot(rois_h.size(0), g)
+    rois, onehot = rois_h.to(dev), onehot_h.to(dev)
+    K = rois.size(0)
+    scales = [1.0 / s for s in STRIDES]
+    out_hw = [v for s in BUCKET_SIZES for v in (s, s)]
+    feat_shapes = [int(v) for f in feats for v in f.shape]
+
+    # bucket counts are host ints known before the loop (one readback at setup)
+    lvl0, bucket0, _, seg0 = ops.assign(rois, onehot, 4, 56.0, 4)
+    seg_h = seg0.cpu()
+    counts = (seg_h[1:] - seg_h[:-1]).tolist()
+    fwd_bytes, bwd_bytes = algorithmic_bytes(rois_h, lvl0.cpu().long(), bucket0.cpu().long(), shapes, B, C)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks = []
+
+    def step(record):
+        e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None, ) * 4
+        if record:
+            e0.record()
+        lvl, _, perm, seg = ops.assign(rois, onehot, 4, 56.0, 4)
+        if record:
+            e1.record()
+        outs = ops.roi_align_forward(feats, rois, lvl, perm, seg, counts, out_hw, scales, 0, True, False)
+        if record:
+            e2.record()
+        grads = ops.roi_align_backward(outs, rois, lvl, perm, seg, feat_shapes, [False] * 4, out_hw,
+                                       scales, 0, True)
+        if record:
+            e3.record()
+            marks.append((e0, e1, e2, e3))
+        return outs, grads
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        outs, grads = step(False)
+    del outs, grads
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    t_start, t_end = ev(), ev()
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        outs, grads = step(True)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    checksum = float(sum(float(gr.double().sum()) for gr in grads))
+    del outs, grads
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sums = [None] * world
+        dist.all_gather_object(sums, checksum)
+    else:
+        sums = [checksum]
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * K / (ms_per_step / 1000.0)
+
+    asg_ms = float(np.mean([a.elapsed_time(b) for a, b, _, _ in marks]))
+    fwd_ms = float(np.mean([b.elapsed_time(c) for _, b, c, _ in marks]))
+    bwd_ms = float(np.mean([c.elapsed_time(d) for _, _, c, d in marks]))
+    peak, peak_src = peaks()
+    kern = {
+        'dm_roi_align_fwd': {'ms': fwd_ms, 'algorithmic_bytes': fwd_bytes,
+                             'achieved_gbs': fwd_bytes / fwd_ms / 1e6, 'rois_per_s': K / fwd_ms * 1e3},
+        'dm_roi_align_bwd(+zero-init)': {'ms': bwd_ms, 'algorithmic_bytes': bwd_bytes,
+                                        'achieved_gbs': bwd_bytes / bwd_ms / 1e6,
+                                        'rois_per_s': K / bwd_ms * 1e3},
+        'dm_assign': {'ms': asg_ms},
+    }
+    for v in kern.values():
+        if 'achieved_gbs' in v:
+            v['frac_of_measured_peak'] = v['achieved_gbs'] / peak
+            v['frac_of_8TBs_spec'] = v['achieved_gbs'] / 8000.0
+    dom = 'dm_roi_align_bwd(+zero-init)' if bwd_ms >= fwd_ms else 'dm_roi_align_fwd'
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kern[dom]['achieved_gbs'], 'peak': peak,
+                'peak_source': peak_src, 'unit': 'GB/s', 'frac': kern[dom]['achieved_gbs'] / peak,
+                'traffic': None}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
+        'roofline': roofline, 'kernels': kern, 'gpu_launches': int(launches), 'clocks': clocks,
+        'checksums': sums,
+    }
+
+    # ---- extras: the other two kernels on their own configs (rank 0 reports) ------------------
+    if not args.no_extras:
+        line['extras'] = run_extras(dm, ops, dev, rank, peak)
+
+    # ---- e2e: plugin surface with host buffers -------------------------------------------------
+    if not args.no_e2e:
+        e2e = run_e2e(args, dm, dev, rank, world, feats, rois_h, onehot_h, counts)
+        line['e2e'] = e2e
+    del feats
+    torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, 32))
+        n_img = max(1, min(threads, 16))
+        n, dt = cpu_extract_fwd_bwd(n_img, args.cpu_sample_rois, C, 1234, threads)
+        line['cpu_baseline'] = {
+            'value': n / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': '%d images x %d RoIs of the C2 workload (uniform size mix), fwd+bwd, one pass, '
+                      'torchvision CPU roi_align under the reference host loop, thread pool over images' % (
+                          n_img, args.cpu_sample_rois)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_extras(dm, ops, dev, rank, peak):
+    ex = {}
+    g = torch.Generator().manual_seed(99 + rank)
+    # paste: C4 shape per GPU, 8 images x 100 detections pasted into 800x1333 canvases, one launch
+    n = 800
+    logits = synth.make_mask_logits(n, 112, g).to(dev)
+    boxes = synth.make_boxes(n, 800, 1333, g, s_lo=8, s_hi=500).to(dev)
+    for _ in range(3):
+        out = ops.paste_masks(logits, boxes, None, 800, 1333, [0, 0, 1333, 800], True, 0.5, ops.PASTE_BOOL)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    reps = 10
+    for _ in range(reps):
+        out = ops.paste_masks(logits, boxes, None, 800, 1333, [0, 0, 1333, 800], True, 0.5, ops.PASTE_BOOL)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    by = n * 800 * 1333 + 4 * n * 112 * 112 + 16 * n
+    ex['dm_paste_masks'] = {'workload': 'C4 per GPU: 800 instances (8 img x 100 dets), 112x112 -> 800x1333 bool',
+                            'ms': ms, 'instances_per_s': n / ms * 1e3, 'algorithmic_bytes': by,
+                            'achieved_gbs': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak}
+    del out, logits
+    # mask targets: C3 shape, 2 images x 128 positives, all four sizes in one launch
+    rng = np.random.default_rng(7 + rank)
+    masks_l, props, inds = [], [], []
+    for _ in range(2):
+        m = synth.make_gt_masks(int(rng.integers(1, 21)), IMG_H, IMG_W, rng)
+        pb, pi = synth.jitter_boxes_from_masks(m, 128, rng)
+        masks_l.append(dm.BitmapMasks(m, IMG_H, IMG_W))
+        props.append(torch.from_numpy(pb).to(dev))
+        inds.append(torch.from_numpy(pi).to(dev))
+    for _ in range(3):
+        t = dm.multi_size_mask_targets(props, inds, masks_l)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        t = dm.multi_size_mask_targets(props, inds, masks_l)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    ex['dm_mask_target'] = {'workload': 'C3: 2 images x 128 positives, G~U{1..20} 800x1344 bitmaps, sizes 14/28/56/112, '
+                                        'includes the per-step upload of the bitmaps',
+                            'ms': ms, 'rois_per_s': 256 / ms * 1e3}
+    return ex
+
+
+def run_e2e(args, dm, dev, rank, world, feats_dev, rois_h, onehot_h, counts):
+    """Same pass through the plugin surface (BucketedRoIExtractor + autograd) with HOST buffers.
+
+    The batch is fed in chunks of `--e2e-chunk-images` images so that the pinned staging buffers
+    stay a few GB per rank (8 ranks share one host); every byte of the pyramid, the pooled
+    features and the gradient pyramid still crosses PCIe inside the timed region."""
+    import torch.distributed as dist
+    C = args.channels
+    ci = max(1, min(args.e2e_chunk_images, args.batch))
+    R = args.rois_per_img
+    ext = dm.BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), C, STRIDES)
+    bucket_h = onehot_h.argmax(1)
+    chunks = []
+    for i0 in range(0, args.batch, ci):
+        i1 = min(i0 + ci, args.batch)
+        sel = slice(i0 * R, i1 * R)
+        r = rois_h[sel].clone()
+        r[:, 0] -= i0
+        cnt = torch.bincount(bucket_h[sel], minlength=len(BUCKET_SIZES)).tolist()
+        chunks.append((i0, i1, r.pin_memory(), onehot_h[sel].clone().pin_memory(), cnt))
+    max_cnt = [max(c[4][b] for c in chunks) for b in range(len(BUCKET_SIZES))]
+    try:
+        feats_pin = [torch.empty(f.shape, dtype=f.dtype, pin_memory=True) for f in feats_dev]
+        for p, f in zip(feats_pin, feats_dev):
+            p.copy_(f)
+        outs_pin = [torch.empty((max_cnt[b], C, s, s), dtype=torch.float32, pin_memory=True)
+                    for b, s in enumerate(BUCKET_SIZES)]
+        grads_pin = [torch.empty((ci, ) + tuple(f.shape[1:]), dtype=f.dtype, pin_memory=True) for f in feats_dev]
+    except RuntimeError as e:
+        return {'value': None, 'unit': UNIT, 'error': 'pinned allocation failed: %s' % str(e)[:80]}
+    h2d = sum(p.numel() * 4 for p in feats_pin) + rois_h.numel() * 4 + onehot_h.numel() * 4
+    d2h = sum(counts[b] * C * s * s * 4 for b, s in enumerate(BUCKET_SIZES)) + sum(p.numel() * 4 for p in feats_pin)
+    torch.cuda.synchronize()
+
+    def one():
+        for (i0, i1, r_pin, o_pin, cnt) in chunks:
+            fd = [p[i0:i1].to(dev, non_blocking=True).requires_grad_() for p in feats_pin]
+            rd = r_pin.to(dev, non_blocking=True)
+            od = o_pin.to(dev, non_blocking=True)
+            res = ext.forward_bucketed(fd, rd, od)
+            for p, o in zip(outs_pin, res.feats):
+                p[:o.size(0)].copy_(o.detach(), non_blocking=True)
+            torch.autograd.backward(res.feats, [o.detach() for o in res.feats])
+            for p, f in zip(grads_pin, fd):
+                p[:i1 - i0].copy_(f.grad, non_blocking=True)
+            torch.cuda.synchronize()   # the host consumes this chunk's results before the buffers are reused
+
+    one()  # warm-up
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        one()
+    if world > 1:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    return {'value': world * rois_h.size(0) / dt, 'unit': UNIT, 'ms_per_step': dt * 1e3,
+            'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': args.e2e_steps,
+            'chunk_images': ci,
+            'api': 'BucketedRoIExtractor.forward_bucketed + autograd backward per chunk, pinned host in / out'}
+
+
+if __name__ == '__main__':
+    main()
