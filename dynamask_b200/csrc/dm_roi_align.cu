@@ -12,13 +12,19 @@
 //   1. folds the g_w (g_h) sample weights of every bin into the banded tables Ax, Ay and stages
 //      them in shared memory once per work unit (they are shared by all channels),
 //   2. stages the RoI's feature patch (rows Y0..Y1, columns X0..X1) for a group of channels,
-//   3. X pass:  V[y][pw]  = sum_j Ax[pw][j] * patch[y][xs[pw]+j]          (shared -> shared)
-//   4. Y pass:  out[ph][pw] = sum_j Ay[ph][j] * V[ys[ph]+j][pw]           (shared -> 16-B streaming stores)
+//   3. lets every thread own a column strip (channel, VEC adjacent pooled columns) and walk it
+//      top to bottom: the X-interpolated patch rows the strip currently needs live in a register
+//      window (V[y][pw] = sum_j Ax[pw][j] * patch[y][xs[pw]+j], recomputed from shared memory
+//      only when the window slides), each pooled row is out = sum_j Ay[ph][j] * window[j] and
+//      leaves as one 16-byte streaming store,
 // so HBM sees each patch element once and each output element once.  Backward is the transpose:
-// a column pass that walks grad_out down each column with a register window of band rows
-// (grad_out is read once, straight into registers), a row pass that gathers the patch gradient,
-// and one global reduction (RED.ADD.F32) per touched feature pixel -- i.e. the atomics are
+// the same strip walk reads grad_out once, straight into registers, accumulates the band rows
+// in the register window and retires completed rows into U[c][y][pw] in shared memory (plain
+// stores: a strip owns its columns); a row pass gathers the patch gradient from U, and one global
+// reduction (RED.ADD.F32) per touched feature pixel leaves the CTA -- i.e. the atomics are
 // aggregated per CTA in shared memory before they reach L2.
+// Geometries whose bands are wider than 8 pixels fall back to a two-pass shared-memory form, and
+// those that do not fit shared memory at all to direct sample-by-sample evaluation.
 //
 // Scheduling.  All resolution buckets run in ONE persistent launch: grid = SMs x resident CTAs,
 // work units = (RoI, channel slab) enumerated bucket by bucket from the largest output size to the
@@ -121,8 +127,12 @@ struct Tables {
     float* wx;  // [JX][pw] folded weights (already divided by g_w)
     float* wy;  // [JY][ph]
     int JX, JY, X0, X1, Y0, Y1;
-    int floats;  // shared-memory floats consumed (multiple of 4)
+    int JXa, JYa;  // rows allocated for wx / wy (>= JX / JY, zero padded up to the window class)
+    int floats;    // shared-memory floats consumed (multiple of 4)
 };
+
+// register-window class for a band width: 2, 4, 8, or 0 when wider than 8
+__device__ __forceinline__ int window_class(int j) { return j <= 2 ? 2 : (j <= 4 ? 4 : (j <= 8 ? 8 : 0)); }
 
 __device__ __forceinline__ void axis_scan(int P, int size, float start, float bin, int grid,
                                           int* s_start, int* stat) {
@@ -185,11 +195,16 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     if (t.JX <= 0 || t.JY <= 0) return false;
     const int pa = stat[ST_PA], pb = stat[ST_PB], qa = stat[ST_QA], qb = stat[ST_QB];
     const int base = (Pw + Ph + 3) & ~3;
-    const int wfloats = t.JX * Pw + t.JY * Ph;
+    // both tables padded to the common window class when both bands are <= 8 wide (forward walk),
+    // otherwise each to its own class (the backward walk only needs the Y table)
+    const int wc = window_class(max(t.JX, t.JY));
+    t.JXa = wc ? wc : (window_class(t.JX) ? window_class(t.JX) : t.JX);
+    t.JYa = wc ? wc : (window_class(t.JY) ? window_class(t.JY) : t.JY);
+    const int wfloats = t.JXa * Pw + t.JYa * Ph;
     t.floats = (base + wfloats + 3) & ~3;
     if (t.floats > smem_floats) { fits = false; return true; }
     t.wx = smem + base;
-    t.wy = t.wx + t.JX * Pw;
+    t.wy = t.wx + t.JXa * Pw;
     // bins without any valid sample sit at the two ends; give them a start that keeps xs / ys
     // monotone (their weights stay zero)
     const int xs_last = t.xs[pb], ys_last = t.ys[qb];
@@ -304,7 +319,113 @@ __device__ __forceinline__ int band_rows(const Tables& t, int p0, int p1) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward unit
+// Patch staging: rows [Yt0, Yt0+R) x columns [X0, X0+fw) of `cs` channels -> shared memory
+// [cs][R][fws] (fws >= fw; columns >= fw are zero so banded reads never need a clamp).
+// One warp per (channel, row), PF rows in flight per warp.
+// ---------------------------------------------------------------------------------------------
+__device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0, int cs, int Yt0,
+                            int R, int X0, int fw, int fws) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* src = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Yt0 * Lv.sH + (long long)X0 * Lv.sW;
+    const int nrows = cs * R;
+    FastDiv fdR;
+    fdR.init(R);
+    constexpr int PF = 8;
+    for (int r0 = warp; r0 < nrows; r0 += PF * kRaWarps) {
+        for (int x = lane; x < fws; x += 32) {
+            float v[PF];
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int row = r0 + q * kRaWarps;
+                v[q] = 0.0f;
+                if (row < nrows && x < fw) {
+                    const int c = fdR.div(row), r = row - c * R;
+                    v[q] = __ldg(src + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int row = r0 + q * kRaWarps;
+                if (row < nrows) patch[row * fws + x] = v[q];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, fast path: strip walk with a register window of JW X-interpolated patch rows.
+// Requires JX <= JW and JY <= JW (tables are zero padded to JW rows) and the whole band in smem.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, int JW>
+__device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, float* patch,
+                         int batch, int i, int c0, int cs) {
+    const int Pw = B.pw, Ph = B.ph;
+    const int fw = t.X1 - t.X0 + 1, fws = fw + JW - 1;
+    const int R = t.Y1 - t.Y0 + 1;
+    stage_patch(Lv, patch, batch, c0, cs, t.Y0, R, t.X0, fw, fws);
+    __syncthreads();
+    const int PwV = Pw / VEC;
+    const int nstrips = cs * PwV;
+    FastDiv fdV;
+    fdV.init(PwV);
+    float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+    for (int s = threadIdx.x; s < nstrips; s += kRaThreads) {
+        const int c = fdV.div(s), pv = s - c * PwV;
+        int xoff[VEC];
+        float wxr[JW][VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            xoff[e] = t.xs[pv * VEC + e] - t.X0;
+#pragma unroll
+            for (int j = 0; j < JW; ++j) wxr[j][e] = t.wx[j * Pw + pv * VEC + e];
+        }
+        const float* pc = patch + c * R * fws;
+        float win[JW][VEC];
+        // X-interpolate patch row r (relative to Y0) for this strip's VEC columns
+        auto xrow = [&](int r, float (&v)[VEC]) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
+            if (r < R) {
+                const float* pr = pc + r * fws;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const float* pe = pr + xoff[e];
+#pragma unroll
+                    for (int j = 0; j < JW; ++j) v[e] += wxr[j][e] * pe[j];
+                }
+            }
+        };
+        int base = 0;  // window row 0, relative to Y0 (ys[0] == Y0)
+#pragma unroll
+        for (int j = 0; j < JW; ++j) xrow(j, win[j]);
+        float* o = obase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW;
+        for (int ph = 0; ph < Ph; ++ph) {
+            const int y0 = t.ys[ph] - t.Y0;
+            while (base < y0) {
+#pragma unroll
+                for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
+                ++base;
+                xrow(base + JW - 1, win[JW - 1]);
+            }
+            float acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < JW; ++j) {
+                const float w = t.wy[j * Ph + ph];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += w * win[j][e];
+            }
+            st_stream_vec<VEC>(o + (long long)ph * B.sH, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, generic path (bands wider than 8, or bands too tall for one tile): two passes through
+// shared memory, pooled rows processed in tiles [p0, p1).
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, float* tile,
@@ -315,42 +436,11 @@ __device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables&
     const int R = band_rows(t, p0, p1);
     float* V = tile;                    // [cs][R][Pw]
     float* patch = tile + cs * R * Pw;  // [cs][R][fw]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- stage the patch: one warp per (channel, row), eight rows in flight per warp ----------
-    {
-        const float* src = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Yt0 * Lv.sH + (long long)t.X0 * Lv.sW;
-        const int nrows = cs * R;
-        FastDiv fdR;
-        fdR.init(R);
-        constexpr int PF = 8;  // rows in flight per warp
-        for (int r0 = warp; r0 < nrows; r0 += PF * kRaWarps) {
-            for (int x = lane; x < fw; x += 32) {
-                float v[PF];
-#pragma unroll
-                for (int q = 0; q < PF; ++q) {
-                    const int row = r0 + q * kRaWarps;
-                    v[q] = 0.0f;
-                    if (row < nrows) {
-                        const int c = fdR.div(row), r = row - c * R;
-                        v[q] = __ldg(src + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < PF; ++q) {
-                    const int row = r0 + q * kRaWarps;
-                    if (row < nrows) patch[row * fw + x] = v[q];
-                }
-            }
-        }
-    }
+    stage_patch(Lv, patch, batch, c0, cs, Yt0, R, t.X0, fw, fw);
     __syncthreads();
-
-    // ---- X pass: V[c][r][pw] = sum_j wx[j][pw] * patch[c][r][xs[pw]-X0+j] ---------------------
-    {
+    {   // X pass: V[c][r][pw] = sum_j wx[j][pw] * patch[c][r][xs[pw]-X0+j]
         const int sh = pow2_shift_ge(Pw);
-        const int nrows = cs * R;
-        const int items = nrows << sh;
+        const int items = (cs * R) << sh;
         const int JX = t.JX;
         for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
             const int row = vi >> sh, pw = vi & ((1 << sh) - 1);
@@ -363,14 +453,11 @@ __device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables&
         }
     }
     __syncthreads();
-
-    // ---- Y pass: out[c][ph][pw..pw+VEC) = sum_j wy[j][ph] * V[c][ys[ph]-Yt0+j][pw..] ----------
-    {
+    {   // Y pass: out[c][ph][pw..pw+VEC) = sum_j wy[j][ph] * V[c][ys[ph]-Yt0+j][pw..]
         const int PwV = Pw / VEC;
         const int sh = pow2_shift_ge(PwV);
         const int nph = p1 - p0;
-        const int nrows = cs * nph;
-        const int items = nrows << sh;
+        const int items = (cs * nph) << sh;
         const int JY = t.JY;
         FastDiv fdP;
         fdP.init(nph);
@@ -391,9 +478,7 @@ __device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables&
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) acc[e] += w * v[e];
             }
-            float* o = obase + (long long)c * B.sC + (long long)ph * B.sH + (long long)(pv * VEC) * B.sW;
-            if (VEC == 1) __stcs(o, acc[0]);
-            else st_stream_vec<VEC>(o, acc);
+            st_stream_vec<VEC>(obase + (long long)c * B.sC + (long long)ph * B.sH + (long long)(pv * VEC) * B.sW, acc);
         }
     }
 }
@@ -421,14 +506,27 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     }
     const int fw = fits ? t.X1 - t.X0 + 1 : 0;
     const int avail = p.smem_floats - (fits ? t.floats : 0);
-    // smallest possible tile: one channel, one pooled row
+    // smallest possible generic tile: one channel, one pooled row
     if (!fits || (long long)t.JY * (fw + B.pw) > avail) {
         direct_unit<false>(Lv, B, g, batch, un.i, c0, c1);
         return;
     }
     float* tile = smem + t.floats;
-    const int per_row = fw + B.pw;
     const int Rfull = t.Y1 - t.Y0 + 1;
+    const int wc = window_class(max(t.JX, t.JY));
+    if (wc && (long long)Rfull * (fw + wc - 1) <= avail) {
+        // fast path: only the patch lives in shared memory
+        const int cs_max = min(c1 - c0, avail / (Rfull * (fw + wc - 1)));
+        for (int c = c0; c < c1; c += cs_max) {
+            const int cs = min(cs_max, c1 - c);
+            if (wc == 2) fwd_walk<VEC, 2>(Lv, B, t, tile, batch, un.i, c, cs);
+            else if (wc == 4) fwd_walk<VEC, 4>(Lv, B, t, tile, batch, un.i, c, cs);
+            else fwd_walk<VEC, 8>(Lv, B, t, tile, batch, un.i, c, cs);
+            __syncthreads();
+        }
+        return;
+    }
+    const int per_row = fw + B.pw;
     if ((long long)Rfull * per_row <= avail) {
         const int cs_max = min(c1 - c0, avail / (Rfull * per_row));
         for (int c = c0; c < c1; c += cs_max) {
@@ -453,89 +551,82 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // ---------------------------------------------------------------------------------------------
 // Backward unit
 // ---------------------------------------------------------------------------------------------
-// Column pass: every thread owns (channel, column vector, run of pooled rows) and walks its run
-// top to bottom keeping the JYW band rows it is currently touching in registers.  Completed band
-// rows are added to the shared accumulator U[c][r][pw] (shared-memory reductions; runs of the
-// same column overlap in at most JY-1 rows).
-template <int VEC, int JYW>
-__device__ void bwd_column_pass(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
+// Column pass, fast path: a thread owns (channel, VEC adjacent pooled columns) and walks all
+// pooled rows top to bottom; the JW band rows it is accumulating live in registers, completed
+// rows retire to U[c][r][pw] with one plain vector store (the strip owns those columns, so no
+// atomics and no zero-init are needed: every row 0..R-1 is retired exactly once).
+template <int VEC, int JW>
+__device__ void bwd_walk(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
     const int Pw = B.pw, Ph = B.ph;
     const int PwV = Pw / VEC;
     const int R = t.Y1 - t.Y0 + 1;
     const int nstrips = cs * PwV;
-    // split the pooled rows into runs so that there are >= 2 items per thread when possible
-    int nseg = (2 * kRaThreads + nstrips - 1) / nstrips;
-    nseg = max(1, min(nseg, Ph / 8 > 0 ? Ph / 8 : 1));
-    const int seg_len = (Ph + nseg - 1) / nseg;
-    const int items = nstrips * nseg;
-    FastDiv fdS, fdV;
-    fdS.init(nstrips);
+    FastDiv fdV;
     fdV.init(PwV);
     const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-    const int JY = t.JY;
-    for (int it = threadIdx.x; it < items; it += kRaThreads) {
-        const int sg = fdS.div(it), strip = it - sg * nstrips;
-        const int c = fdV.div(strip), pv = strip - c * PwV;
-        const int q0 = sg * seg_len, q1 = min(q0 + seg_len, Ph);
-        if (q0 >= q1) continue;
+    constexpr int PF = (VEC * JW >= 32) ? 4 : 8;  // pooled rows loaded ahead of use
+    for (int s = threadIdx.x; s < nstrips; s += kRaThreads) {
+        const int c = fdV.div(s), pv = s - c * PwV;
         const float* gp = gbase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW;
         float* uc = U + c * R * Pw + pv * VEC;
-        float acc[JYW][VEC];
+        float acc[JW][VEC];
 #pragma unroll
-        for (int j = 0; j < JYW; ++j)
+        for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
-        int base = t.ys[q0];
-        constexpr int PF = 8;  // pooled rows loaded ahead of use
-        for (int ph0 = q0; ph0 < q1; ph0 += PF) {
+        int base = 0;  // window row 0 relative to Y0
+        for (int ph0 = 0; ph0 < Ph; ph0 += PF) {
             float gv[PF][VEC];
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                if (ph0 + u < q1) ldg_stream_vec<VEC>(gp + (long long)(ph0 + u) * B.sH, gv[u]);
-            }
+            for (int u = 0; u < PF; ++u)
+                if (ph0 + u < Ph) ldg_stream_vec<VEC>(gp + (long long)(ph0 + u) * B.sH, gv[u]);
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 const int ph = ph0 + u;
-                if (ph >= q1) break;
-                const int y0 = t.ys[ph];
+                if (ph >= Ph) break;
+                const int y0 = t.ys[ph] - t.Y0;
                 while (base < y0) {
-                    const int r = base - t.Y0;
-                    if (r < R) {
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e)
-                            if (acc[0][e] != 0.0f) atomicAdd(uc + r * Pw + e, acc[0][e]);
+                    if (base < R) {
+                        if (VEC == 1) uc[base * Pw] = acc[0][0];
+                        else if (VEC == 2) *reinterpret_cast<float2*>(uc + base * Pw) = make_float2(acc[0][0], acc[0][1 % VEC]);
+                        else *reinterpret_cast<float4*>(uc + base * Pw) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
                     }
 #pragma unroll
-                    for (int j = 0; j + 1 < JYW; ++j)
+                    for (int j = 0; j + 1 < JW; ++j)
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[JYW - 1][e] = 0.0f;
+                    for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
                     ++base;
                 }
 #pragma unroll
-                for (int j = 0; j < JYW; ++j) {
-                    if (j < JY) {
-                        const float w = t.wy[j * Ph + ph];
+                for (int j = 0; j < JW; ++j) {
+                    const float w = t.wy[j * Ph + ph];
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[j][e] += w * gv[u][e];
-                    }
+                    for (int e = 0; e < VEC; ++e) acc[j][e] += w * gv[u][e];
                 }
             }
         }
+        // retire what is left; rows between the last window and R-1 (none in practice) get zeros
+        for (int r = base; r < R; ++r) {
+            const int j = r - base;
+            float v[VEC];
 #pragma unroll
-        for (int j = 0; j < JYW; ++j) {
-            const int r = base + j - t.Y0;
-            if (r < R) {
+            for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    if (acc[j][e] != 0.0f) atomicAdd(uc + r * Pw + e, acc[j][e]);
-            }
+            for (int jj = 0; jj < JW; ++jj)
+                if (jj == j) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) v[e] = acc[jj][e];
+                }
+            if (VEC == 1) uc[r * Pw] = v[0];
+            else if (VEC == 2) *reinterpret_cast<float2*>(uc + r * Pw) = make_float2(v[0], v[1 % VEC]);
+            else *reinterpret_cast<float4*>(uc + r * Pw) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
         }
     }
 }
 
-// Generic column pass for very tall bands (JY > 8): straight shared-memory reductions.
+// Column pass, generic path for bands taller than 8 rows: shared-memory reductions into a zeroed U.
 template <int VEC>
 __device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
     const int Pw = B.pw, Ph = B.ph;
@@ -543,6 +634,8 @@ __device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables& t, fl
     const int R = t.Y1 - t.Y0 + 1;
     const int per_c = Ph * PwV;
     const int items = cs * per_c;
+    for (int e = threadIdx.x; e < cs * R * Pw; e += kRaThreads) U[e] = 0.0f;
+    __syncthreads();
     const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
     for (int it = threadIdx.x; it < items; it += kRaThreads) {
         const int c = it / per_c, rem = it - c * per_c;
@@ -562,29 +655,27 @@ __device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables& t, fl
     }
 }
 
-// Row pass + flush: grad_patch[c][r][x] = sum_{pw : xs[pw] <= x < xs[pw]+JX} wx[x-xs[pw]][pw] * U[c][r][pw],
+// Row pass + flush: grad_patch[c][r][x] = sum_{pw in [plo[x], phi[x]]} wxT[x][pw-plo[x]] * U[c][r][pw],
 // one global reduction per touched feature element.
 __device__ void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, const float* U,
-                             const int* plo, const int* phi, int batch, int c0, int cs) {
+                             const int* plo, const int* pcnt, const float* wxT, int TW, int batch,
+                             int c0, int cs) {
     const int Pw = B.pw;
     const int fw = t.X1 - t.X0 + 1;
     const int R = t.Y1 - t.Y0 + 1;
     const int sh = pow2_shift_ge(fw);
-    const int nrows = cs * R;
-    const int items = nrows << sh;
+    const int items = (cs * R) << sh;
     FastDiv fdR;
     fdR.init(R);
     float* dst = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + (long long)t.X0 * Lv.sW;
     for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
         const int row = vi >> sh, x = vi & ((1 << sh) - 1);
         if (x >= fw) continue;
-        const float* urow = U + row * Pw;
-        const int lo = plo[x], hi = phi[x];
+        const float* up = U + row * Pw + plo[x];
+        const float* wp = wxT + x * TW;
+        const int n = pcnt[x];
         float acc = 0.0f;
-        for (int pw = lo; pw <= hi; ++pw) {
-            const int j = x + t.X0 - t.xs[pw];
-            acc += t.wx[j * Pw + pw] * urow[pw];
-        }
+        for (int q = 0; q < n; ++q) acc += wp[q] * up[q];
         if (acc != 0.0f) {
             const int c = fdR.div(row), r = row - c * R;
             atomicAdd(dst + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW, acc);
@@ -610,36 +701,65 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) return;
     const int fw = fits ? t.X1 - t.X0 + 1 : 0;
     const int R = fits ? t.Y1 - t.Y0 + 1 : 0;
-    // extra tables: pooled-column range touching each feature column
-    const int extra = (2 * fw + 3) & ~3;
+    // transposed X tables: for feature column x the pooled columns [plo, plo+pcnt) whose band covers
+    // it, and their weights wxT[x][q]
+    int* plo = reinterpret_cast<int*>(smem + (fits ? t.floats : 0));
+    int* pcnt = plo + fw;
+    int* s_tw = stat + ST_PA;  // reuse a stat slot for the max range length
+    if (fits && 2 * fw <= p.smem_floats - t.floats) {
+        if (threadIdx.x == 0) *s_tw = 0;
+        __syncthreads();
+        for (int x = threadIdx.x; x < fw; x += kRaThreads) {
+            const int xa = x + t.X0;
+            // xs is monotone: first bin whose band reaches xa, last bin whose band starts at or before xa
+            int lo = 0, hi = B.pw;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (t.xs[mid] + t.JX - 1 < xa) lo = mid + 1; else hi = mid;
+            }
+            int a = lo;
+            lo = 0; hi = B.pw;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (t.xs[mid] <= xa) lo = mid + 1; else hi = mid;
+            }
+            const int n = max(lo - a, 0);
+            plo[x] = a;
+            pcnt[x] = n;
+            atomicMax(s_tw, n);
+        }
+        __syncthreads();
+    }
+    const int TW = fits ? *s_tw : 0;
+    const int extra = (2 * fw + fw * TW + 3) & ~3;
     const long long avail = (long long)p.smem_floats - (fits ? t.floats : 0) - extra;
     if (!fits || (long long)R * B.pw > avail) {
         direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
         return;
     }
-    int* plo = reinterpret_cast<int*>(smem + t.floats);
-    int* phi = plo + fw;
-    for (int x = threadIdx.x; x < fw; x += kRaThreads) {
-        const int xa = x + t.X0;
-        // first bin whose band reaches xa, last bin whose band starts at or before xa (xs is monotone)
-        int lo = 0, hi = B.pw - 1;
-        while (lo < B.pw && t.xs[lo] + t.JX - 1 < xa) ++lo;
-        while (hi >= 0 && t.xs[hi] > xa) --hi;
-        plo[x] = lo;
-        phi[x] = hi;
+    float* wxT = reinterpret_cast<float*>(pcnt + fw);
+    for (int e = threadIdx.x; e < fw * TW; e += kRaThreads) {
+        const int x = e / TW, q = e - x * TW;
+        float w = 0.0f;
+        if (q < pcnt[x]) {
+            const int pw = plo[x] + q;
+            w = t.wx[(x + t.X0 - t.xs[pw]) * B.pw + pw];
+        }
+        wxT[e] = w;
     }
     float* U = smem + t.floats + extra;
     const int per_c = R * B.pw;
     const int cs_max = min(c1 - c0, (int)(avail / per_c));
+    const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
+    __syncthreads();
     for (int c = c0; c < c1; c += cs_max) {
         const int cs = min(cs_max, c1 - c);
-        for (int e = threadIdx.x; e < cs * per_c; e += kRaThreads) U[e] = 0.0f;
-        __syncthreads();
-        if (t.JY <= 4) bwd_column_pass<VEC, 4>(B, t, U, un.i, c, cs);
-        else if (t.JY <= 8) bwd_column_pass<VEC, 8>(B, t, U, un.i, c, cs);
+        if (wc == 2) bwd_walk<VEC, 2>(B, t, U, un.i, c, cs);
+        else if (wc == 4) bwd_walk<VEC, 4>(B, t, U, un.i, c, cs);
+        else if (wc == 8) bwd_walk<VEC, 8>(B, t, U, un.i, c, cs);
         else bwd_column_pass_generic<VEC>(B, t, U, un.i, c, cs);
         __syncthreads();
-        bwd_row_pass(Lv, B, t, U, plo, phi, batch, c, cs);
+        bwd_row_pass(Lv, B, t, U, plo, pcnt, wxT, TW, batch, c, cs);
         __syncthreads();
     }
 }
@@ -721,12 +841,12 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
         d.sH = out_strides[4 * b + 2];
         d.sW = out_strides[4 * b + 3];
         if (d.ph < 1 || d.pw < 1 || d.ph >= (1 << 15) || d.pw >= (1 << 15)) return DM_EINVAL;
-        // ~256 KB of pooled output per work unit
-        int cg = 65536 / (d.ph * d.pw);
+        // ~1 MB of pooled output per work unit: the banded tables are rebuilt per unit
+        int cg = 393216 / (d.ph * d.pw);
         int pw2 = 1;
         while (pw2 * 2 <= cg) pw2 *= 2;
         cg = cg < 1 ? 1 : pw2;
-        cg = cg < 4 ? 4 : (cg > 64 ? 64 : cg);
+        cg = cg < 4 ? 4 : (cg > 256 ? 256 : cg);
         cg = env_int("DM_RA_CG", 0) > 0 ? env_int("DM_RA_CG", 0) : cg;
         if (cg > p.C) cg = p.C;
         d.cg = cg;
