@@ -72,12 +72,20 @@ struct RaParams {
     int smem_floats;
 };
 
-// exact n / d for n, d < 2^20
+// exact n / d whenever n * d < 2^32 (indices here are far below that)
 struct FastDiv {
-    unsigned long long m;
-    __device__ __forceinline__ void init(unsigned d) { m = ((1ull << 40) + d - 1) / d; }
-    __device__ __forceinline__ unsigned div(unsigned n) const { return (unsigned)((n * m) >> 40); }
+    unsigned m, d;
+    __device__ __forceinline__ void init(unsigned dd) {
+        d = dd;
+        m = dd > 1 ? 0xFFFFFFFFu / dd + 1u : 0u;
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return d > 1 ? __umulhi(n, m) : n; }
 };
+
+// fraction of thread slots doing work when n items are dealt round-robin to the CTA
+__device__ __forceinline__ float cta_util(int n) {
+    return (float)n / (float)(((n + kRaThreads - 1) / kRaThreads) * kRaThreads);
+}
 
 __device__ __forceinline__ int pow2_shift_ge(int n) {  // smallest s with (1 << s) >= n
     return n <= 1 ? 0 : 32 - __clz(n - 1);
@@ -128,6 +136,8 @@ struct Tables {
     float* wy;  // [JY][ph]
     int JX, JY, X0, X1, Y0, Y1;
     int JXa, JYa;  // rows allocated for wx / wy (>= JX / JY, zero padded up to the window class)
+    float* ytab;   // packed per-pooled-row records {ys - Y0, wy[0..JYa)} when JYa is a window class
+    int ystride;   // floats per record (4, 8 or 12), 0 when there is no packed table
     int floats;    // shared-memory floats consumed (multiple of 4)
 };
 
@@ -200,11 +210,13 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     const int wc = window_class(max(t.JX, t.JY));
     t.JXa = wc ? wc : (window_class(t.JX) ? window_class(t.JX) : t.JX);
     t.JYa = wc ? wc : (window_class(t.JY) ? window_class(t.JY) : t.JY);
-    const int wfloats = t.JXa * Pw + t.JYa * Ph;
-    t.floats = (base + wfloats + 3) & ~3;
+    const int wfloats = (t.JXa * Pw + t.JYa * Ph + 3) & ~3;
+    t.ystride = (t.JYa == 2) ? 4 : (t.JYa == 4 ? 8 : (t.JYa == 8 ? 12 : 0));
+    t.floats = base + wfloats + t.ystride * Ph;
     if (t.floats > smem_floats) { fits = false; return true; }
     t.wx = smem + base;
     t.wy = t.wx + t.JXa * Pw;
+    t.ytab = smem + base + wfloats;
     // bins without any valid sample sit at the two ends; give them a start that keeps xs / ys
     // monotone (their weights stay zero)
     const int xs_last = t.xs[pb], ys_last = t.ys[qb];
@@ -218,7 +230,35 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     axis_fill(Pw, W, g.rsw, g.bw, g.gw, t.xs, t.wx);
     axis_fill(Ph, H, g.rsh, g.bh, g.gh, t.ys, t.wy);
     __syncthreads();
+    if (t.ystride) {
+        for (int i = threadIdx.x; i < Ph * t.ystride; i += kRaThreads) {
+            const int ph = i / t.ystride, f = i - ph * t.ystride;
+            float v = 0.0f;
+            if (f == 0) v = __int_as_float(t.ys[ph] - t.Y0);
+            else if (f <= t.JYa) v = t.wy[(f - 1) * Ph + ph];
+            t.ytab[i] = v;
+        }
+        __syncthreads();
+    }
     return true;
+}
+
+// one packed Y record: window-relative start row and the JW row weights
+template <int JW>
+__device__ __forceinline__ void load_yrec(const float* __restrict__ ytab, int ph, int& y0, float (&w)[JW]) {
+    constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
+    const float4* r = reinterpret_cast<const float4*>(ytab + ph * YS);
+    const float4 a = r[0];
+    y0 = __float_as_int(a.x);
+    w[0] = a.y; w[1] = a.z;
+    if (JW >= 4) {
+        const float4 b = r[1];
+        w[2 % JW] = a.w; w[3 % JW] = b.x;
+        if (JW == 8) {
+            const float4 c = r[2];
+            w[4 % JW] = b.y; w[5 % JW] = b.z; w[6 % JW] = b.w; w[7 % JW] = c.x;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -326,21 +366,24 @@ __device__ __forceinline__ int band_rows(const Tables& t, int p0, int p1) {
 __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0, int cs, int Yt0,
                             int R, int X0, int fw, int fws) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* src = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Yt0 * Lv.sH + (long long)X0 * Lv.sW;
+    const float* __restrict__ src = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Yt0 * Lv.sH + (long long)X0 * Lv.sW;
+    const long long sC = Lv.sC, sH = Lv.sH, sW = Lv.sW;
     const int nrows = cs * R;
     FastDiv fdR;
     fdR.init(R);
     constexpr int PF = 8;
-    for (int r0 = warp; r0 < nrows; r0 += PF * kRaWarps) {
-        for (int x = lane; x < fws; x += 32) {
+    for (int x = lane; x < fws; x += 32) {
+        const float* __restrict__ sx = src + (long long)x * sW;
+        const bool live = x < fw;
+        for (int r0 = warp; r0 < nrows; r0 += PF * kRaWarps) {
             float v[PF];
 #pragma unroll
             for (int q = 0; q < PF; ++q) {
                 const int row = r0 + q * kRaWarps;
                 v[q] = 0.0f;
-                if (row < nrows && x < fw) {
+                if (live && row < nrows) {
                     const int c = fdR.div(row), r = row - c * R;
-                    v[q] = __ldg(src + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW);
+                    v[q] = __ldg(sx + c * sC + r * sH);
                 }
             }
 #pragma unroll
@@ -357,7 +400,7 @@ __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0
 // Requires JX <= JW and JY <= JW (tables are zero padded to JW rows) and the whole band in smem.
 // ---------------------------------------------------------------------------------------------
 template <int VEC, int JW>
-__device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, float* patch,
+__device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables t, float* patch,
                          int batch, int i, int c0, int cs) {
     const int Pw = B.pw, Ph = B.ph;
     const int fw = t.X1 - t.X0 + 1, fws = fw + JW - 1;
@@ -366,41 +409,66 @@ __device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables&
     __syncthreads();
     const int PwV = Pw / VEC;
     const int nstrips = cs * PwV;
-    FastDiv fdV;
+    // split the pooled rows into nseg runs when that fills the CTA's thread slots better
+    int nseg = 1;
+    {
+        float best = cta_util(nstrips);
+        for (int ns = 2; ns <= 4; ++ns) {
+            const float u = cta_util(nstrips * ns);
+            if (Ph >= 8 * ns && u > best + 0.03f) { best = u; nseg = ns; }
+        }
+    }
+    const int seg_len = (Ph + nseg - 1) / nseg;
+    const int items = nstrips * nseg;
+    FastDiv fdV, fdS;
     fdV.init(PwV);
+    fdS.init(nstrips);
+    const int* __restrict__ xs = t.xs;
+    const float* __restrict__ wx = t.wx;
+    const float* __restrict__ ytab = t.ytab;
+    const int X0 = t.X0;
+    const long long osH = B.sH;
     float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-    for (int s = threadIdx.x; s < nstrips; s += kRaThreads) {
+    for (int it = threadIdx.x; it < items; it += kRaThreads) {
+        const int sg = fdS.div(it), s = it - sg * nstrips;
         const int c = fdV.div(s), pv = s - c * PwV;
-        int xoff[VEC];
+        const int q0 = sg * seg_len, q1 = min(q0 + seg_len, Ph);
+        if (q0 >= q1) continue;
+        const float* pe[VEC];
         float wxr[JW][VEC];
+        const float* pc = patch + c * R * fws;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            xoff[e] = t.xs[pv * VEC + e] - t.X0;
+            pe[e] = pc + (xs[pv * VEC + e] - X0);
 #pragma unroll
-            for (int j = 0; j < JW; ++j) wxr[j][e] = t.wx[j * Pw + pv * VEC + e];
+            for (int j = 0; j < JW; ++j) wxr[j][e] = wx[j * Pw + pv * VEC + e];
         }
-        const float* pc = patch + c * R * fws;
         float win[JW][VEC];
         // X-interpolate patch row r (relative to Y0) for this strip's VEC columns
         auto xrow = [&](int r, float (&v)[VEC]) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
             if (r < R) {
-                const float* pr = pc + r * fws;
+                const int ro = r * fws;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    const float* pe = pr + xoff[e];
 #pragma unroll
-                    for (int j = 0; j < JW; ++j) v[e] += wxr[j][e] * pe[j];
+                    for (int j = 0; j < JW; ++j) v[e] += wxr[j][e] * pe[e][ro + j];
                 }
             }
         };
-        int base = 0;  // window row 0, relative to Y0 (ys[0] == Y0)
+        int base;  // window row 0, relative to Y0
+        {
+            float wtmp[JW];
+            load_yrec<JW>(ytab, q0, base, wtmp);
+        }
 #pragma unroll
-        for (int j = 0; j < JW; ++j) xrow(j, win[j]);
-        float* o = obase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW;
-        for (int ph = 0; ph < Ph; ++ph) {
-            const int y0 = t.ys[ph] - t.Y0;
+        for (int j = 0; j < JW; ++j) xrow(base + j, win[j]);
+        float* o = obase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW + (long long)q0 * osH;
+        for (int ph = q0; ph < q1; ++ph) {
+            int y0;
+            float w[JW];
+            load_yrec<JW>(ytab, ph, y0, w);
             while (base < y0) {
 #pragma unroll
                 for (int j = 0; j + 1 < JW; ++j)
@@ -411,14 +479,13 @@ __device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables&
             }
             float acc[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+            for (int e = 0; e < VEC; ++e) acc[e] = w[0] * win[0][e];
 #pragma unroll
-            for (int j = 0; j < JW; ++j) {
-                const float w = t.wy[j * Ph + ph];
+            for (int j = 1; j < JW; ++j)
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[e] += w * win[j][e];
-            }
-            st_stream_vec<VEC>(o + (long long)ph * B.sH, acc);
+                for (int e = 0; e < VEC; ++e) acc[e] += w[j] * win[j][e];
+            st_stream_vec<VEC>(o, acc);
+            o += osH;
         }
     }
 }
@@ -428,7 +495,7 @@ __device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables&
 // shared memory, pooled rows processed in tiles [p0, p1).
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
-__device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, float* tile,
+__device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables t, float* tile,
                          int batch, int i, int c0, int cs, int p0, int p1) {
     const int Pw = B.pw;
     const int fw = t.X1 - t.X0 + 1;
@@ -556,15 +623,17 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // rows retire to U[c][r][pw] with one plain vector store (the strip owns those columns, so no
 // atomics and no zero-init are needed: every row 0..R-1 is retired exactly once).
 template <int VEC, int JW>
-__device__ void bwd_walk(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
+__device__ void bwd_walk(const BucketDesc& B, const Tables t, float* U, int i, int c0, int cs) {
     const int Pw = B.pw, Ph = B.ph;
     const int PwV = Pw / VEC;
     const int R = t.Y1 - t.Y0 + 1;
     const int nstrips = cs * PwV;
     FastDiv fdV;
     fdV.init(PwV);
+    const float* __restrict__ ytab = t.ytab;
+    const long long gsH = B.sH;
     const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-    constexpr int PF = (VEC * JW >= 32) ? 4 : 8;  // pooled rows loaded ahead of use
+    constexpr int PF = (JW == 8) ? 2 : 4;  // pooled rows per batch; the next batch is in flight while this one is used
     for (int s = threadIdx.x; s < nstrips; s += kRaThreads) {
         const int c = fdV.div(s), pv = s - c * PwV;
         const float* gp = gbase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW;
@@ -575,60 +644,64 @@ __device__ void bwd_walk(const BucketDesc& B, const Tables& t, float* U, int i, 
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
         int base = 0;  // window row 0 relative to Y0
+        float cur[PF][VEC], nxt[PF][VEC];
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (u < Ph) ldg_stream_vec<VEC>(gp + (long long)u * gsH, cur[u]);
         for (int ph0 = 0; ph0 < Ph; ph0 += PF) {
-            float gv[PF][VEC];
 #pragma unroll
             for (int u = 0; u < PF; ++u)
-                if (ph0 + u < Ph) ldg_stream_vec<VEC>(gp + (long long)(ph0 + u) * B.sH, gv[u]);
+                if (ph0 + PF + u < Ph) ldg_stream_vec<VEC>(gp + (long long)(ph0 + PF + u) * gsH, nxt[u]);
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 const int ph = ph0 + u;
-                if (ph >= Ph) break;
-                const int y0 = t.ys[ph] - t.Y0;
-                while (base < y0) {
-                    if (base < R) {
-                        if (VEC == 1) uc[base * Pw] = acc[0][0];
-                        else if (VEC == 2) *reinterpret_cast<float2*>(uc + base * Pw) = make_float2(acc[0][0], acc[0][1 % VEC]);
-                        else *reinterpret_cast<float4*>(uc + base * Pw) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
+                if (ph < Ph) {
+                    int y0;
+                    float w[JW];
+                    load_yrec<JW>(ytab, ph, y0, w);
+                    while (base < y0) {
+                        if (base < R) {
+                            if (VEC == 1) uc[base * Pw] = acc[0][0];
+                            else if (VEC == 2) *reinterpret_cast<float2*>(uc + base * Pw) = make_float2(acc[0][0], acc[0][1 % VEC]);
+                            else *reinterpret_cast<float4*>(uc + base * Pw) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
+                        }
+#pragma unroll
+                        for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
+                        ++base;
                     }
 #pragma unroll
-                    for (int j = 0; j + 1 < JW; ++j)
+                    for (int j = 0; j < JW; ++j)
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
-                    ++base;
-                }
-#pragma unroll
-                for (int j = 0; j < JW; ++j) {
-                    const float w = t.wy[j * Ph + ph];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[j][e] += w * gv[u][e];
+                        for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * cur[u][e];
                 }
             }
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) cur[u][e] = nxt[u][e];
         }
-        // retire what is left; rows between the last window and R-1 (none in practice) get zeros
-        for (int r = base; r < R; ++r) {
-            const int j = r - base;
-            float v[VEC];
+        // retire the window, then zero any band rows below it (none in practice)
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
-#pragma unroll
-            for (int jj = 0; jj < JW; ++jj)
-                if (jj == j) {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) v[e] = acc[jj][e];
-                }
-            if (VEC == 1) uc[r * Pw] = v[0];
-            else if (VEC == 2) *reinterpret_cast<float2*>(uc + r * Pw) = make_float2(v[0], v[1 % VEC]);
-            else *reinterpret_cast<float4*>(uc + r * Pw) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        for (int j = 0; j < JW; ++j) {
+            const int r = base + j;
+            if (r < R) {
+                if (VEC == 1) uc[r * Pw] = acc[j][0];
+                else if (VEC == 2) *reinterpret_cast<float2*>(uc + r * Pw) = make_float2(acc[j][0], acc[j][1 % VEC]);
+                else *reinterpret_cast<float4*>(uc + r * Pw) = make_float4(acc[j][0], acc[j][1 % VEC], acc[j][2 % VEC], acc[j][3 % VEC]);
+            }
         }
+        for (int r = base + JW; r < R; ++r)
+            for (int e = 0; e < VEC; ++e) uc[r * Pw + e] = 0.0f;
     }
 }
 
 // Column pass, generic path for bands taller than 8 rows: shared-memory reductions into a zeroed U.
 template <int VEC>
-__device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables& t, float* U, int i, int c0, int cs) {
+__device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables t, float* U, int i, int c0, int cs) {
     const int Pw = B.pw, Ph = B.ph;
     const int PwV = Pw / VEC;
     const int R = t.Y1 - t.Y0 + 1;
@@ -657,7 +730,7 @@ __device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables& t, fl
 
 // Row pass + flush: grad_patch[c][r][x] = sum_{pw in [plo[x], phi[x]]} wxT[x][pw-plo[x]] * U[c][r][pw],
 // one global reduction per touched feature element.
-__device__ void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, const float* U,
+__device__ void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, const Tables t, const float* U,
                              const int* plo, const int* pcnt, const float* wxT, int TW, int batch,
                              int c0, int cs) {
     const int Pw = B.pw;
@@ -749,7 +822,17 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     }
     float* U = smem + t.floats + extra;
     const int per_c = R * B.pw;
-    const int cs_max = min(c1 - c0, (int)(avail / per_c));
+    int cs_max = min(c1 - c0, (int)(avail / per_c));
+    {   // a strip owns its columns for the whole walk, so pick the group size that fills the CTA best
+        const int PwV = B.pw / VEC;
+        int best_cs = cs_max;
+        float best = cta_util(cs_max * PwV);
+        for (int cs = cs_max - 1; cs >= 1 && cs >= cs_max - 12; --cs) {
+            const float u = cta_util(cs * PwV) * (cs * 2 >= cs_max ? 1.0f : 0.9f);
+            if (u > best + 0.04f) { best = u; best_cs = cs; }
+        }
+        cs_max = best_cs;
+    }
     const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
     __syncthreads();
     for (int c = c0; c < c1; c += cs_max) {
