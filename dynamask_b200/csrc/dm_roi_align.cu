@@ -12,19 +12,23 @@
 //   1. folds the g_w (g_h) sample weights of every bin into the banded tables Ax, Ay and stages
 //      them in shared memory once per work unit (they are shared by all channels),
 //   2. stages the RoI's feature patch (rows Y0..Y1, columns X0..X1) for a group of channels,
-//   3. lets every thread own a column strip (channel, VEC adjacent pooled columns) and walk it
-//      top to bottom: the X-interpolated patch rows the strip currently needs live in a register
-//      window (V[y][pw] = sum_j Ax[pw][j] * patch[y][xs[pw]+j], recomputed from shared memory
-//      only when the window slides), each pooled row is out = sum_j Ay[ph][j] * window[j] and
-//      leaves as one 16-byte streaming store,
-// so HBM sees each patch element once and each output element once.  Backward is the transpose:
-// the same strip walk reads grad_out once, straight into registers, accumulates the band rows
-// in the register window and retires completed rows into U[c][y][pw] in shared memory (plain
-// stores: a strip owns its columns); a row pass gathers the patch gradient from U, and one global
-// reduction (RED.ADD.F32) per touched feature pixel leaves the CTA -- i.e. the atomics are
-// aggregated per CTA in shared memory before they reach L2.
-// Geometries whose bands are wider than 8 pixels fall back to a two-pass shared-memory form, and
-// those that do not fit shared memory at all to direct sample-by-sample evaluation.
+//   3. lets every WARP own whole channels: the warp stages its channel's patch in a private slice
+//      of shared memory and its lanes are that channel's column strips (VEC adjacent pooled
+//      columns each).  A lane walks its strip top to bottom; the X-interpolated patch rows it
+//      currently needs live in a register window (V[y][pw] = sum_j Ax[pw][j] * patch[y][xs[pw]+j],
+//      recomputed from shared memory only when the window slides), each pooled row is
+//      out = sum_j Ay[ph][j] * window[j] and leaves as one 16-byte streaming store.
+// HBM sees each patch element once and each output element once.  Backward is the transpose: the
+// same strip walk reads grad_out once, straight into registers (two batches of rows in flight),
+// accumulates the band rows in the register window, and when a band row is complete the warp
+// drops it into a 512-byte private row buffer, gathers the patch-gradient row from it with the
+// transposed X table and issues one global reduction (RED.ADD.F32) per touched feature pixel --
+// i.e. the atomics are aggregated per warp before they reach L2.
+// After the per-unit table build no CTA-wide barrier is needed: warps run independently, so one
+// warp's load latency is hidden by the others' stores.
+// Geometries whose bands are wider than 8 pixels (or pooled rows wider than 32 strips) fall back
+// to a CTA-wide two-pass shared-memory form, and those that do not fit shared memory at all to
+// direct sample-by-sample evaluation.
 //
 // Scheduling.  All resolution buckets run in ONE persistent launch: grid = SMs x resident CTAs,
 // work units = (RoI, channel slab) enumerated bucket by bucket from the largest output size to the
@@ -79,6 +83,7 @@ struct FastDiv {
         d = dd;
         m = dd > 1 ? 0xFFFFFFFFu / dd + 1u : 0u;
     }
+    __device__ __forceinline__ void set(unsigned dd, unsigned mm) { d = dd; m = mm; }
     __device__ __forceinline__ unsigned div(unsigned n) const { return d > 1 ? __umulhi(n, m) : n; }
 };
 
@@ -127,7 +132,7 @@ __device__ __forceinline__ void st_stream_vec(float* p, const float (&a)[VEC]) {
 // ---------------------------------------------------------------------------------------------
 // Banded weight tables of one RoI, staged in shared memory.
 // ---------------------------------------------------------------------------------------------
-enum { ST_JX = 0, ST_X0, ST_X1, ST_PA, ST_PB, ST_JY, ST_Y0, ST_Y1, ST_QA, ST_QB, ST_N };
+enum { ST_JX = 0, ST_X0, ST_X1, ST_PA, ST_PB, ST_JY, ST_Y0, ST_Y1, ST_QA, ST_QB, ST_MR, ST_TW, ST_N };
 
 struct Tables {
     int* xs;    // [pw]  first feature column touched by bin pw
@@ -136,6 +141,7 @@ struct Tables {
     float* wy;  // [JY][ph]
     int JX, JY, X0, X1, Y0, Y1;
     int JXa, JYa;  // rows allocated for wx / wy (>= JX / JY, zero padded up to the window class)
+    unsigned mR;   // FastDiv magic of R = Y1 - Y0 + 1
     float* ytab;   // packed per-pooled-row records {ys - Y0, wy[0..JYa)} when JYa is a window class
     int ystride;   // floats per record (4, 8 or 12), 0 when there is no packed table
     int floats;    // shared-memory floats consumed (multiple of 4)
@@ -220,6 +226,10 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     // bins without any valid sample sit at the two ends; give them a start that keeps xs / ys
     // monotone (their weights stay zero)
     const int xs_last = t.xs[pb], ys_last = t.ys[qb];
+    if (threadIdx.x == 0) {
+        const unsigned R = (unsigned)(t.Y1 - t.Y0 + 1);
+        stat[ST_MR] = (int)(R > 1 ? 0xFFFFFFFFu / R + 1u : 0u);
+    }
     __syncthreads();
     for (int p = threadIdx.x; p < Pw; p += kRaThreads)
         if (t.xs[p] == INT_MAX) t.xs[p] = p < pa ? t.X0 : xs_last;
@@ -230,6 +240,7 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     axis_fill(Pw, W, g.rsw, g.bw, g.gw, t.xs, t.wx);
     axis_fill(Ph, H, g.rsh, g.bh, g.gh, t.ys, t.wy);
     __syncthreads();
+    t.mR = (unsigned)stat[ST_MR];
     if (t.ystride) {
         for (int i = threadIdx.x; i < Ph * t.ystride; i += kRaThreads) {
             const int ph = i / t.ystride, f = i - ph * t.ystride;
@@ -396,97 +407,101 @@ __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward, fast path: strip walk with a register window of JW X-interpolated patch rows.
-// Requires JX <= JW and JY <= JW (tables are zero padded to JW rows) and the whole band in smem.
+// Forward, fast path: warp-autonomous strip walk.  Requires JX, JY <= JW (tables are zero padded
+// to JW rows), Pw / VEC <= 32 strips per channel and a channel patch that fits the warp's slice.
+// `cpw` channels are processed per warp pass (lanes = cpw x PwV strips).
 // ---------------------------------------------------------------------------------------------
 template <int VEC, int JW>
-__device__ void fwd_walk(const LevelDesc& Lv, const BucketDesc& B, const Tables t, float* patch,
-                         int batch, int i, int c0, int cs) {
-    const int Pw = B.pw, Ph = B.ph;
+__device__ void fwd_warp(const LevelDesc& Lv, const BucketDesc& B, const Tables t, float* wpatch, int cpw,
+                         int batch, int i, int c0, int nc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Pw = B.pw, Ph = B.ph, PwV = Pw / VEC;
     const int fw = t.X1 - t.X0 + 1, fws = fw + JW - 1;
     const int R = t.Y1 - t.Y0 + 1;
-    stage_patch(Lv, patch, batch, c0, cs, t.Y0, R, t.X0, fw, fws);
-    __syncthreads();
-    const int PwV = Pw / VEC;
-    const int nstrips = cs * PwV;
-    // split the pooled rows into nseg runs when that fills the CTA's thread slots better
-    int nseg = 1;
-    {
-        float best = cta_util(nstrips);
-        for (int ns = 2; ns <= 4; ++ns) {
-            const float u = cta_util(nstrips * ns);
-            if (Ph >= 8 * ns && u > best + 0.03f) { best = u; nseg = ns; }
-        }
-    }
-    const int seg_len = (Ph + nseg - 1) / nseg;
-    const int items = nstrips * nseg;
-    FastDiv fdV, fdS;
-    fdV.init(PwV);
-    fdS.init(nstrips);
-    const int* __restrict__ xs = t.xs;
-    const float* __restrict__ wx = t.wx;
+    const int sub = lane / PwV, pv = lane - sub * PwV;
+    const bool lane_on = sub < cpw;
     const float* __restrict__ ytab = t.ytab;
-    const int X0 = t.X0;
-    const long long osH = B.sH;
-    float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-    for (int it = threadIdx.x; it < items; it += kRaThreads) {
-        const int sg = fdS.div(it), s = it - sg * nstrips;
-        const int c = fdV.div(s), pv = s - c * PwV;
-        const int q0 = sg * seg_len, q1 = min(q0 + seg_len, Ph);
-        if (q0 >= q1) continue;
-        const float* pe[VEC];
-        float wxr[JW][VEC];
-        const float* pc = patch + c * R * fws;
+    // strip constants: the same for every channel of the RoI
+    int xo[VEC];
+    float wxr[JW][VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            pe[e] = pc + (xs[pv * VEC + e] - X0);
+    for (int e = 0; e < VEC; ++e) {
+        xo[e] = lane_on ? t.xs[pv * VEC + e] - t.X0 : 0;
 #pragma unroll
-            for (int j = 0; j < JW; ++j) wxr[j][e] = wx[j * Pw + pv * VEC + e];
-        }
-        float win[JW][VEC];
-        // X-interpolate patch row r (relative to Y0) for this strip's VEC columns
-        auto xrow = [&](int r, float (&v)[VEC]) {
+        for (int j = 0; j < JW; ++j) wxr[j][e] = lane_on ? t.wx[j * Pw + pv * VEC + e] : 0.0f;
+    }
+    const long long sC = Lv.sC, sH = Lv.sH, sW = Lv.sW, osH = B.sH;
+    const float* __restrict__ src0 = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * sC + (long long)t.Y0 * sH + (long long)t.X0 * sW;
+    float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC + (long long)(pv * VEC) * B.sW;
+    const float* mypatch = wpatch + sub * R * fws;
+    FastDiv fdR;
+    fdR.set(R, t.mR);
+    constexpr int PF = 8;  // patch rows in flight per lane while staging
+    for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
+        const int nact = min(cpw, nc - cb);
+        const int nrows = nact * R;
+        for (int x = lane; x < fws; x += 32) {
+            const float* __restrict__ sx = src0 + (long long)cb * sC + (long long)x * sW;
+            const bool live = x < fw;
+            for (int r0 = 0; r0 < nrows; r0 += PF) {
+                float v[PF];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
-            if (r < R) {
-                const int ro = r * fws;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-#pragma unroll
-                    for (int j = 0; j < JW; ++j) v[e] += wxr[j][e] * pe[e][ro + j];
+                for (int q = 0; q < PF; ++q) {
+                    const int row = r0 + q;
+                    v[q] = 0.0f;
+                    if (live && row < nrows) {
+                        const int c = fdR.div(row), r = row - c * R;
+                        v[q] = __ldg(sx + c * sC + r * sH);
+                    }
                 }
+#pragma unroll
+                for (int q = 0; q < PF; ++q)
+                    if (r0 + q < nrows) wpatch[(r0 + q) * fws + x] = v[q];
             }
-        };
-        int base;  // window row 0, relative to Y0
-        {
-            float wtmp[JW];
-            load_yrec<JW>(ytab, q0, base, wtmp);
         }
+        __syncwarp();
+        if (lane_on && sub < nact) {
+            float win[JW][VEC];
+            auto xrow = [&](int r, float (&v)[VEC]) {
 #pragma unroll
-        for (int j = 0; j < JW; ++j) xrow(base + j, win[j]);
-        float* o = obase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW + (long long)q0 * osH;
-        for (int ph = q0; ph < q1; ++ph) {
-            int y0;
-            float w[JW];
-            load_yrec<JW>(ytab, ph, y0, w);
-            while (base < y0) {
+                for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
+                if (r < R) {
+                    const float* pr = mypatch + r * fws;
 #pragma unroll
-                for (int j = 0; j + 1 < JW; ++j)
+                    for (int e = 0; e < VEC; ++e) {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
-                ++base;
-                xrow(base + JW - 1, win[JW - 1]);
+                        for (int j = 0; j < JW; ++j) v[e] += wxr[j][e] * pr[xo[e] + j];
+                    }
+                }
+            };
+            int base = 0;  // window row 0, relative to Y0 (ys[0] == Y0)
+#pragma unroll
+            for (int j = 0; j < JW; ++j) xrow(j, win[j]);
+            float* o = obase + (long long)(cb + sub) * B.sC;
+            for (int ph = 0; ph < Ph; ++ph) {
+                int y0;
+                float w[JW];
+                load_yrec<JW>(ytab, ph, y0, w);
+                while (base < y0) {
+#pragma unroll
+                    for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
+                    ++base;
+                    xrow(base + JW - 1, win[JW - 1]);
+                }
+                float acc[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] = w[0] * win[0][e];
+#pragma unroll
+                for (int j = 1; j < JW; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[e] += w[j] * win[j][e];
+                st_stream_vec<VEC>(o, acc);
+                o += osH;
             }
-            float acc[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] = w[0] * win[0][e];
-#pragma unroll
-            for (int j = 1; j < JW; ++j)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[e] += w[j] * win[j][e];
-            st_stream_vec<VEC>(o, acc);
-            o += osH;
         }
+        __syncwarp();
     }
 }
 
@@ -581,17 +596,18 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     float* tile = smem + t.floats;
     const int Rfull = t.Y1 - t.Y0 + 1;
     const int wc = window_class(max(t.JX, t.JY));
-    if (wc && (long long)Rfull * (fw + wc - 1) <= avail) {
-        // fast path: only the patch lives in shared memory
-        const int cs_max = min(c1 - c0, avail / (Rfull * (fw + wc - 1)));
-        for (int c = c0; c < c1; c += cs_max) {
-            const int cs = min(cs_max, c1 - c);
-            if (wc == 2) fwd_walk<VEC, 2>(Lv, B, t, tile, batch, un.i, c, cs);
-            else if (wc == 4) fwd_walk<VEC, 4>(Lv, B, t, tile, batch, un.i, c, cs);
-            else fwd_walk<VEC, 8>(Lv, B, t, tile, batch, un.i, c, cs);
-            __syncthreads();
+    const int PwV = B.pw / VEC;
+    if (wc && PwV <= 32) {
+        // fast path: every warp gets a private slice of shared memory for its channels' patches
+        const int slice = (avail / kRaWarps) & ~3;
+        const int cpw = min(32 / PwV, slice / (Rfull * (fw + wc - 1)));
+        if (cpw >= 1) {
+            float* wpatch = tile + (threadIdx.x >> 5) * slice;
+            if (wc == 2) fwd_warp<VEC, 2>(Lv, B, t, wpatch, cpw, batch, un.i, c0, c1 - c0);
+            else if (wc == 4) fwd_warp<VEC, 4>(Lv, B, t, wpatch, cpw, batch, un.i, c0, c1 - c0);
+            else fwd_warp<VEC, 8>(Lv, B, t, wpatch, cpw, batch, un.i, c0, c1 - c0);
+            return;
         }
-        return;
     }
     const int per_row = fw + B.pw;
     if ((long long)Rfull * per_row <= avail) {
@@ -618,40 +634,74 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // ---------------------------------------------------------------------------------------------
 // Backward unit
 // ---------------------------------------------------------------------------------------------
-// Column pass, fast path: a thread owns (channel, VEC adjacent pooled columns) and walks all
-// pooled rows top to bottom; the JW band rows it is accumulating live in registers, completed
-// rows retire to U[c][r][pw] with one plain vector store (the strip owns those columns, so no
-// atomics and no zero-init are needed: every row 0..R-1 is retired exactly once).
+// Fast path: warp-autonomous strip walk.  Lanes = cpw channels x PwV column strips; every lane
+// walks all pooled rows top to bottom with the JW band rows it is accumulating in registers.
+// All lanes of a warp see the same pooled-row sequence, so a band row completes for the whole
+// warp at once: it is dropped into the warp's row buffer, the patch-gradient row is gathered
+// from it (lane = feature column) and reduced into the gradient map with one RED per element.
 template <int VEC, int JW>
-__device__ void bwd_walk(const BucketDesc& B, const Tables t, float* U, int i, int c0, int cs) {
-    const int Pw = B.pw, Ph = B.ph;
-    const int PwV = Pw / VEC;
+__device__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const Tables t, const int* plo,
+                         const int* pcnt, const float* wxT, int TW, float* rowbuf, int cpw,
+                         int batch, int i, int c0, int nc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Pw = B.pw, Ph = B.ph, PwV = Pw / VEC;
+    const int fw = t.X1 - t.X0 + 1;
     const int R = t.Y1 - t.Y0 + 1;
-    const int nstrips = cs * PwV;
-    FastDiv fdV;
-    fdV.init(PwV);
+    const int sub = lane / PwV, pv = lane - sub * PwV;
+    const bool lane_on = sub < cpw;
     const float* __restrict__ ytab = t.ytab;
-    const long long gsH = B.sH;
-    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+    const long long gsH = B.sH, dsC = Lv.sC, dsH = Lv.sH, dsW = Lv.sW;
+    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC + (long long)(pv * VEC) * B.sW;
+    float* dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * dsC + (long long)t.Y0 * dsH + (long long)t.X0 * dsW;
+    float* myrow = rowbuf + sub * Pw + pv * VEC;
     constexpr int PF = (JW == 8) ? 2 : 4;  // pooled rows per batch; the next batch is in flight while this one is used
-    for (int s = threadIdx.x; s < nstrips; s += kRaThreads) {
-        const int c = fdV.div(s), pv = s - c * PwV;
-        const float* gp = gbase + (long long)c * B.sC + (long long)(pv * VEC) * B.sW;
-        float* uc = U + c * R * Pw + pv * VEC;
+    for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
+        const int nact = min(cpw, nc - cb);
+        const bool on = lane_on && sub < nact;
+        const float* gp = gbase + (long long)(cb + sub) * B.sC;
+        float* dst = dbase + (long long)cb * dsC;
         float acc[JW][VEC];
 #pragma unroll
         for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
+        // band row `r` (relative to Y0) is complete: reduce it into the gradient map
+        auto retire = [&](int r, const float (&v)[VEC]) {
+            if (r >= R) return;
+            if (on) {
+                if (VEC == 1) myrow[0] = v[0];
+                else if (VEC == 2) *reinterpret_cast<float2*>(myrow) = make_float2(v[0], v[1 % VEC]);
+                else *reinterpret_cast<float4*>(myrow) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+            }
+            __syncwarp();
+            for (int s2 = 0; s2 < nact; ++s2) {
+                const float* ur = rowbuf + s2 * Pw;
+                for (int x = lane; x < fw; x += 32) {
+                    const float* up = ur + plo[x];
+                    const float* wp = wxT + x * TW;
+                    const int n = pcnt[x];
+                    float a = 0.0f;
+                    for (int q = 0; q < n; ++q) a += wp[q] * up[q];
+                    if (a != 0.0f) atomicAdd(dst + (long long)s2 * dsC + (long long)r * dsH + (long long)x * dsW, a);
+                }
+            }
+            __syncwarp();
+        };
         int base = 0;  // window row 0 relative to Y0
         float cur[PF][VEC], nxt[PF][VEC];
 #pragma unroll
-        for (int u = 0; u < PF; ++u)
-            if (u < Ph) ldg_stream_vec<VEC>(gp + (long long)u * gsH, cur[u]);
+        for (int u = 0; u < PF; ++u) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) cur[u][e] = 0.0f;
+            if (on && u < Ph) ldg_stream_vec<VEC>(gp + (long long)u * gsH, cur[u]);
+        }
         for (int ph0 = 0; ph0 < Ph; ph0 += PF) {
 #pragma unroll
-            for (int u = 0; u < PF; ++u)
-                if (ph0 + PF + u < Ph) ldg_stream_vec<VEC>(gp + (long long)(ph0 + PF + u) * gsH, nxt[u]);
+            for (int u = 0; u < PF; ++u) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) nxt[u][e] = 0.0f;
+                if (on && ph0 + PF + u < Ph) ldg_stream_vec<VEC>(gp + (long long)(ph0 + PF + u) * gsH, nxt[u]);
+            }
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 const int ph = ph0 + u;
@@ -660,11 +710,7 @@ __device__ void bwd_walk(const BucketDesc& B, const Tables t, float* U, int i, i
                     float w[JW];
                     load_yrec<JW>(ytab, ph, y0, w);
                     while (base < y0) {
-                        if (base < R) {
-                            if (VEC == 1) uc[base * Pw] = acc[0][0];
-                            else if (VEC == 2) *reinterpret_cast<float2*>(uc + base * Pw) = make_float2(acc[0][0], acc[0][1 % VEC]);
-                            else *reinterpret_cast<float4*>(uc + base * Pw) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
-                        }
+                        retire(base, acc[0]);
 #pragma unroll
                         for (int j = 0; j + 1 < JW; ++j)
 #pragma unroll
@@ -684,18 +730,8 @@ __device__ void bwd_walk(const BucketDesc& B, const Tables t, float* U, int i, i
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) cur[u][e] = nxt[u][e];
         }
-        // retire the window, then zero any band rows below it (none in practice)
 #pragma unroll
-        for (int j = 0; j < JW; ++j) {
-            const int r = base + j;
-            if (r < R) {
-                if (VEC == 1) uc[r * Pw] = acc[j][0];
-                else if (VEC == 2) *reinterpret_cast<float2*>(uc + r * Pw) = make_float2(acc[j][0], acc[j][1 % VEC]);
-                else *reinterpret_cast<float4*>(uc + r * Pw) = make_float4(acc[j][0], acc[j][1 % VEC], acc[j][2 % VEC], acc[j][3 % VEC]);
-            }
-        }
-        for (int r = base + JW; r < R; ++r)
-            for (int e = 0; e < VEC; ++e) uc[r * Pw + e] = 0.0f;
+        for (int j = 0; j < JW; ++j) retire(base + j, acc[j]);
     }
 }
 
@@ -778,7 +814,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     // it, and their weights wxT[x][q]
     int* plo = reinterpret_cast<int*>(smem + (fits ? t.floats : 0));
     int* pcnt = plo + fw;
-    int* s_tw = stat + ST_PA;  // reuse a stat slot for the max range length
+    int* s_tw = stat + ST_TW;
     if (fits && 2 * fw <= p.smem_floats - t.floats) {
         if (threadIdx.x == 0) *s_tw = 0;
         __syncthreads();
@@ -803,10 +839,10 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
         }
         __syncthreads();
     }
-    const int TW = fits ? *s_tw : 0;
+    const int TW = fits ? (*s_tw | 1) : 0;  // odd stride: conflict-free column-wise reads
     const int extra = (2 * fw + fw * TW + 3) & ~3;
     const long long avail = (long long)p.smem_floats - (fits ? t.floats : 0) - extra;
-    if (!fits || (long long)R * B.pw > avail) {
+    if (!fits || avail < (long long)kRaWarps * (32 * VEC + 4)) {
         direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
         return;
     }
@@ -820,27 +856,32 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
         }
         wxT[e] = w;
     }
+    const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
+    {
+        const int PwV = B.pw / VEC;
+        if (wc && PwV <= 32) {
+            // fast path: warp-private row buffers, no CTA-wide barrier after this point
+            const int cpw = 32 / PwV;
+            __syncthreads();
+            float* rowbuf = smem + t.floats + extra + (threadIdx.x >> 5) * ((cpw * B.pw + 3) & ~3);
+            if (wc == 2) bwd_warp<VEC, 2>(Lv, B, t, plo, pcnt, wxT, TW, rowbuf, cpw, batch, un.i, c0, c1 - c0);
+            else if (wc == 4) bwd_warp<VEC, 4>(Lv, B, t, plo, pcnt, wxT, TW, rowbuf, cpw, batch, un.i, c0, c1 - c0);
+            else bwd_warp<VEC, 8>(Lv, B, t, plo, pcnt, wxT, TW, rowbuf, cpw, batch, un.i, c0, c1 - c0);
+            return;
+        }
+    }
     float* U = smem + t.floats + extra;
     const int per_c = R * B.pw;
-    int cs_max = min(c1 - c0, (int)(avail / per_c));
-    {   // a strip owns its columns for the whole walk, so pick the group size that fills the CTA best
-        const int PwV = B.pw / VEC;
-        int best_cs = cs_max;
-        float best = cta_util(cs_max * PwV);
-        for (int cs = cs_max - 1; cs >= 1 && cs >= cs_max - 12; --cs) {
-            const float u = cta_util(cs * PwV) * (cs * 2 >= cs_max ? 1.0f : 0.9f);
-            if (u > best + 0.04f) { best = u; best_cs = cs; }
-        }
-        cs_max = best_cs;
+    if (per_c > avail) {
+        __syncthreads();
+        direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
+        return;
     }
-    const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
+    const int cs_max = min(c1 - c0, (int)(avail / per_c));
     __syncthreads();
     for (int c = c0; c < c1; c += cs_max) {
         const int cs = min(cs_max, c1 - c);
-        if (wc == 2) bwd_walk<VEC, 2>(B, t, U, un.i, c, cs);
-        else if (wc == 4) bwd_walk<VEC, 4>(B, t, U, un.i, c, cs);
-        else if (wc == 8) bwd_walk<VEC, 8>(B, t, U, un.i, c, cs);
-        else bwd_column_pass_generic<VEC>(B, t, U, un.i, c, cs);
+        bwd_column_pass_generic<VEC>(B, t, U, un.i, c, cs);
         __syncthreads();
         bwd_row_pass(Lv, B, t, U, plo, pcnt, wxT, TW, batch, c, cs);
         __syncthreads();
@@ -851,7 +892,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __launch_bounds__(kRaThreads, 2) ra_kernel(const __grid_constant__ RaParams p) {
+__global__ void __launch_bounds__(kRaThreads, BWD ? 3 : 2) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
@@ -924,12 +965,13 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
         d.sH = out_strides[4 * b + 2];
         d.sW = out_strides[4 * b + 3];
         if (d.ph < 1 || d.pw < 1 || d.ph >= (1 << 15) || d.pw >= (1 << 15)) return DM_EINVAL;
-        // ~1 MB of pooled output per work unit: the banded tables are rebuilt per unit
-        int cg = 393216 / (d.ph * d.pw);
+        // a few MB of pooled output per work unit: the banded tables are rebuilt per unit and the
+        // warps of a CTA only re-synchronise at unit boundaries
+        int cg = 1572864 / (d.ph * d.pw);
         int pw2 = 1;
         while (pw2 * 2 <= cg) pw2 *= 2;
         cg = cg < 1 ? 1 : pw2;
-        cg = cg < 4 ? 4 : (cg > 256 ? 256 : cg);
+        cg = cg < 16 ? 16 : (cg > 256 ? 256 : cg);
         cg = env_int("DM_RA_CG", 0) > 0 ? env_int("DM_RA_CG", 0) : cg;
         if (cg > p.C) cg = p.C;
         d.cg = cg;
@@ -962,7 +1004,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
 
 template <bool BWD>
 static int launch(RaParams& p, cudaStream_t st, const char* where) {
-    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", 100);
+    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 64 : 100);
     const int smem_bytes = smem_kb * 1024;
     p.smem_floats = smem_bytes / 4;
     DM_CUDA_CHECK(cudaFuncSetAttribute(ra_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
