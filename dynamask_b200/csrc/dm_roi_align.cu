@@ -129,6 +129,18 @@ __device__ __forceinline__ void st_stream_vec(float* p, const float (&a)[VEC]) {
     else st_stream(p, a[0]);
 }
 
+// Ampere-style asynchronous global->shared copies (LDGSTS): used as a register-free prefetch ring.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // Banded weight tables of one RoI, staged in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -636,104 +648,144 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // ---------------------------------------------------------------------------------------------
 // Fast path: warp-autonomous strip walk.  Lanes = cpw channels x PwV column strips; every lane
 // walks all pooled rows top to bottom with the JW band rows it is accumulating in registers.
-// All lanes of a warp see the same pooled-row sequence, so a band row completes for the whole
-// warp at once: it is dropped into the warp's row buffer, the patch-gradient row is gathered
-// from it (lane = feature column) and reduced into the gradient map with one RED per element.
+// grad_out rows arrive through a per-lane cp.async ring (kRing-1 rows in flight per lane, no
+// registers tied up).  All lanes of a warp see the same pooled-row sequence, so a band row
+// completes for the whole warp at once: it is dropped into the warp's row buffer, the
+// patch-gradient row is gathered from it (lane = feature column, its transposed X weights held in
+// registers) and reduced into the gradient map with one RED per element.
+constexpr int kRing = 8;   // ring depth of the grad_out prefetch, in pooled rows
+constexpr int kTWR = 16;   // transposed X weights a lane keeps in registers
+
+// dot product of a lane's register weights with a shared-memory row segment; NT is a compile-time
+// term count (weights beyond the lane's real count are zero and the row buffer is zero padded, so
+// no predicate is needed)
+template <int NT>
+__device__ __forceinline__ float gather_terms(const float (&wq)[kTWR], const float* up) {
+    float a = 0.0f;
+#pragma unroll
+    for (int q = 0; q < NT; ++q) a += wq[q] * up[q];
+    return a;
+}
+
+// Requirements (checked by the caller): unit inner stride of grad_out and of the gradient map,
+// Pw / VEC <= 32, JY <= JW.
 template <int VEC, int JW>
-__device__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const Tables t, const int* plo,
-                         const int* pcnt, const float* wxT, int TW, float* rowbuf, int cpw,
-                         int batch, int i, int c0, int nc) {
+__device__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const float* __restrict__ ytab,
+                         int X0, int Y0, int fw, int R, const int* plo, const int* pcnt,
+                         const float* wxT, int TW, float* wsm, int cpw, int batch, int i, int c0, int nc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Pw = B.pw, Ph = B.ph, PwV = Pw / VEC;
-    const int fw = t.X1 - t.X0 + 1;
-    const int R = t.Y1 - t.Y0 + 1;
     const int sub = lane / PwV, pv = lane - sub * PwV;
     const bool lane_on = sub < cpw;
-    const float* __restrict__ ytab = t.ytab;
-    const long long gsH = B.sH, dsC = Lv.sC, dsH = Lv.sH, dsW = Lv.sW;
-    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC + (long long)(pv * VEC) * B.sW;
-    float* dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * dsC + (long long)t.Y0 * dsH + (long long)t.X0 * dsW;
+    const long long gsH = B.sH, gsC = B.sC, dsC = Lv.sC, dsH = Lv.sH;
+    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * gsC + pv * VEC;
+    float* dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * dsC + (long long)Y0 * dsH + X0 + lane;
+    // warp-private shared memory: [kRing][32 lanes][VEC] prefetch ring, then [cpw][Pw] row buffer
+    // followed by kTWR zeros
+    float* ring = wsm + lane * VEC;
+    float* rowbuf = wsm + kRing * 32 * VEC;
     float* myrow = rowbuf + sub * Pw + pv * VEC;
-    constexpr int PF = (JW == 8) ? 2 : 4;  // pooled rows per batch; the next batch is in flight while this one is used
+    const int rb_n = cpw * Pw;
+    for (int q = lane; q < kTWR; q += 32) rowbuf[rb_n + q] = 0.0f;
+    // this lane's feature column when it acts as x-owner, with its weights in registers
+    const int xn = lane < fw ? pcnt[lane] : 0;
+    const float* upx = rowbuf + (lane < fw ? plo[lane] : 0);
+    float wq[kTWR];
+#pragma unroll
+    for (int q = 0; q < kTWR; ++q) wq[q] = (q < xn) ? wxT[lane * TW + q] : 0.0f;
+    const int nt_class = TW <= 4 ? 0 : (TW <= 8 ? 1 : 2);
+    const bool wide = fw > 32 || TW > kTWR;  // rare: extra columns / terms handled by slow loops
+    __syncwarp();
+
     for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
-        const float* gp = gbase + (long long)(cb + sub) * B.sC;
-        float* dst = dbase + (long long)cb * dsC;
+        const float* gnext = gbase + (long long)(cb + sub) * gsC;  // next pooled row to prefetch
+        float* drow = dbase + (long long)cb * dsC;                 // gradient-map row being retired
         float acc[JW][VEC];
 #pragma unroll
         for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
-        // band row `r` (relative to Y0) is complete: reduce it into the gradient map
-        auto retire = [&](int r, const float (&v)[VEC]) {
-            if (r >= R) return;
-            if (on) {
-                if (VEC == 1) myrow[0] = v[0];
-                else if (VEC == 2) *reinterpret_cast<float2*>(myrow) = make_float2(v[0], v[1 % VEC]);
-                else *reinterpret_cast<float4*>(myrow) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
-            }
-            __syncwarp();
-            for (int s2 = 0; s2 < nact; ++s2) {
-                const float* ur = rowbuf + s2 * Pw;
-                for (int x = lane; x < fw; x += 32) {
-                    const float* up = ur + plo[x];
-                    const float* wp = wxT + x * TW;
-                    const int n = pcnt[x];
-                    float a = 0.0f;
-                    for (int q = 0; q < n; ++q) a += wp[q] * up[q];
-                    if (a != 0.0f) atomicAdd(dst + (long long)s2 * dsC + (long long)r * dsH + (long long)x * dsW, a);
-                }
-            }
-            __syncwarp();
-        };
-        int base = 0;  // window row 0 relative to Y0
-        float cur[PF][VEC], nxt[PF][VEC];
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) cur[u][e] = 0.0f;
-            if (on && u < Ph) ldg_stream_vec<VEC>(gp + (long long)u * gsH, cur[u]);
+        for (int d = 0; d < kRing - 1; ++d) {
+            if (on && d < Ph) cp_async<VEC * 4>(ring + d * 32 * VEC, gnext);
+            gnext += gsH;
+            cp_async_commit();
         }
-        for (int ph0 = 0; ph0 < Ph; ph0 += PF) {
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) nxt[u][e] = 0.0f;
-                if (on && ph0 + PF + u < Ph) ldg_stream_vec<VEC>(gp + (long long)(ph0 + PF + u) * gsH, nxt[u]);
+        int base = 0;              // window row 0 relative to Y0
+        int slot_w = kRing - 1;    // ring slot the next prefetch lands in
+        int slot_r = 0;            // ring slot holding pooled row `ph`
+        for (int ph = 0; ph <= Ph; ++ph) {
+            int y0 = R;  // sentinel pass (ph == Ph) retires everything that is left
+            float w[JW];
+            if (ph < Ph) {
+                if (on && ph + kRing - 1 < Ph) cp_async<VEC * 4>(ring + slot_w * 32 * VEC, gnext);
+                gnext += gsH;
+                slot_w = (slot_w + 1) & (kRing - 1);
+                cp_async_commit();
+                load_yrec<JW>(ytab, ph, y0, w);
             }
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int ph = ph0 + u;
-                if (ph < Ph) {
-                    int y0;
-                    float w[JW];
-                    load_yrec<JW>(ytab, ph, y0, w);
-                    while (base < y0) {
-                        retire(base, acc[0]);
-#pragma unroll
-                        for (int j = 0; j + 1 < JW; ++j)
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
-                        ++base;
+            while (base < y0) {
+                // band row `base` is complete for every lane of the warp: reduce it into the map
+                if (on) {
+                    if (VEC == 1) myrow[0] = acc[0][0];
+                    else if (VEC == 2) *reinterpret_cast<float2*>(myrow) = make_float2(acc[0][0], acc[0][1 % VEC]);
+                    else *reinterpret_cast<float4*>(myrow) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
+                }
+                __syncwarp();
+                {
+                    const float* up = upx;
+                    float* dp = drow;
+                    for (int s2 = 0; s2 < nact; ++s2) {
+                        float a;
+                        if (nt_class == 0) a = gather_terms<4>(wq, up);
+                        else if (nt_class == 1) a = gather_terms<8>(wq, up);
+                        else a = gather_terms<kTWR>(wq, up);
+                        if (wide) {
+                            for (int q = kTWR; q < xn; ++q) a += wxT[lane * TW + q] * up[q];
+                            for (int x = lane + 32; x < fw; x += 32) {
+                                const float* u2 = rowbuf + s2 * Pw + plo[x];
+                                const float* wp = wxT + x * TW;
+                                const int n = pcnt[x];
+                                float a2 = 0.0f;
+                                for (int q = 0; q < n; ++q) a2 += wp[q] * u2[q];
+                                if (a2 != 0.0f) atomicAdd(dp + (x - lane), a2);
+                            }
+                        }
+                        if (a != 0.0f) atomicAdd(dp, a);
+                        up += Pw;
+                        dp += dsC;
                     }
-#pragma unroll
-                    for (int j = 0; j < JW; ++j)
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * cur[u][e];
                 }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
+                ++base;
+                drow += dsH;
             }
+            if (ph < Ph) {
+                cp_async_wait<kRing - 1>();  // this lane's copy of pooled row `ph` has landed
+                float gv[VEC];
+                ld_vec<VEC>(ring + slot_r * 32 * VEC, gv);
+                slot_r = (slot_r + 1) & (kRing - 1);
 #pragma unroll
-            for (int u = 0; u < PF; ++u)
+                for (int j = 0; j < JW; ++j)
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) cur[u][e] = nxt[u][e];
+                    for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * gv[e];
+            }
         }
-#pragma unroll
-        for (int j = 0; j < JW; ++j) retire(base + j, acc[j]);
+        cp_async_wait<0>();
+        __syncwarp();
     }
 }
+
+// shared-memory floats a warp needs on the fast path: ring + row buffer + zero pad
+__host__ __device__ constexpr int kBwdWarpFloats(int vec) { return kRing * 32 * vec + 32 * vec + kTWR + 4; }
 
 // Column pass, generic path for bands taller than 8 rows: shared-memory reductions into a zeroed U.
 template <int VEC>
@@ -842,7 +894,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int TW = fits ? (*s_tw | 1) : 0;  // odd stride: conflict-free column-wise reads
     const int extra = (2 * fw + fw * TW + 3) & ~3;
     const long long avail = (long long)p.smem_floats - (fits ? t.floats : 0) - extra;
-    if (!fits || avail < (long long)kRaWarps * (32 * VEC + 4)) {
+    if (!fits || avail < (long long)kRaWarps * kBwdWarpFloats(VEC)) {
         direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
         return;
     }
@@ -859,14 +911,14 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
     {
         const int PwV = B.pw / VEC;
-        if (wc && PwV <= 32) {
-            // fast path: warp-private row buffers, no CTA-wide barrier after this point
+        if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1) {
+            // fast path: warp-private ring + row buffer, no CTA-wide barrier after this point
             const int cpw = 32 / PwV;
             __syncthreads();
-            float* rowbuf = smem + t.floats + extra + (threadIdx.x >> 5) * ((cpw * B.pw + 3) & ~3);
-            if (wc == 2) bwd_warp<VEC, 2>(Lv, B, t, plo, pcnt, wxT, TW, rowbuf, cpw, batch, un.i, c0, c1 - c0);
-            else if (wc == 4) bwd_warp<VEC, 4>(Lv, B, t, plo, pcnt, wxT, TW, rowbuf, cpw, batch, un.i, c0, c1 - c0);
-            else bwd_warp<VEC, 8>(Lv, B, t, plo, pcnt, wxT, TW, rowbuf, cpw, batch, un.i, c0, c1 - c0);
+            float* wsm = smem + t.floats + extra + (threadIdx.x >> 5) * kBwdWarpFloats(VEC);
+            if (wc == 2) bwd_warp<VEC, 2>(Lv, B, t.ytab, t.X0, t.Y0, fw, R, plo, pcnt, wxT, TW, wsm, cpw, batch, un.i, c0, c1 - c0);
+            else if (wc == 4) bwd_warp<VEC, 4>(Lv, B, t.ytab, t.X0, t.Y0, fw, R, plo, pcnt, wxT, TW, wsm, cpw, batch, un.i, c0, c1 - c0);
+            else bwd_warp<VEC, 8>(Lv, B, t.ytab, t.X0, t.Y0, fw, R, plo, pcnt, wxT, TW, wsm, cpw, batch, un.i, c0, c1 - c0);
             return;
         }
     }
@@ -1004,7 +1056,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
 
 template <bool BWD>
 static int launch(RaParams& p, cudaStream_t st, const char* where) {
-    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 64 : 100);
+    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 72 : 100);
     const int smem_bytes = smem_kb * 1024;
     p.smem_floats = smem_bytes / 4;
     DM_CUDA_CHECK(cudaFuncSetAttribute(ra_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
