@@ -609,7 +609,7 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int Rfull = t.Y1 - t.Y0 + 1;
     const int wc = window_class(max(t.JX, t.JY));
     const int PwV = B.pw / VEC;
-    if (wc && PwV <= 32) {
+    if (wc && PwV <= 32 && B.sW == 1) {
         // fast path: every warp gets a private slice of shared memory for its channels' patches
         const int slice = (avail / kRaWarps) & ~3;
         const int cpw = min(32 / PwV, slice / (Rfull * (fw + wc - 1)));
@@ -656,52 +656,58 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 constexpr int kRing = 8;   // ring depth of the grad_out prefetch, in pooled rows
 constexpr int kTWR = 16;   // transposed X weights a lane keeps in registers
 
-// dot product of a lane's register weights with a shared-memory row segment; NT is a compile-time
-// term count (weights beyond the lane's real count are zero and the row buffer is zero padded, so
-// no predicate is needed)
-template <int NT>
-__device__ __forceinline__ float gather_terms(const float (&wq)[kTWR], const float* up) {
-    float a = 0.0f;
-#pragma unroll
-    for (int q = 0; q < NT; ++q) a += wq[q] * up[q];
-    return a;
+// Slow retire for geometries with more than 32 patch columns or more than NT taps per column.
+__device__ __noinline__ void bwd_retire_wide(const float* rowbuf, int Pw, int nact, int fw, int nt,
+                                             const int* plo, const int* pcnt, const float* wxT, int TW,
+                                             float* drow0, long long dsC, int lane) {
+    for (int s2 = 0; s2 < nact; ++s2) {
+        const float* ur = rowbuf + s2 * Pw;
+        float* drow = drow0 + s2 * dsC;   // points at column 0 of the patch row
+        for (int x = lane; x < fw; x += 32) {
+            const float* up = ur + plo[x];
+            const float* wp = wxT + x * TW;
+            const int n = pcnt[x];
+            float a = 0.0f;
+            for (int q = (x < 32 ? nt : 0); q < n; ++q) a += wp[q] * up[q];
+            if (a != 0.0f) atomicAdd(drow + x, a);
+        }
+    }
 }
 
-// Requirements (checked by the caller): unit inner stride of grad_out and of the gradient map,
-// Pw / VEC <= 32, JY <= JW.
-template <int VEC, int JW>
-__device__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const float* __restrict__ ytab,
-                         int X0, int Y0, int fw, int R, const int* plo, const int* pcnt,
-                         const float* wxT, int TW, float* wsm, int cpw, int batch, int i, int c0, int nc) {
+// The hot loop lives in a __noinline__ function taking plain scalars so that every instantiation
+// gets its own register allocation and nothing is re-derived from the kernel-parameter structs
+// inside the loop.  Requirements (checked by the caller): unit inner stride of grad_out and of the
+// gradient map, Pw / VEC <= 32, JY <= JW.  NT = transposed X taps a lane keeps in registers.
+template <int VEC, int JW, int NT>
+__device__ __noinline__ void bwd_warp_core(const float* gbase, long long gsC, long long gsH, float* dbase,
+                                           long long dsC, long long dsH, const float* __restrict__ ytab,
+                                           int Ph, int Pw, int R, int fw, const int* plo, const int* pcnt,
+                                           const float* wxT, int TW, float* wsm, int cpw, int nc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Pw = B.pw, Ph = B.ph, PwV = Pw / VEC;
+    const int PwV = Pw / VEC;
     const int sub = lane / PwV, pv = lane - sub * PwV;
     const bool lane_on = sub < cpw;
-    const long long gsH = B.sH, gsC = B.sC, dsC = Lv.sC, dsH = Lv.sH;
-    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * gsC + pv * VEC;
-    float* dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * dsC + (long long)Y0 * dsH + X0 + lane;
+    gbase += pv * VEC;
     // warp-private shared memory: [kRing][32 lanes][VEC] prefetch ring, then [cpw][Pw] row buffer
     // followed by kTWR zeros
-    float* ring = wsm + lane * VEC;
-    float* rowbuf = wsm + kRing * 32 * VEC;
-    float* myrow = rowbuf + sub * Pw + pv * VEC;
-    const int rb_n = cpw * Pw;
-    for (int q = lane; q < kTWR; q += 32) rowbuf[rb_n + q] = 0.0f;
-    // this lane's feature column when it acts as x-owner, with its weights in registers
+    float* const ring = wsm + lane * VEC;
+    float* const rowbuf = wsm + kRing * 32 * VEC;
+    float* const myrow = rowbuf + sub * Pw + pv * VEC;
+    for (int q = lane; q < kTWR; q += 32) rowbuf[cpw * Pw + q] = 0.0f;
+    // this lane's feature column when it acts as x-owner, with its taps in registers
     const int xn = lane < fw ? pcnt[lane] : 0;
-    const float* upx = rowbuf + (lane < fw ? plo[lane] : 0);
-    float wq[kTWR];
+    const float* const upx = rowbuf + (lane < fw ? plo[lane] : 0);
+    float wq[NT];
 #pragma unroll
-    for (int q = 0; q < kTWR; ++q) wq[q] = (q < xn) ? wxT[lane * TW + q] : 0.0f;
-    const int nt_class = TW <= 4 ? 0 : (TW <= 8 ? 1 : 2);
-    const bool wide = fw > 32 || TW > kTWR;  // rare: extra columns / terms handled by slow loops
+    for (int q = 0; q < NT; ++q) wq[q] = (q < xn) ? wxT[lane * TW + q] : 0.0f;
+    const bool wide = fw > 32 || TW > NT;
     __syncwarp();
 
     for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
-        const float* gnext = gbase + (long long)(cb + sub) * gsC;  // next pooled row to prefetch
-        float* drow = dbase + (long long)cb * dsC;                 // gradient-map row being retired
+        const float* gnext = gbase + (cb + sub) * gsC;  // next pooled row to prefetch
+        float* drow = dbase + cb * dsC;                 // gradient-map row being retired (+lane)
         float acc[JW][VEC];
 #pragma unroll
         for (int j = 0; j < JW; ++j)
@@ -713,75 +719,81 @@ __device__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const float* 
             gnext += gsH;
             cp_async_commit();
         }
+        // band row `base` is complete for every lane of the warp: reduce it into the map
+        auto retire = [&]() {
+            if (on) {
+                if (VEC == 1) myrow[0] = acc[0][0];
+                else if (VEC == 2) *reinterpret_cast<float2*>(myrow) = make_float2(acc[0][0], acc[0][1 % VEC]);
+                else *reinterpret_cast<float4*>(myrow) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
+            }
+            __syncwarp();
+            const float* up = upx;
+            float* dp = drow;
+            for (int s2 = 0; s2 < nact; ++s2) {
+                float a = 0.0f;
+#pragma unroll
+                for (int q = 0; q < NT; ++q) a += wq[q] * up[q];
+                if (a != 0.0f) atomicAdd(dp, a);
+                up += Pw;
+                dp += dsC;
+            }
+            if (wide) bwd_retire_wide(rowbuf, Pw, nact, fw, NT, plo, pcnt, wxT, TW, drow - lane, dsC, lane);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
+            drow += dsH;
+        };
         int base = 0;              // window row 0 relative to Y0
         int slot_w = kRing - 1;    // ring slot the next prefetch lands in
         int slot_r = 0;            // ring slot holding pooled row `ph`
-        for (int ph = 0; ph <= Ph; ++ph) {
-            int y0 = R;  // sentinel pass (ph == Ph) retires everything that is left
+        const int Ppre = Ph - (kRing - 1);
+        for (int ph = 0; ph < Ph; ++ph) {
+            if (on && ph < Ppre) cp_async<VEC * 4>(ring + slot_w * 32 * VEC, gnext);
+            gnext += gsH;
+            slot_w = (slot_w + 1) & (kRing - 1);
+            cp_async_commit();
+            int y0;
             float w[JW];
-            if (ph < Ph) {
-                if (on && ph + kRing - 1 < Ph) cp_async<VEC * 4>(ring + slot_w * 32 * VEC, gnext);
-                gnext += gsH;
-                slot_w = (slot_w + 1) & (kRing - 1);
-                cp_async_commit();
-                load_yrec<JW>(ytab, ph, y0, w);
-            }
+            load_yrec<JW>(ytab, ph, y0, w);
             while (base < y0) {
-                // band row `base` is complete for every lane of the warp: reduce it into the map
-                if (on) {
-                    if (VEC == 1) myrow[0] = acc[0][0];
-                    else if (VEC == 2) *reinterpret_cast<float2*>(myrow) = make_float2(acc[0][0], acc[0][1 % VEC]);
-                    else *reinterpret_cast<float4*>(myrow) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
-                }
-                __syncwarp();
-                {
-                    const float* up = upx;
-                    float* dp = drow;
-                    for (int s2 = 0; s2 < nact; ++s2) {
-                        float a;
-                        if (nt_class == 0) a = gather_terms<4>(wq, up);
-                        else if (nt_class == 1) a = gather_terms<8>(wq, up);
-                        else a = gather_terms<kTWR>(wq, up);
-                        if (wide) {
-                            for (int q = kTWR; q < xn; ++q) a += wxT[lane * TW + q] * up[q];
-                            for (int x = lane + 32; x < fw; x += 32) {
-                                const float* u2 = rowbuf + s2 * Pw + plo[x];
-                                const float* wp = wxT + x * TW;
-                                const int n = pcnt[x];
-                                float a2 = 0.0f;
-                                for (int q = 0; q < n; ++q) a2 += wp[q] * u2[q];
-                                if (a2 != 0.0f) atomicAdd(dp + (x - lane), a2);
-                            }
-                        }
-                        if (a != 0.0f) atomicAdd(dp, a);
-                        up += Pw;
-                        dp += dsC;
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j + 1 < JW; ++j)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
+                retire();
                 ++base;
-                drow += dsH;
             }
-            if (ph < Ph) {
-                cp_async_wait<kRing - 1>();  // this lane's copy of pooled row `ph` has landed
-                float gv[VEC];
-                ld_vec<VEC>(ring + slot_r * 32 * VEC, gv);
-                slot_r = (slot_r + 1) & (kRing - 1);
+            cp_async_wait<kRing - 1>();  // this lane's copy of pooled row `ph` has landed
+            float gv[VEC];
+            ld_vec<VEC>(ring + slot_r * 32 * VEC, gv);
+            slot_r = (slot_r + 1) & (kRing - 1);
 #pragma unroll
-                for (int j = 0; j < JW; ++j)
+            for (int j = 0; j < JW; ++j)
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * gv[e];
-            }
+                for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * gv[e];
+        }
+        while (base < R) {
+            retire();
+            ++base;
         }
         cp_async_wait<0>();
         __syncwarp();
     }
+}
+
+template <int VEC, int JW>
+__device__ __forceinline__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const float* ytab, int X0,
+                                         int Y0, int fw, int R, const int* plo, const int* pcnt,
+                                         const float* wxT, int TW, float* wsm, int cpw, int batch, int i,
+                                         int c0, int nc) {
+    const int lane = threadIdx.x & 31;
+    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+    float* dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Y0 * Lv.sH + X0 + lane;
+    // up-sampling buckets (JW == 2) can have many pooled columns per feature column; the others few
+    if (JW == 2 && TW > 4)
+        bwd_warp_core<VEC, JW, kTWR>(gbase, B.sC, B.sH, dbase, Lv.sC, Lv.sH, ytab, B.ph, B.pw, R, fw, plo, pcnt, wxT, TW, wsm, cpw, nc);
+    else
+        bwd_warp_core<VEC, JW, 4>(gbase, B.sC, B.sH, dbase, Lv.sC, Lv.sH, ytab, B.ph, B.pw, R, fw, plo, pcnt, wxT, TW, wsm, cpw, nc);
 }
 
 // shared-memory floats a warp needs on the fast path: ring + row buffer + zero pad
@@ -944,7 +956,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __launch_bounds__(kRaThreads, BWD ? 3 : 2) ra_kernel(const __grid_constant__ RaParams p) {
+__global__ void __launch_bounds__(kRaThreads, 2) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
