@@ -411,6 +411,15 @@ def run_extras(dm, ops, dev, rank, peak):
     ex['dm_paste_masks'] = {'workload': 'C4 per GPU: 800 instances (8 img x 100 dets), 112x112 -> 800x1333 bool',
                             'ms': ms, 'instances_per_s': n / ms * 1e3, 'algorithmic_bytes': by,
                             'achieved_gbs': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak}
+    # write-only reference point: the same number of output bytes zero-filled by cudaMemsetAsync
+    out.zero_()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        out.zero_()
+    b.record()
+    torch.cuda.synchronize()
+    ex['dm_paste_masks']['memset_same_bytes_ms'] = a.elapsed_time(b) / reps
     del out, logits
     # mask targets: C3 shape, 2 images x 128 positives, all four sizes in one launch
     rng = np.random.default_rng(7 + rank)

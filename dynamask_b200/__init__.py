@@ -15,6 +15,7 @@ from .mask_target import mask_target, mask_target_single, multi_size_mask_target
 from .roi_align import RoIAlign, roi_align
 from .roi_extractors import (BaseRoIExtractor, BucketedRoIExtractor, BucketedRoIFeats,
                              SingleRoIExtractor)
+from .sharding import checksum64, gather_checksums, image_shard, shard_rois
 from .switch import get_mask_label, gumbel_softmax
 
 __version__ = '0.1.0'
@@ -23,5 +24,6 @@ __all__ = [
     'ops', 'bbox2roi', 'RoIAlign', 'roi_align', 'BaseRoIExtractor', 'SingleRoIExtractor',
     'BucketedRoIExtractor', 'BucketedRoIFeats', 'BitmapMasks', 'mask_target',
     'mask_target_single', 'multi_size_mask_targets', '_do_paste_mask', 'get_seg_masks',
-    'paste_masks_in_image', 'DynaMaskHeadMixin', 'get_mask_label', 'gumbel_softmax'
+    'paste_masks_in_image', 'DynaMaskHeadMixin', 'get_mask_label', 'gumbel_softmax',
+    'image_shard', 'shard_rois', 'checksum64', 'gather_checksums'
 ]

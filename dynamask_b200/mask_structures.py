@@ -23,7 +23,8 @@ def pack_bitmaps(masks_list, device):
     total = max(sum(sizes), 1)
     offs = np.zeros(len(masks_list), np.int64)
     ghw = np.zeros((len(masks_list), 3), np.int32)
-    stage = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    pin = torch.device(device).type == 'cuda'
+    stage = torch.empty(total, dtype=torch.uint8, pin_memory=pin)
     view = stage.numpy()
     pos = 0
     for b, m in enumerate(masks_list):
@@ -33,7 +34,7 @@ def pack_bitmaps(masks_list, device):
         view[pos:pos + sizes[b]] = np.ascontiguousarray(m, dtype=np.uint8).reshape(-1)
         pos += sizes[b]
     blob = stage.to(device, non_blocking=True)
-    meta = torch.empty(len(masks_list) * 5, dtype=torch.int64, pin_memory=True)
+    meta = torch.empty(len(masks_list) * 5, dtype=torch.int64, pin_memory=pin)
     meta_np = meta.numpy()
     meta_np[:len(masks_list)] = offs
     # int32 (G,H,W) triples stored behind the int64 offsets in the same pinned buffer

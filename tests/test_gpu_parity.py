@@ -445,3 +445,148 @@ def test_mask_targets_exact_half_ties():
     ref = O.dyna_get_targets([boxes], [inds], [masks])
     for s in range(4):
         assert torch.equal(out[s].cpu(), ref[s])
+
+
+# ------------------------------------------------------------------------------------------
+# golden fixtures produced by the unmodified reference (oracle/gen_golden.py)
+# ------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_golden_assign_gpu():
+    d = gold('assign.npz')
+    lvl, bucket, perm, seg = dm().ops.assign(torch.from_numpy(d['rois']).cuda(), torch.from_numpy(d['onehot']).cuda(),
+                                             4, 56.0, 4)
+    ref = d['lvl']
+    nan = np.isnan(np.sqrt((d['rois'][:, 3] - d['rois'][:, 1]) * (d['rois'][:, 4] - d['rois'][:, 2])))
+    assert np.array_equal(lvl.cpu().numpy()[~nan], ref[~nan])
+    assert np.array_equal(bucket.cpu().numpy(), d['bucket'])
+    _, _, perm_o, seg_o = O.assign(d['rois'], d['onehot'], 4, 56)
+    assert np.array_equal(perm.cpu().numpy(), perm_o) and np.array_equal(seg.cpu().numpy(), seg_o)
+
+
+def test_golden_extractor_gpu():
+    d = gold('extractor.npz')
+    feats = [torch.from_numpy(d['feat_l%d' % l]).cuda() for l in range(4)]
+    rois = torch.from_numpy(d['rois']).cuda()
+    for p in (7, 14):
+        ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=p, sampling_ratio=0), 4, [4, 8, 16, 32])
+        fr = [f.clone().requires_grad_() for f in feats]
+        out = ext(fr, rois)
+        assert_close(out, torch.from_numpy(d['out_%d' % p]), FWD_RTOL, FWD_ATOL, 'golden fwd %d' % p)
+        out.backward(torch.from_numpy(d['gout_%d' % p]).cuda())
+        for l in range(4):
+            assert_close(fr[l].grad, torch.from_numpy(d['grad_%d_l%d' % (p, l)]), BWD_RTOL, BWD_ATOL,
+                         'golden grad %d level %d' % (p, l))
+    ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=2), 4, [4, 8, 16, 32])
+    assert_close(ext(feats, rois, roi_scale_factor=1.25), torch.from_numpy(d['out_7_sr2_rescaled']),
+                 FWD_RTOL, FWD_ATOL, 'golden sr2 rescaled')
+    sem = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=56, sampling_ratio=0), 4, [4])
+    assert_close(sem([feats[0]], rois[:6]), torch.from_numpy(d['out_56_single_level']), FWD_RTOL, FWD_ATOL,
+                 'golden single level 56')
+    bext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 4, [4, 8, 16, 32])
+    res = bext.forward_bucketed(feats, rois[:8], torch.from_numpy(d['onehot8']).cuda())
+    for b in range(4):
+        assert_close(res.feats[b], torch.from_numpy(d['bucket_%d' % b]), FWD_RTOL, FWD_ATOL, 'golden bucket %d' % b)
+
+
+def test_golden_paste_gpu():
+    d = gold('paste.npz')
+    n = d['logits'].shape[0]
+    logits = torch.from_numpy(d['logits']).cuda()
+    det = torch.cat([torch.from_numpy(d['boxes']), torch.ones(n, 1)], 1).cuda()
+    labels = torch.zeros(n, dtype=torch.long).cuda()
+    out = np.stack(dm().get_seg_masks(logits, det, labels, _Cfg(0.5), (120, 160, 3), 1.0, False))
+    assert (out == d['segs']).mean() >= 0.9999
+    sf = np.array([1.5] * 4, np.float32)
+    det_rs = det * torch.tensor([1.5, 1.5, 1.5, 1.5, 1.0]).cuda()
+    out = np.stack(dm().get_seg_masks(logits, det_rs, labels, _Cfg(0.5), (120, 160, 3), sf, True))
+    assert (out == d['segs_rescaled']).mean() >= 0.9999
+    out = np.stack(dm().get_seg_masks(logits, det, labels, _Cfg(-1), (120, 160, 3), 1.0, False))
+    assert np.abs(out.astype(np.int32) - d['segs_u8'].astype(np.int32)).max() <= 1
+    vals, _ = dm()._do_paste_mask(logits.sigmoid(), det[:, :4], 120, 160, skip_empty=False)
+    ref = torch.from_numpy(d['values'])
+    ok = ~(torch.isnan(ref) | torch.isnan(vals.cpu()))
+    assert float((vals.cpu()[ok] - ref[ok]).abs().max()) < 1e-5
+
+
+def test_golden_mask_targets_gpu():
+    d = gold('mask_target.npz')
+    bm = dm().BitmapMasks(d['masks'], 96, 128)
+    out = dm().multi_size_mask_targets([torch.from_numpy(d['boxes']).cuda()], [torch.from_numpy(d['inds']).cuda()], [bm])
+    for s, size in enumerate((14, 28, 56, 112)):
+        assert torch.equal(out[s].cpu(), torch.from_numpy(d['target_%d' % size]))
+    assert np.array_equal(bm.crop_and_resize(d['boxes'], (28, 28), d['inds'], device='cuda').masks, d['crop_28'])
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at the benchmark's shapes (256 channels, 800x1344 pyramid)
+# ------------------------------------------------------------------------------------------
+def _full_size_case(batch, per_img, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    gc = gen(seed)
+    shapes = synth.pyramid_shapes(800, 1344)
+    feats = [torch.randn(batch, 256, h, w, generator=g, device='cuda') for (h, w) in shapes]
+    rois = synth.make_rois(batch, per_img, 800, 1344, gc).cuda()
+    onehot = synth.make_onehot(rois.size(0), gc).cuda()
+    return feats, rois, onehot
+
+
+def test_full_size_constant_map_is_reproduced():
+    """Interpolation weights sum to one: a constant pyramid pools to the same constant."""
+    feats, rois, onehot = _full_size_case(2, 256, 61)
+    const = [torch.full_like(f, 3.25) for f in feats]
+    ext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 256, [4, 8, 16, 32])
+    res = ext.forward_bucketed(const, rois, onehot)
+    assert sum(res.counts) == rois.size(0)
+    for o in res.feats:
+        assert float((o - 3.25).abs().max()) < 1e-5
+
+
+def test_full_size_forward_backward_are_adjoint_and_linear():
+    """<A f, g> == <f, A^T g> and A(a f1 + f2) == a A f1 + A f2 for the bucketed operator."""
+    feats, rois, onehot = _full_size_case(2, 256, 62)
+    ext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 256, [4, 8, 16, 32])
+    fr = [f.clone().requires_grad_() for f in feats]
+    res = ext.forward_bucketed(fr, rois, onehot)
+    g = torch.Generator(device='cuda').manual_seed(63)
+    gos = [torch.randn(o.shape, generator=g, device='cuda') for o in res.feats]
+    lhs = sum(float((o.double() * go.double()).sum()) for o, go in zip(res.feats, gos))
+    torch.autograd.backward(res.feats, gos)
+    rhs = sum(float((f.double() * f.grad.double()).sum()) for f in fr)
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    del fr, gos
+    f2 = [torch.randn(f.shape, generator=g, device='cuda') for f in feats]
+    a = ext.forward_bucketed(feats, rois, onehot, counts=res.counts).feats
+    b = ext.forward_bucketed(f2, rois, onehot, counts=res.counts).feats
+    c = ext.forward_bucketed([0.5 * x + y for x, y in zip(feats, f2)], rois, onehot, counts=res.counts).feats
+    for x, y, z in zip(a, b, c):
+        assert float((0.5 * x + y - z).abs().max()) < 2e-5
+
+
+def test_full_size_paste_and_targets_properties():
+    # a saturated mask pastes to (approximately) the box: pixel count ~ box area, all inside the box
+    n, H, W = 64, 800, 1333
+    boxes = synth.make_boxes(n, H, W, gen(64), s_lo=16, s_hi=500).cuda()
+    logits = torch.full((n, 1, 112, 112), 20.0, device='cuda')
+    out = dm().paste_masks_in_image(logits, boxes, torch.zeros(n, dtype=torch.long).cuda(), 0.5, (H, W, 3), 1.0, False)
+    assert out.dtype == torch.bool and tuple(out.shape) == (n, H, W)
+    area = ((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])).cpu()
+    cnt = out.flatten(1).sum(1).cpu().float()
+    perim = 2 * ((boxes[:, 2] - boxes[:, 0]) + (boxes[:, 3] - boxes[:, 1])).cpu()
+    assert bool(((cnt - area).abs() <= perim + 4).all())
+    # all-ones / all-zero bitmaps give all-ones / all-zero targets for boxes inside the canvas
+    ones = dm().BitmapMasks(np.ones((2, 800, 1344), np.uint8), 800, 1344)
+    zeros = dm().BitmapMasks(np.zeros((2, 800, 1344), np.uint8), 800, 1344)
+    pb = synth.make_boxes(128, 800, 1344, gen(65), s_lo=8, s_hi=700).cuda()
+    pi = torch.randint(0, 2, (128, ), generator=gen(66)).cuda()
+    for t in dm().multi_size_mask_targets([pb], [pi], [ones]):
+        assert float(t.min()) == 1.0
+    for t in dm().multi_size_mask_targets([pb], [pi], [zeros]):
+        assert float(t.max()) == 0.0
