@@ -11,7 +11,7 @@ import torch
 from torch.nn.modules.utils import _pair
 
 from . import ops
-from .mask_structures import BitmapMasks, pack_bitmaps
+from .mask_structures import BitmapMasks
 
 
 def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list, sizes):
@@ -31,11 +31,24 @@ def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_lis
         blob, offs, ghw = gt_masks_list[keep[0]].to_device(device)
         roi_img = None
     else:
-        blob, offs, ghw = pack_bitmaps([gt_masks_list[i].masks for i in keep], device)
-        roi_img = torch.cat([
-            torch.full((pos_proposals_list[i].size(0), ), j, dtype=torch.int32, device=device)
-            for j, i in enumerate(keep)
-        ])
+        # every image's bitmaps are uploaded once and cached on its BitmapMasks; the kernel
+        # addresses them relative to the first blob, so nothing is re-packed per step
+        blobs = [gt_masks_list[i].to_device(device)[0] for i in keep]
+        blob = blobs[0]
+        meta = torch.empty(len(keep) * 5, dtype=torch.int64, pin_memory=True)
+        meta_np = meta.numpy()
+        for j, i in enumerate(keep):
+            meta_np[j] = blobs[j].data_ptr() - blob.data_ptr() if blobs[j].numel() else 0
+        ghw_np = meta_np[len(keep):].view('int32')
+        for j, i in enumerate(keep):
+            m = gt_masks_list[i].masks
+            ghw_np[3 * j:3 * j + 3] = (m.shape[0], m.shape[1], m.shape[2])
+        meta_dev = meta.to(device, non_blocking=True)
+        offs = meta_dev[:len(keep)]
+        ghw = meta_dev[len(keep):].view(torch.int32)[:3 * len(keep)]
+        counts = torch.tensor([pos_proposals_list[i].size(0) for i in keep])
+        roi_img = torch.repeat_interleave(torch.arange(len(keep), dtype=torch.int32), counts).to(
+            device, non_blocking=True)
     boxes = torch.cat([pos_proposals_list[i][:, :4] for i in keep]).float()
     inds = torch.cat([pos_assigned_gt_inds_list[i] for i in keep])
     return ops.mask_target(blob, offs, ghw, boxes, inds, roi_img, True, sizes_hw)

@@ -315,8 +315,13 @@ def do_paste_mask(masks, boxes, img_h, img_w, skip_empty=True):
 
 
 def get_seg_masks(mask_pred, det_bboxes, det_labels, mask_thr_binary, ori_shape, scale_factor,
-                  rescale):
-    """DynaMaskHead.get_seg_masks on CPU: list of N numpy [img_h,img_w] (bool, or uint8 if thr<0)."""
+                  rescale, device_mode='cpu'):
+    """DynaMaskHead.get_seg_masks on CPU: list of N numpy [img_h,img_w] (bool, or uint8 if thr<0).
+
+    ``device_mode='cpu'`` follows the reference's CPU branch (one instance per chunk,
+    ``skip_empty=True``, dynamask_head.py:301-305); ``'gpu'`` follows its CUDA branch (full canvas,
+    ``skip_empty=False``, :306-312).  The two agree except for degenerate boxes (x1 == x0 or
+    y1 == y0), where the inf->0 patch makes the full-canvas mode paint whole rows / columns."""
     prob = torch.as_tensor(mask_pred, dtype=torch.float32).sigmoid()
     det_bboxes = torch.as_tensor(det_bboxes, dtype=torch.float32)
     boxes = det_bboxes[:, :4]
@@ -334,8 +339,9 @@ def get_seg_masks(mask_pred, det_bboxes, det_labels, mask_thr_binary, ori_shape,
         prob = prob[range(n), torch.as_tensor(det_labels)][:, None]
     thr = mask_thr_binary
     canvas = torch.zeros(n, img_h, img_w, dtype=torch.bool if thr >= 0 else torch.uint8)
-    for i in range(n):  # CPU mode of the reference: one instance per chunk, skip_empty=True
-        chunk, sl = do_paste_mask(prob[i:i + 1], boxes[i:i + 1], img_h, img_w, skip_empty=True)
+    for i in range(n):  # one instance per chunk
+        chunk, sl = do_paste_mask(prob[i:i + 1], boxes[i:i + 1], img_h, img_w,
+                                  skip_empty=(device_mode == 'cpu'))
         if thr >= 0:
             chunk = (chunk >= thr).to(torch.bool)
         else:
