@@ -515,7 +515,19 @@ def test_golden_paste_gpu():
     out = np.stack(dm().get_seg_masks(logits, det_rs, labels, _Cfg(0.5), (120, 160, 3), sf, True))
     assert (out[keep] == d['segs_rescaled'][keep]).mean() >= 0.9999
     out = np.stack(dm().get_seg_masks(logits, det, labels, _Cfg(-1), (120, 160, 3), 1.0, False))
-    assert np.abs(out[keep].astype(np.int32) - d['segs_u8'][keep].astype(np.int32)).max() <= 1
+    # uint8 mode: the golden comes from the reference's CPU branch (skip_empty=True), which only
+    # evaluates the integer box +-1 px (fcn_mask_head.py:269-276) and so drops the sub-threshold
+    # fringe of half a mask pixel that the CUDA branch keeps.  Compare with the golden inside that
+    # region, and with the full-canvas (CUDA-branch) oracle everywhere.
+    bx = d['boxes']
+    for i in keep:
+        xa, ya = max(int(np.floor(bx[i, 0])) - 1, 0), max(int(np.floor(bx[i, 1])) - 1, 0)
+        xb, yb = min(int(np.ceil(bx[i, 2])) + 1, 160), min(int(np.ceil(bx[i, 3])) + 1, 120)
+        diff = np.abs(out[i, ya:yb, xa:xb].astype(np.int32) - d['segs_u8'][i, ya:yb, xa:xb].astype(np.int32))
+        assert diff.size == 0 or diff.max() <= 1, 'uint8 paste instance %d' % i
+    full8 = np.stack(O.get_seg_masks(d['logits'], det.cpu(), labels.cpu(), -1, (120, 160, 3), 1.0, False,
+                                     device_mode='gpu'))
+    assert np.abs(out[keep].astype(np.int32) - full8[keep].astype(np.int32)).max() <= 1
     vals, _ = dm()._do_paste_mask(logits.sigmoid(), det[:, :4], 120, 160, skip_empty=False)
     ref = torch.from_numpy(d['values'])
     ok = ~(torch.isnan(ref) | torch.isnan(vals.cpu()))
