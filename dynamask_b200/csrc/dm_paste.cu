@@ -12,23 +12,26 @@
 //   ix = ((gx + 1) * S_w - 1) / 2                                  (grid_sample, align_corners=False)
 //   bilinear, zero padding, four taps weighted (east-ix)*(south-iy) ...
 // Pixels whose sample falls outside (-1, S) are exactly zero; a conservative per-instance window
-// lets whole 16-byte chunks be zero-filled without evaluating the expression.
+// bounds the pixels that have to be evaluated at all.
 //
-// Work layout: grid = (tiles, instances).  A CTA owns 64 KB of one instance's output, produced in
-// four 16 KB passes; the box,
-// the non-zero window and the division magic are per-CTA constants, the x terms (which depend on
-// the column only) are staged once in shared memory, and each thread produces whole 16-byte
-// chunks.  The output is >98 % zeros on COCO-shaped detections, so the kernel is a streaming
-// zero-fill with a sparse compute region.
+// Work layout.  The [N, rh, rw] output is treated as one flat array cut into 16 KB tiles, one CTA
+// per tile (a write-only stream on this part runs fastest as many small CTAs, profiles/
+// r01_membench.md).  >90 % of the tiles miss their instance's window: they are four 16-byte
+// streaming zero stores per thread and nothing else.  A tile that meets the window
+//   1. zeroes a 16 KB shared image of itself,
+//   2. stages the source x coordinate of every window column (the x terms depend on the column
+//      only) and sigmoid(mask) of the mask rows its canvas rows can reach, with a zero border,
+//   3. evaluates the window pixels one per lane (a warp per canvas row) into the shared image,
+//   4. streams the image out with the same four 16-byte stores per thread.
+// Tiles that straddle two instances (or the end of the output) take a per-pixel path.
 #include "dm_common.cuh"
 
 namespace dm {
 
 constexpr int kPasteThreads = 256;
-constexpr int kChunksPerThread = 4;
-constexpr int kChunksPerTile = kPasteThreads * kChunksPerThread;  // 16 KB per pass
-constexpr int kSubTiles = 4;                                      // passes per CTA (64 KB of output)
-constexpr int kColTabMax = 1024;                                  // columns staged in shared memory
+constexpr int kTileBytes = 16384;   // output bytes per CTA: 4 x 16 B per thread
+constexpr int kIxTab = 2048;        // window columns whose x coordinate is staged in shared memory
+constexpr int kMaskStage = 3072;    // floats of sigmoid(mask) window staged per tile (12 KB)
 
 struct PasteParams {
     const float* masks;
@@ -39,18 +42,11 @@ struct PasteParams {
     const float* boxes;
     int img_h, img_w;
     int x_lo, y_lo, rw, rh;  // region origin and size
-    unsigned rw_magic;       // ceil(2^32 / rw): exact t / rw for t < rw + 16 KB (t * rw < 2^32)
+    long long total;         // N * rh * rw output elements
+    float inv_T;             // 1 / (rh * rw), first guess of the instance of a flat element index
     float thr;
     void* out;
 };
-
-struct __align__(16) ColTerm {
-    int xw;       // west tap column; kColZero when the column contributes nothing, kColNaN for NaN
-    float ww, we; // weights of the west / east taps
-    int pad;
-};
-constexpr int kColZero = INT_MIN;
-constexpr int kColNaN = INT_MIN + 1;
 
 __device__ __forceinline__ void window_1d(float lo_c, float hi_c, int S, int size, int& a, int& b) {
     const float w = hi_c - lo_c;
@@ -77,39 +73,39 @@ __device__ __forceinline__ float src_coord(int pc, float c0, float c1, int S) {
     return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)S), 1.0f), 2.0f);
 }
 
-__device__ __forceinline__ ColTerm col_term(int px, float x0, float x1, int sw) {
-    ColTerm c;
-    const float ix = src_coord(px, x0, x1, sw);
-    c.ww = 0.0f;
-    c.we = 0.0f;
-    if (ix != ix) { c.xw = kColNaN; return c; }
-    if (!(ix > -1.0f && ix < (float)sw)) { c.xw = kColZero; return c; }
-    const float fx = floorf(ix);
-    c.xw = (int)fx;
-    c.we = __fsub_rn(ix, fx);
-    c.ww = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
-    return c;
-}
-
-struct RowTerm {
-    int yn;
-    float wn, ws;  // weights of the north / south mask rows
-    int state;     // 0 zero row, 1 live, 2 NaN row
+// One axis of the bilinear tap pair at source coordinate `i`:
+//   state 0: the pixel is exactly zero (sample outside (-1, S)), 1: live, 2: NaN coordinate.
+struct AxisTerm {
+    int lo;        // first tap index, in [-1, S-1]
+    float wl, wh;  // weights of tap lo and tap lo+1
+    int state;
 };
 
-__device__ __forceinline__ RowTerm row_term(int py, float y0, float y1, int sh, int ya, int yb) {
-    RowTerm r;
-    r.yn = 0; r.wn = 0.0f; r.ws = 0.0f; r.state = 0;
-    if (py < ya || py >= yb) return r;
-    const float iy = src_coord(py, y0, y1, sh);
-    if (iy != iy) { r.state = 2; return r; }
-    if (!(iy > -1.0f && iy < (float)sh)) return r;
-    const float fy = floorf(iy);
-    r.yn = (int)fy;
-    r.wn = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
-    r.ws = __fsub_rn(iy, fy);
-    r.state = 1;
-    return r;
+__device__ __forceinline__ AxisTerm axis_term(float i, int S) {
+    AxisTerm t;
+    t.lo = 0; t.wl = 0.0f; t.wh = 0.0f;
+    if (i != i) { t.state = 2; return t; }
+    if (!(i > -1.0f && i < (float)S)) { t.state = 0; return t; }
+    const float f = floorf(i);
+    t.lo = (int)f;
+    t.wh = __fsub_rn(i, f);
+    t.wl = __fsub_rn(__fadd_rn(f, 1.0f), i);
+    t.state = 1;
+    return t;
+}
+
+__device__ __forceinline__ float sigmoidf_exact(float v) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+}
+
+// the reference's four-tap sum, in grid_sample's order
+__device__ __forceinline__ float bilerp(float nw, float ne, float sw, float se, const AxisTerm& cx,
+                                        const AxisTerm& ry) {
+    float acc = nw * (cx.wl * ry.wl);
+    acc += ne * (cx.wh * ry.wl);
+    acc += sw * (cx.wl * ry.wh);
+    acc += se * (cx.wh * ry.wh);
+    return acc;
 }
 
 template <int MODE>
@@ -120,198 +116,180 @@ __device__ __forceinline__ uint32_t encode(float v, float thr) {
     return (s != s) ? 0u : (uint32_t)(unsigned char)(int)s;
 }
 
-// Mask taps of one instance: either from a shared-memory window that already holds
-// sigmoid(mask) with a one-pixel zero border, or straight from global memory.
-struct Sampler {
+// One instance as the per-pixel path sees it: taps straight from global memory.
+struct Instance {
     const float* m;
+    float x0, y0, x1, y1;
+    int xa, xb, ya, yb;  // conservative non-zero window, canvas coordinates
     int sh, sw, apply_sigmoid;
-    const float* stage;  // null -> read global memory
-    int st_lo, st_w;     // first staged mask row, staged row width (sw + 2)
 
+    __device__ __forceinline__ void load(const PasteParams& p, long long n) {
+        const long long cls = p.labels ? p.labels[n] : 0;
+        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
+        x0 = bx.x; y0 = bx.y; x1 = bx.z; y1 = bx.w;
+        window_1d(x0, x1, p.sw, p.img_w, xa, xb);
+        window_1d(y0, y1, p.sh, p.img_h, ya, yb);
+        m = p.masks + n * p.stride_n + cls * p.stride_c;
+        sh = p.sh; sw = p.sw; apply_sigmoid = p.apply_sigmoid;
+    }
     __device__ __forceinline__ float tap(int y, int x) const {
         if (y < 0 || y >= sh || x < 0 || x >= sw) return 0.0f;
-        float v = __ldg(m + y * sw + x);
-        if (apply_sigmoid) v = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
-        return v;
+        const float v = __ldg(m + y * sw + x);
+        return apply_sigmoid ? sigmoidf_exact(v) : v;
     }
-    __device__ __forceinline__ float eval(const RowTerm& rt, const ColTerm& ct) const {
-        if (rt.state == 0 || ct.xw == kColZero) return 0.0f;
-        if (rt.state == 2 || ct.xw == kColNaN) return __int_as_float(0x7fc00000);
-        float nw, ne, sw_, se;
-        if (stage) {
-            const float* q = stage + (rt.yn - st_lo) * st_w + ct.xw + 1;
-            nw = q[0]; ne = q[1]; sw_ = q[st_w]; se = q[st_w + 1];
-        } else {
-            nw = tap(rt.yn, ct.xw); ne = tap(rt.yn, ct.xw + 1);
-            sw_ = tap(rt.yn + 1, ct.xw); se = tap(rt.yn + 1, ct.xw + 1);
-        }
-        float acc = nw * (ct.ww * rt.wn);
-        acc += ne * (ct.we * rt.wn);
-        acc += sw_ * (ct.ww * rt.ws);
-        acc += se * (ct.we * rt.ws);
-        return acc;
+    // canvas pixel (px, py) -> interpolated value
+    __device__ float eval(int px, int py) const {
+        if (px < xa || px >= xb || py < ya || py >= yb) return 0.0f;
+        const AxisTerm cx = axis_term(src_coord(px, x0, x1, sw), sw);
+        const AxisTerm ry = axis_term(src_coord(py, y0, y1, sh), sh);
+        if (cx.state == 0 || ry.state == 0) return 0.0f;
+        if (cx.state == 2 || ry.state == 2) return __int_as_float(0x7fc00000);
+        return bilerp(tap(ry.lo, cx.lo), tap(ry.lo, cx.lo + 1), tap(ry.lo + 1, cx.lo), tap(ry.lo + 1, cx.lo + 1), cx, ry);
     }
 };
 
-constexpr int kMaskStage = 3072;  // floats of sigmoid(mask) window staged per tile (12 KB)
-
 template <int MODE>
-__global__ void __launch_bounds__(kPasteThreads)
+__global__ void __launch_bounds__(kPasteThreads, 5)
 paste_kernel(const __grid_constant__ PasteParams p) {
     constexpr int ES = (MODE == DM_PASTE_F32) ? 4 : 1;  // bytes per output element
     constexpr int V = 16 / ES;                          // elements per 16-byte chunk
-    __shared__ ColTerm s_col[kColTabMax];
+    constexpr int TE = kTileBytes / ES;                 // elements per tile
+    __shared__ __align__(16) unsigned char s_tile[kTileBytes];
     __shared__ __align__(16) float s_mask[kMaskStage];
-    __shared__ __align__(16) unsigned char s_tile[kChunksPerTile * 16];
-    const int T = p.rh * p.rw;  // elements per instance (< 2^30, checked on the host)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float s_ix[kIxTab];
 
-    for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
-        // ---- per-instance constants (identical in every thread of the CTA) -------------------
-        const long long b0 = (long long)n * T * ES;              // first byte of the instance
-        const long long c_first = (b0 + 15) >> 4;                // first chunk fully inside
-        const long long c_last = (b0 + (long long)T * ES) >> 4;  // one past the last chunk fully inside
-        const int head = (int)((c_first * 16 - b0) / ES);        // elements before the first full chunk
-        const long long nchunks = c_last > c_first ? c_last - c_first : 0;
-        if ((long long)blockIdx.x * kSubTiles * kChunksPerTile >= nchunks && blockIdx.x != 0) continue;  // uniform
+    const long long E0 = (long long)blockIdx.x * TE;  // first flat element of the tile
+    const int T = p.rh * p.rw;                        // elements per instance (< 2^30, host-checked)
+    long long n = (long long)((float)E0 * p.inv_T);
+    n = n < 0 ? 0 : (n >= p.N ? p.N - 1 : n);
+    while (n * T > E0) --n;
+    while ((n + 1) * T <= E0) ++n;
+    uint4* const out16 = reinterpret_cast<uint4*>(p.out) + (long long)blockIdx.x * (kTileBytes / 16);
 
-        const long long cls = p.labels ? p.labels[n] : 0;
-        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
-        int xa, xb, ya, yb;
-        window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
-        window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
-        // window in region coordinates, clipped to the region
-        const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
-        const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
-        Sampler sm;
-        sm.m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
-        sm.sh = p.sh; sm.sw = p.sw; sm.apply_sigmoid = p.apply_sigmoid;
-        sm.stage = nullptr; sm.st_lo = 0; sm.st_w = p.sw + 2;
-
-        const bool use_tab = (xb - xa) <= kColTabMax;
-        const bool tiny = p.rw < 2 * V;  // chunks may span several rows: evaluate every pixel
-        bool have_tab = false;           // column table of this instance built yet?
-        __syncthreads();                 // shared tables of the previous instance are no longer in use
-
-      for (int sub = 0; sub < kSubTiles; ++sub) {
-        const long long k0 = ((long long)blockIdx.x * kSubTiles + sub) * kChunksPerTile;
-        if (k0 >= nchunks && !(blockIdx.x == 0 && sub == 0)) break;  // uniform
-        sm.stage = nullptr;
-        // elements / rows covered by this tile's full chunks
-        const int kn = (int)min((long long)kChunksPerTile, nchunks > k0 ? nchunks - k0 : 0);
-        const int e_lo = head + (int)k0 * V;
-        const int e_hi = e_lo + kn * V;  // exclusive
-        // exact row / column of the tile's first element by a real division (once per thread);
-        // chunks then use small offsets from it, for which the magic multiply is exact
-        const int row_b = e_lo / p.rw;
-        const int col_b = e_lo - row_b * p.rw;
-        const int span = col_b + max(e_hi - e_lo - 1, 0);
-        const int row_e = row_b + (p.rw > 1 ? (int)__umulhi((unsigned)span, p.rw_magic) : span);
-        const int ra = max(row_b, wya), rb = min(row_e, wyb - 1);  // live rows of the tile, inclusive
-        const bool tile_live = kn > 0 && ra <= rb && wxb > wxa;
-        const bool edge = blockIdx.x == 0 && sub == 0;  // this pass also writes the head / tail elements
-
-        if ((tile_live || edge) && use_tab && !have_tab) {
-            for (int c = threadIdx.x; c < xb - xa; c += kPasteThreads) s_col[c] = col_term(xa + c, bx.x, bx.z, p.sw);
-            have_tab = true;
-        }
-        if (tile_live) {
-            // mask rows the live canvas rows can touch (the source coordinate is monotone in py)
-            const float ia = src_coord(p.y_lo + ra, bx.y, bx.w, p.sh);
-            const float ib = src_coord(p.y_lo + rb, bx.y, bx.w, p.sh);
-            if (ia == ia && ib == ib) {
-                const float lo_f = fmaxf(floorf(fminf(ia, ib)), -1.0f);
-                const float hi_f = fminf(floorf(fmaxf(ia, ib)) + 1.0f, (float)p.sh);
-                const int lo = (int)lo_f, hi = (int)hi_f;
-                const int nrow = hi - lo + 1;
-                if (nrow >= 1 && nrow * sm.st_w <= kMaskStage) {
-                    for (int q = threadIdx.x; q < nrow * sm.st_w; q += kPasteThreads) {
-                        const int y = lo + q / sm.st_w, x = q % sm.st_w - 1;
-                        s_mask[q] = sm.tap(y, x);
-                    }
-                    sm.stage = s_mask;
-                    sm.st_lo = lo;
-                }
-            }
-        }
-        if (tile_live || edge) __syncthreads();
-
-        auto column = [&](int col) -> ColTerm {  // col in region coordinates
-            const int px = p.x_lo + col;
-            if (px < xa || px >= xb) { ColTerm z; z.xw = kColZero; z.ww = 0.f; z.we = 0.f; return z; }
-            return use_tab ? s_col[px - xa] : col_term(px, bx.x, bx.z, p.sw);
-        };
-        auto put = [&](int q, float v) {  // q = element offset inside the tile
-            if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(s_tile)[q] = v;
-            else s_tile[q] = (unsigned char)encode<MODE>(v, p.thr);
-        };
-
-        // ---- phase A: evaluate the live pixels, one pixel per lane, into the shared tile ---------
-        if (tile_live && !tiny) {
-            for (int r = ra + warp; r <= rb; r += kPasteThreads / 32) {
-                const RowTerm rt = row_term(p.y_lo + r, bx.y, bx.w, p.sh, ya, yb);
-                // window elements of this row, clipped to the tile and widened to whole chunks
-                const int a = max(r * p.rw + wxa, e_lo), b = min(r * p.rw + wxb, e_hi);
-                if (a >= b) continue;
-                const int qa = ((a - e_lo) / V) * V, qb = min(((b - e_lo + V - 1) / V) * V, kn * V);
-                for (int q = qa + lane; q < qb; q += 32) {
-                    int col = e_lo + q - r * p.rw;
-                    float v;
-                    if (col < 0) {
-                        v = sm.eval(row_term(p.y_lo + r - 1, bx.y, bx.w, p.sh, ya, yb), column(col + p.rw));
-                    } else if (col >= p.rw) {
-                        v = sm.eval(row_term(p.y_lo + r + 1, bx.y, bx.w, p.sh, ya, yb), column(col - p.rw));
-                    } else {
-                        v = sm.eval(rt, column(col));
-                    }
-                    put(q, v);
-                }
-            }
-        } else if (tile_live) {
-            for (int q = threadIdx.x; q < kn * V; q += kPasteThreads) {
-                const int e = e_lo + q, row = e / p.rw, col = e - row * p.rw;
-                put(q, sm.eval(row_term(p.y_lo + row, bx.y, bx.w, p.sh, ya, yb), column(col)));
-            }
-        }
-        if (tile_live) __syncthreads();
-
-        // ---- phase B: one 16-byte streaming store per chunk (zeros outside the live window) ------
-        uint4* out16 = reinterpret_cast<uint4*>(p.out) + c_first + k0;
-        const uint4* tile16 = reinterpret_cast<const uint4*>(s_tile);
+    if (E0 + TE > (n + 1) * T) {
+        // ---- per-pixel path: the tile straddles instances or is the last, partial one ------------
+        Instance in;
+        long long cur = -1;
 #pragma unroll 1
-        for (int kk = threadIdx.x; kk < kn; kk += kPasteThreads) {
-            bool live = tile_live;
-            if (live && !tiny) {
-                const int t0 = col_b + kk * V;
-                const int dr = (int)__umulhi((unsigned)t0, p.rw_magic);
-                const int row = row_b + dr, col = t0 - dr * p.rw;
-                const int len1 = min(V, p.rw - col);
-                live = (row >= wya && row < wyb && col < wxb && col + len1 > wxa);
-                if (len1 < V) live = live || (row + 1 >= wya && row + 1 < wyb && 0 < wxb && V - len1 > wxa);
+        for (int k = 0; k < 4; ++k) {
+            const int ck = threadIdx.x + k * kPasteThreads;
+            const long long Ec = E0 + (long long)ck * V;
+            if (Ec >= p.total) break;
+            long long nc = Ec / T;
+            int e = (int)(Ec - nc * T);
+            int row = e / p.rw, col = e - row * p.rw;
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            const int cnt = (int)min((long long)V, p.total - Ec);
+            for (int j = 0; j < cnt; ++j) {
+                if (nc != cur) { in.load(p, nc); cur = nc; }
+                const float v = in.eval(p.x_lo + col, p.y_lo + row);
+                if (MODE == DM_PASTE_F32) w[j & 3] = __float_as_uint(v);
+                else w[j >> 2] |= encode<MODE>(v, p.thr) << (8 * (j & 3));
+                if (++col == p.rw) { col = 0; if (++row == p.rh) { row = 0; ++nc; } }
             }
-            __stcs(out16 + kk, live ? tile16[kk] : make_uint4(0u, 0u, 0u, 0u));
-        }
-
-        if (tile_live) __syncthreads();  // the shared tile / mask window are rewritten by the next pass
-
-        // ---- head / tail elements that share a 16-byte chunk with a neighbouring instance -------
-        if (edge) {
-            const int tail_start = nchunks > 0 ? head + (int)nchunks * V : 0;
-            const int n_head = nchunks > 0 ? head : 0;
-            const int n_edge = n_head + (T - tail_start);  // (if no full chunk, everything is "tail")
-            Sampler s2 = sm;
-            s2.stage = nullptr;  // the staged window belongs to the tile's rows, not to these
-            for (int q = threadIdx.x; q < n_edge; q += kPasteThreads) {
-                const int e = q < n_head ? q : tail_start + (q - n_head);
-                const int row = e / p.rw;
-                const int col = e - row * p.rw;
-                const float v = s2.eval(row_term(p.y_lo + row, bx.y, bx.w, p.sh, ya, yb), column(col));
-                if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(p.out)[(long long)n * T + e] = v;
-                else reinterpret_cast<uint8_t*>(p.out)[(long long)n * T + e] = (uint8_t)encode<MODE>(v, p.thr);
+            if (cnt == V) {
+                __stcs(out16 + ck, make_uint4(w[0], w[1], w[2], w[3]));
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(p.out)[Ec + j] = __uint_as_float(w[j & 3]);
+                    else reinterpret_cast<uint8_t*>(p.out)[Ec + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+                }
             }
         }
-      }  // sub-tiles
+        return;
     }
+
+    // ---- the tile lies inside instance n: rows [row_b, row_e] of its region --------------------
+    const int e_lo = (int)(E0 - n * T);
+    const int row_b = e_lo / p.rw;
+    const int row_e = (e_lo + TE - 1) / p.rw;
+    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
+    int xa, xb, ya, yb;
+    window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
+    window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
+    // window in region coordinates, clipped to the region and to the tile's rows
+    const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
+    const int ra = max(max(ya - p.y_lo, 0), row_b), rb = min(min(yb - p.y_lo, p.rh) - 1, row_e);  // inclusive
+    if (ra > rb || wxa >= wxb) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) __stcs(out16 + threadIdx.x + k * kPasteThreads, z);
+        return;
+    }
+
+    // ---- live tile ---------------------------------------------------------------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(s_tile)[threadIdx.x + k * kPasteThreads] = z;
+    }
+    const int ww = wxb - wxa;
+    const bool use_tab = ww <= kIxTab;
+    if (use_tab)
+        for (int c = threadIdx.x; c < ww; c += kPasteThreads) s_ix[c] = src_coord(p.x_lo + wxa + c, bx.x, bx.z, p.sw);
+    const long long cls = p.labels ? p.labels[n] : 0;
+    const float* __restrict__ m = p.masks + n * p.stride_n + cls * p.stride_c;
+    const int st_w = p.sw + 2;
+    int st_lo = 0;
+    bool staged = false;
+    {
+        // mask rows the live canvas rows can reach (the source coordinate is monotone in py)
+        const float ia = src_coord(p.y_lo + ra, bx.y, bx.w, p.sh);
+        const float ib = src_coord(p.y_lo + rb, bx.y, bx.w, p.sh);
+        if (ia == ia && ib == ib) {
+            const int lo = (int)fmaxf(floorf(fminf(ia, ib)), -1.0f);
+            const int hi = (int)fminf(floorf(fmaxf(ia, ib)) + 1.0f, (float)p.sh);
+            const int nrow = hi - lo + 1;
+            if (nrow >= 1 && nrow * st_w <= kMaskStage) {
+                for (int q = threadIdx.x; q < nrow * st_w; q += kPasteThreads) {
+                    const int yy = q / st_w;
+                    const int y = lo + yy, x = q - yy * st_w - 1;
+                    float v = 0.0f;
+                    if (y >= 0 && y < p.sh && x >= 0 && x < p.sw) {
+                        v = __ldg(m + y * p.sw + x);
+                        if (p.apply_sigmoid) v = sigmoidf_exact(v);
+                    }
+                    s_mask[q] = v;
+                }
+                staged = true;
+                st_lo = lo;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- evaluate the window pixels of the tile: a warp per canvas row, a lane per pixel ----------
+    Instance in;
+    if (!staged) in.load(p, n);
+    for (int r = ra + warp; r <= rb; r += kPasteThreads / 32) {
+        const AxisTerm ry = axis_term(src_coord(p.y_lo + r, bx.y, bx.w, p.sh), p.sh);
+        if (ry.state == 0) continue;
+        const int e_row = r * p.rw - e_lo;  // tile offset of the row's column 0
+        const int ca = max(wxa, -e_row), cb = min(wxb, TE - e_row);
+        const float* mrow = s_mask + (ry.lo - st_lo) * st_w + 1;
+        for (int c = ca + lane; c < cb; c += 32) {
+            const float ix = use_tab ? s_ix[c - wxa] : src_coord(p.x_lo + c, bx.x, bx.z, p.sw);
+            const AxisTerm cx = axis_term(ix, p.sw);
+            if (cx.state == 0) continue;
+            float v;
+            if (cx.state == 2 || ry.state == 2) {
+                v = __int_as_float(0x7fc00000);
+            } else if (staged) {
+                const float* q = mrow + cx.lo;
+                v = bilerp(q[0], q[1], q[st_w], q[st_w + 1], cx, ry);
+            } else {
+                v = bilerp(in.tap(ry.lo, cx.lo), in.tap(ry.lo, cx.lo + 1), in.tap(ry.lo + 1, cx.lo),
+                           in.tap(ry.lo + 1, cx.lo + 1), cx, ry);
+            }
+            if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(s_tile)[e_row + c] = v;
+            else s_tile[e_row + c] = (unsigned char)encode<MODE>(v, p.thr);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        __stcs(out16 + threadIdx.x + k * kPasteThreads, reinterpret_cast<const uint4*>(s_tile)[threadIdx.x + k * kPasteThreads]);
 }
 
 }  // namespace dm
@@ -350,15 +328,12 @@ extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t
     p.y_lo = y_lo;
     p.thr = thr;
     p.out = out;
-    // the magic multiply divides offsets below rw + 16 K exactly as long as their product with rw
-    // stays below 2^32
-    if (p.rw > 50000) return DM_EUNSUPPORTED;
-    p.rw_magic = (unsigned)(0xFFFFFFFFu / (unsigned)p.rw + 1u);  // rw == 1 wraps to 0: handled below
+    p.total = per_inst * N;
+    p.inv_T = 1.0f / (float)per_inst;
     const int ES = out_mode == DM_PASTE_F32 ? 4 : 1;
-    const long long chunks = (per_inst * ES + 15) / 16 + 1;
-    const long long per_cta = (long long)dm::kChunksPerTile * dm::kSubTiles;
-    const unsigned tiles = (unsigned)((chunks + per_cta - 1) / per_cta);
-    dim3 grid(tiles, (unsigned)(N < 65535 ? N : 65535));
+    const long long tiles = (p.total * ES + dm::kTileBytes - 1) / dm::kTileBytes;
+    if (tiles >= (1ll << 31)) return DM_EUNSUPPORTED;
+    dim3 grid((unsigned)tiles);
     cudaStream_t st = (cudaStream_t)stream;
     switch (out_mode) {
         case DM_PASTE_BOOL:
