@@ -1,5 +1,4 @@
-// Stage 3: paste instance masks into image canvases -- sigmoid + bilinear resample + threshold in
-// one pass, one 16-byte store per 16 output pixels.
+// Stage 3: paste instance masks into image canvases -- sigmoid + bilinear resample + threshold.
 //
 // Replaces _do_paste_mask (mmdet/models/roi_heads/mask_heads/fcn_mask_head.py:240-308) and the
 // sigmoid / class select / threshold / index_put around it in DynaMaskHead.get_seg_masks
@@ -7,31 +6,38 @@
 // [N,H,W,2] fp32 sampling grid (8 B per output pixel), an fp32 result, a thresholded copy and an
 // index_put; here the only HBM traffic is the N*H*W output bytes plus the N tiny masks.
 //
-// Arithmetic follows the reference expression order:
+// Arithmetic follows the reference:
 //   gx = ((px + .5) - x0) / (x1 - x0) * 2 - 1 ; +-inf -> 0        (fcn_mask_head.py:284-296)
 //   ix = ((gx + 1) * S_w - 1) / 2                                  (grid_sample, align_corners=False)
-//   bilinear, zero padding, four taps weighted (east-ix)*(south-iy) ...
+//   bilinear, zero padding.
 // Pixels whose sample falls outside (-1, S) are exactly zero; a conservative per-instance window
-// bounds the pixels that have to be evaluated at all.
+// bounds the pixels that have to be evaluated at all (~2-3 % of a COCO-shaped canvas).
 //
-// Work layout.  The [N, rh, rw] output is treated as one flat array cut into 16 KB tiles, one CTA
-// per tile (a write-only stream on this part runs fastest as many small CTAs, profiles/
-// r01_membench.md).  >90 % of the tiles miss their instance's window: they are four 16-byte
-// streaming zero stores per thread and nothing else.  A tile that meets the window
-//   1. zeroes a 16 KB shared image of itself,
-//   2. stages the source x coordinate of every window column (the x terms depend on the column
-//      only) and sigmoid(mask) of the mask rows its canvas rows can reach, with a zero border,
-//   3. evaluates the window pixels one per lane (a warp per canvas row) into the shared image,
-//   4. streams the image out with the same four 16-byte stores per thread.
-// Tiles that straddle two instances (or the end of the output) take a per-pixel path.
+// Two launches on the caller's stream:
+//   1. paste_fill_kernel: the whole [N, rh, rw] output leaves as zeros, 16 bytes per thread, one
+//      shot -- the flavour of write-only stream that runs fastest on this part
+//      (profiles/r01_membench.md: 7.4 TB/s).
+//   2. paste_window_kernel: grid = (16-row bands of a window, instances).  A CTA stages
+//      sigmoid(mask) for the mask rows its canvas rows can reach and the x terms of the window's
+//      columns (both depend on one axis only), then a warp per canvas row interpolates along y into
+//      a private row buffer and along x straight into global memory, one pixel per lane.
+// An earlier single-launch form (every 16 KB tile decides "zero or evaluate") spent more time in
+// the latency chains of its sparse live tiles than in the fill itself.
+//
+// The four-tap sum is evaluated separably, which regroups the reference's
+// nw*(wl*wn) + ne*(wh*wn) + sw*(wl*ws) + se*(wh*ws) as wl*(wn*nw + ws*sw) + wh*(wn*ne + ws*se):
+// a few 1e-8 apart, far inside the 1e-5 / 99.99 % bars (tests/test_gpu_parity.py).
+#include <cstdlib>
+
 #include "dm_common.cuh"
 
 namespace dm {
 
 constexpr int kPasteThreads = 256;
-constexpr int kTileBytes = 16384;   // output bytes per CTA: 4 x 16 B per thread
-constexpr int kIxTab = 2048;        // window columns whose x coordinate is staged in shared memory
-constexpr int kMaskStage = 3072;    // floats of sigmoid(mask) window staged per tile (12 KB)
+constexpr int kBandRows = 16;       // window rows per CTA
+constexpr int kColTab = 512;        // window columns whose x terms are staged in shared memory
+constexpr int kVRow = 256;          // floats of one warp's y-interpolated mask row (S + 2 <= 256)
+constexpr int kMaskStage = 3072;    // floats of sigmoid(mask) window staged per CTA (12 KB)
 
 struct PasteParams {
     const float* masks;
@@ -43,7 +49,6 @@ struct PasteParams {
     int img_h, img_w;
     int x_lo, y_lo, rw, rh;  // region origin and size
     long long total;         // N * rh * rw output elements
-    float inv_T;             // 1 / (rh * rw), first guess of the instance of a flat element index
     float thr;
     void* out;
 };
@@ -95,7 +100,7 @@ __device__ __forceinline__ AxisTerm axis_term(float i, int S) {
 }
 
 __device__ __forceinline__ float sigmoidf_exact(float v) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+    return __frcp_rn(__fadd_rn(1.0f, expf(-v)));  // == 1 / (1 + e^-v), correctly rounded
 }
 
 // the reference's four-tap sum, in grid_sample's order
@@ -149,147 +154,133 @@ struct Instance {
 };
 
 template <int MODE>
+__device__ __forceinline__ void put(const PasteParams& p, long long e, float v) {
+    if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(p.out)[e] = v;
+    else reinterpret_cast<uint8_t*>(p.out)[e] = (uint8_t)encode<MODE>(v, p.thr);
+}
+
+// 1. zero fill: one 16-byte streaming store per thread (the last, partial chunk element-wise)
+__global__ void __launch_bounds__(256) paste_fill_kernel(uint4* __restrict__ out, long long n16, long long nbytes) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n16) {
+        __stcs(out + i, make_uint4(0u, 0u, 0u, 0u));
+    } else if (i == n16) {
+        unsigned char* tail = reinterpret_cast<unsigned char*>(out + n16);
+        for (long long k = 0; k < nbytes - n16 * 16; ++k) tail[k] = 0;
+    }
+}
+
+// 2. the instances' windows
+template <int MODE>
 __global__ void __launch_bounds__(kPasteThreads, 5)
-paste_kernel(const __grid_constant__ PasteParams p) {
-    constexpr int ES = (MODE == DM_PASTE_F32) ? 4 : 1;  // bytes per output element
-    constexpr int V = 16 / ES;                          // elements per 16-byte chunk
-    constexpr int TE = kTileBytes / ES;                 // elements per tile
-    __shared__ __align__(16) unsigned char s_tile[kTileBytes];
-    __shared__ __align__(16) float s_mask[kMaskStage];
-    __shared__ float s_ix[kIxTab];
-
-    const long long E0 = (long long)blockIdx.x * TE;  // first flat element of the tile
-    const int T = p.rh * p.rw;                        // elements per instance (< 2^30, host-checked)
-    long long n = (long long)((float)E0 * p.inv_T);
-    n = n < 0 ? 0 : (n >= p.N ? p.N - 1 : n);
-    while (n * T > E0) --n;
-    while ((n + 1) * T <= E0) ++n;
-    uint4* const out16 = reinterpret_cast<uint4*>(p.out) + (long long)blockIdx.x * (kTileBytes / 16);
-
-    if (E0 + TE > (n + 1) * T) {
-        // ---- per-pixel path: the tile straddles instances or is the last, partial one ------------
-        Instance in;
-        long long cur = -1;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            const int ck = threadIdx.x + k * kPasteThreads;
-            const long long Ec = E0 + (long long)ck * V;
-            if (Ec >= p.total) break;
-            long long nc = Ec / T;
-            int e = (int)(Ec - nc * T);
-            int row = e / p.rw, col = e - row * p.rw;
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-            const int cnt = (int)min((long long)V, p.total - Ec);
-            for (int j = 0; j < cnt; ++j) {
-                if (nc != cur) { in.load(p, nc); cur = nc; }
-                const float v = in.eval(p.x_lo + col, p.y_lo + row);
-                if (MODE == DM_PASTE_F32) w[j & 3] = __float_as_uint(v);
-                else w[j >> 2] |= encode<MODE>(v, p.thr) << (8 * (j & 3));
-                if (++col == p.rw) { col = 0; if (++row == p.rh) { row = 0; ++nc; } }
-            }
-            if (cnt == V) {
-                __stcs(out16 + ck, make_uint4(w[0], w[1], w[2], w[3]));
-            } else {
-                for (int j = 0; j < cnt; ++j) {
-                    if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(p.out)[Ec + j] = __uint_as_float(w[j & 3]);
-                    else reinterpret_cast<uint8_t*>(p.out)[Ec + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
-                }
-            }
-        }
-        return;
-    }
-
-    // ---- the tile lies inside instance n: rows [row_b, row_e] of its region --------------------
-    const int e_lo = (int)(E0 - n * T);
-    const int row_b = e_lo / p.rw;
-    const int row_e = (e_lo + TE - 1) / p.rw;
-    const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
-    int xa, xb, ya, yb;
-    window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
-    window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
-    // window in region coordinates, clipped to the region and to the tile's rows
-    const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
-    const int ra = max(max(ya - p.y_lo, 0), row_b), rb = min(min(yb - p.y_lo, p.rh) - 1, row_e);  // inclusive
-    if (ra > rb || wxa >= wxb) {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) __stcs(out16 + threadIdx.x + k * kPasteThreads, z);
-        return;
-    }
-
-    // ---- live tile ---------------------------------------------------------------------------------
+paste_window_kernel(const __grid_constant__ PasteParams p) {
+    __shared__ __align__(16) float s_mask[kMaskStage];       // sigmoid(mask) rows, one-pixel zero border
+    __shared__ float4 s_col[kColTab];                        // x terms per window column {lo, wl, wh, state}
+    __shared__ float s_vrow[(kPasteThreads / 32) * kVRow];   // per warp: mask interpolated to one canvas row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(s_tile)[threadIdx.x + k * kPasteThreads] = z;
-    }
-    const int ww = wxb - wxa;
-    const bool use_tab = ww <= kIxTab;
-    if (use_tab)
-        for (int c = threadIdx.x; c < ww; c += kPasteThreads) s_ix[c] = src_coord(p.x_lo + wxa + c, bx.x, bx.z, p.sw);
-    const long long cls = p.labels ? p.labels[n] : 0;
-    const float* __restrict__ m = p.masks + n * p.stride_n + cls * p.stride_c;
     const int st_w = p.sw + 2;
-    int st_lo = 0;
-    bool staged = false;
-    {
-        // mask rows the live canvas rows can reach (the source coordinate is monotone in py)
-        const float ia = src_coord(p.y_lo + ra, bx.y, bx.w, p.sh);
-        const float ib = src_coord(p.y_lo + rb, bx.y, bx.w, p.sh);
-        if (ia == ia && ib == ib) {
-            const int lo = (int)fmaxf(floorf(fminf(ia, ib)), -1.0f);
-            const int hi = (int)fminf(floorf(fmaxf(ia, ib)) + 1.0f, (float)p.sh);
-            const int nrow = hi - lo + 1;
-            if (nrow >= 1 && nrow * st_w <= kMaskStage) {
-                for (int q = threadIdx.x; q < nrow * st_w; q += kPasteThreads) {
-                    const int yy = q / st_w;
-                    const int y = lo + yy, x = q - yy * st_w - 1;
-                    float v = 0.0f;
-                    if (y >= 0 && y < p.sh && x >= 0 && x < p.sw) {
-                        v = __ldg(m + y * p.sw + x);
-                        if (p.apply_sigmoid) v = sigmoidf_exact(v);
-                    }
-                    s_mask[q] = v;
+    const long long T = (long long)p.rh * p.rw;
+    for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
+        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
+        int xa, xb, ya, yb;
+        window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
+        // window in region coordinates, clipped to the region; this CTA's band of its rows
+        const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
+        const int r0 = wya + blockIdx.x * kBandRows;
+        if (r0 >= wyb) continue;  // CTA-uniform
+        const int r1 = min(r0 + kBandRows, wyb);  // exclusive
+        window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
+        const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
+        if (wxa >= wxb) continue;
+        const long long cls = p.labels ? p.labels[n] : 0;
+        const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
+        // mask rows the band's canvas rows can reach (the source coordinate is monotone in py)
+        bool staged = false;
+        int mlo = 0, mtot = 0;
+        {
+            const float ia = src_coord(p.y_lo + r0, bx.y, bx.w, p.sh);
+            const float ib = src_coord(p.y_lo + r1 - 1, bx.y, bx.w, p.sh);
+            if (ia == ia && ib == ib && st_w <= kVRow) {
+                mlo = (int)fmaxf(floorf(fminf(ia, ib)), -1.0f);
+                const int hi = (int)fminf(floorf(fmaxf(ia, ib)) + 1.0f, (float)p.sh);
+                const int mrows = hi - mlo + 1;
+                if (mrows >= 1 && mrows * st_w <= kMaskStage) { staged = true; mtot = mrows * st_w; }
+            }
+        }
+        long long obase = (long long)n * T;
+        if (!staged) {
+            // direct path (mask window larger than the scratch, NaN geometry): taps from global memory
+            Instance in;
+            in.load(p, n);
+            for (int r = r0 + warp; r < r1; r += kPasteThreads / 32)
+                for (int c = wxa + lane; c < wxb; c += 32) {
+                    const float v = in.eval(p.x_lo + c, p.y_lo + r);
+                    if (v != 0.0f) put<MODE>(p, obase + (long long)r * p.rw + c, v);
                 }
-                staged = true;
-                st_lo = lo;
-            }
+            continue;
         }
-    }
-    __syncthreads();
-
-    // ---- evaluate the window pixels of the tile: a warp per canvas row, a lane per pixel ----------
-    Instance in;
-    if (!staged) in.load(p, n);
-    for (int r = ra + warp; r <= rb; r += kPasteThreads / 32) {
-        const AxisTerm ry = axis_term(src_coord(p.y_lo + r, bx.y, bx.w, p.sh), p.sh);
-        if (ry.state == 0) continue;
-        const int e_row = r * p.rw - e_lo;  // tile offset of the row's column 0
-        const int ca = max(wxa, -e_row), cb = min(wxb, TE - e_row);
-        const float* mrow = s_mask + (ry.lo - st_lo) * st_w + 1;
-        for (int c = ca + lane; c < cb; c += 32) {
-            const float ix = use_tab ? s_ix[c - wxa] : src_coord(p.x_lo + c, bx.x, bx.z, p.sw);
-            const AxisTerm cx = axis_term(ix, p.sw);
-            if (cx.state == 0) continue;
-            float v;
-            if (cx.state == 2 || ry.state == 2) {
-                v = __int_as_float(0x7fc00000);
-            } else if (staged) {
-                const float* q = mrow + cx.lo;
-                v = bilerp(q[0], q[1], q[st_w], q[st_w + 1], cx, ry);
-            } else {
-                v = bilerp(in.tap(ry.lo, cx.lo), in.tap(ry.lo, cx.lo + 1), in.tap(ry.lo + 1, cx.lo),
-                           in.tap(ry.lo + 1, cx.lo + 1), cx, ry);
-            }
-            if (MODE == DM_PASTE_F32) reinterpret_cast<float*>(s_tile)[e_row + c] = v;
-            else s_tile[e_row + c] = (unsigned char)encode<MODE>(v, p.thr);
-        }
-    }
-    __syncthreads();
+        // ---- mask window: every load is issued before the first value is used ---------------------
+        constexpr int kPer = kMaskStage / kPasteThreads;  // 12 staged mask values per thread at most
+        float mv[kPer];
+        {
+            const unsigned magic = 0xFFFFFFFFu / (unsigned)st_w + 1u;  // exact q / st_w for q * st_w < 2^32
+            // outside the mask: sigmoid(-inf) == 0 exactly, so the border needs no second predicate
+            const float pad = p.apply_sigmoid ? __int_as_float(0xff800000) : 0.0f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        __stcs(out16 + threadIdx.x + k * kPasteThreads, reinterpret_cast<const uint4*>(s_tile)[threadIdx.x + k * kPasteThreads]);
+            for (int k = 0; k < kPer; ++k) {
+                const int q = threadIdx.x + k * kPasteThreads;
+                mv[k] = pad;
+                if (q < mtot) {
+                    const int yy = (int)__umulhi((unsigned)q, magic);
+                    const int y = mlo + yy, x = q - yy * st_w - 1;
+                    if (y >= 0 && y < p.sh && x >= 0 && x < p.sw) mv[k] = __ldg(m + y * p.sw + x);
+                }
+            }
+        }
+        __syncthreads();  // the scratch of the previous instance is no longer read
+        const int ww = wxb - wxa;
+        const bool use_tab = ww <= kColTab;
+        if (use_tab)
+            for (int c = threadIdx.x; c < ww; c += kPasteThreads) {
+                const AxisTerm a = axis_term(src_coord(p.x_lo + wxa + c, bx.x, bx.z, p.sw), p.sw);
+                s_col[c] = make_float4(__int_as_float(a.lo), a.wl, a.wh, __int_as_float(a.state));
+            }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int q = threadIdx.x + k * kPasteThreads;
+            if (q < mtot) s_mask[q] = p.apply_sigmoid ? sigmoidf_exact(mv[k]) : mv[k];
+        }
+        __syncthreads();
+        // ---- a warp per canvas row: y pass into the warp's row buffer, x pass to global memory -----
+        float* vr = s_vrow + warp * kVRow;
+        for (int r = r0 + warp; r < r1; r += kPasteThreads / 32) {
+            const AxisTerm ry = axis_term(src_coord(p.y_lo + r, bx.y, bx.w, p.sh), p.sh);
+            if (ry.state == 0) continue;  // warp-uniform
+            __syncwarp();
+            if (ry.state == 1) {
+                const float* m0 = s_mask + (ry.lo - mlo) * st_w;
+                for (int xx = lane; xx < st_w; xx += 32) vr[xx] = ry.wl * m0[xx] + ry.wh * m0[xx + st_w];
+            } else {
+                for (int xx = lane; xx < st_w; xx += 32) vr[xx] = __int_as_float(0x7fc00000);
+            }
+            __syncwarp();
+            const long long orow = obase + (long long)r * p.rw;
+            for (int c = wxa + lane; c < wxb; c += 32) {
+                AxisTerm cx;
+                if (use_tab) {
+                    const float4 ct = s_col[c - wxa];
+                    cx.lo = __float_as_int(ct.x); cx.wl = ct.y; cx.wh = ct.z; cx.state = __float_as_int(ct.w);
+                } else {
+                    cx = axis_term(src_coord(p.x_lo + c, bx.x, bx.z, p.sw), p.sw);
+                }
+                if (cx.state == 0) continue;
+                float v = __int_as_float(0x7fc00000);
+                if (cx.state == 1) v = cx.wl * vr[cx.lo + 1] + cx.wh * vr[cx.lo + 2];
+                if (MODE == DM_PASTE_F32) { if (v != 0.0f) put<MODE>(p, orow + c, v); }
+                else { const uint32_t b = encode<MODE>(v, p.thr); if (b) reinterpret_cast<uint8_t*>(p.out)[orow + c] = (uint8_t)b; }
+            }
+        }
+    }
 }
 
 }  // namespace dm
@@ -329,22 +320,20 @@ extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t
     p.thr = thr;
     p.out = out;
     p.total = per_inst * N;
-    p.inv_T = 1.0f / (float)per_inst;
     const int ES = out_mode == DM_PASTE_F32 ? 4 : 1;
-    const long long tiles = (p.total * ES + dm::kTileBytes - 1) / dm::kTileBytes;
-    if (tiles >= (1ll << 31)) return DM_EUNSUPPORTED;
-    dim3 grid((unsigned)tiles);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const long long nbytes = p.total * ES, n16 = nbytes / 16;
+        const long long blocks = (n16 + 1 + 255) / 256;
+        if (blocks >= (1ll << 31)) return DM_EUNSUPPORTED;
+        dm::paste_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(out), n16, nbytes);
+        DM_LAUNCH_CHECK("dm_paste_masks/fill");
+    }
+    dim3 grid((unsigned)((p.rh + dm::kBandRows - 1) / dm::kBandRows), (unsigned)(N < 65535 ? N : 65535));
     switch (out_mode) {
-        case DM_PASTE_BOOL:
-            dm::paste_kernel<DM_PASTE_BOOL><<<grid, dm::kPasteThreads, 0, st>>>(p);
-            break;
-        case DM_PASTE_U8:
-            dm::paste_kernel<DM_PASTE_U8><<<grid, dm::kPasteThreads, 0, st>>>(p);
-            break;
-        default:
-            dm::paste_kernel<DM_PASTE_F32><<<grid, dm::kPasteThreads, 0, st>>>(p);
-            break;
+        case DM_PASTE_BOOL: dm::paste_window_kernel<DM_PASTE_BOOL><<<grid, dm::kPasteThreads, 0, st>>>(p); break;
+        case DM_PASTE_U8: dm::paste_window_kernel<DM_PASTE_U8><<<grid, dm::kPasteThreads, 0, st>>>(p); break;
+        default: dm::paste_window_kernel<DM_PASTE_F32><<<grid, dm::kPasteThreads, 0, st>>>(p); break;
     }
     DM_LAUNCH_CHECK("dm_paste_masks");
     return DM_OK;

@@ -46,12 +46,14 @@ namespace dm {
 
 constexpr int kRaThreads = 256;
 constexpr int kRaWarps = kRaThreads / 32;
+constexpr int kFwdCtasPerSm = 3;  // forward: 24 warps per SM at <= 80 registers
 
 struct LevelDesc {
     float* ptr;  // const for forward, accumulated into for backward
     int N, C, H, W;
     long long sN, sC, sH, sW;
     float scale;
+    int cw;  // floats per asynchronous copy when staging patch rows: 4, 2 or 1 (alignment of rows)
 };
 
 struct BucketDesc {
@@ -110,6 +112,19 @@ __device__ __forceinline__ void ld_vec(const float* p, float (&a)[VEC]) {
 }
 
 template <int VEC>
+__device__ __forceinline__ void ld_vec_i(const int* p, int (&a)[VEC]) {
+    if (VEC == 4) {
+        const int4 v = *reinterpret_cast<const int4*>(p);
+        a[0] = v.x; a[1 % VEC] = v.y; a[2 % VEC] = v.z; a[3 % VEC] = v.w;
+    } else if (VEC == 2) {
+        const int2 v = *reinterpret_cast<const int2*>(p);
+        a[0] = v.x; a[1 % VEC] = v.y;
+    } else {
+        a[0] = *p;
+    }
+}
+
+template <int VEC>
 __device__ __forceinline__ void ldg_stream_vec(const float* p, float (&a)[VEC]) {
     if (VEC == 4) {
         const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
@@ -144,7 +159,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ---------------------------------------------------------------------------------------------
 // Banded weight tables of one RoI, staged in shared memory.
 // ---------------------------------------------------------------------------------------------
-enum { ST_JX = 0, ST_X0, ST_X1, ST_PA, ST_PB, ST_JY, ST_Y0, ST_Y1, ST_QA, ST_QB, ST_MR, ST_TW, ST_N };
+enum { ST_JX = 0, ST_X0, ST_X1, ST_PA, ST_PB, ST_JY, ST_Y0, ST_Y1, ST_QA, ST_QB, ST_MR, ST_TW, ST_NEED, ST_N };
 
 struct Tables {
     int* xs;    // [pw]  first feature column touched by bin pw
@@ -156,6 +171,7 @@ struct Tables {
     unsigned mR;   // FastDiv magic of R = Y1 - Y0 + 1
     float* ytab;   // packed per-pooled-row records {ys - Y0, wy[0..JYa)} when JYa is a window class
     int ystride;   // floats per record (4, 8 or 12), 0 when there is no packed table
+    int* rcnt;     // [R] pooled rows whose band starts at patch row r (only with a packed table)
     int floats;    // shared-memory floats consumed (multiple of 4)
 };
 
@@ -230,11 +246,14 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     t.JYa = wc ? wc : (window_class(t.JY) ? window_class(t.JY) : t.JY);
     const int wfloats = (t.JXa * Pw + t.JYa * Ph + 3) & ~3;
     t.ystride = (t.JYa == 2) ? 4 : (t.JYa == 4 ? 8 : (t.JYa == 8 ? 12 : 0));
-    t.floats = base + wfloats + t.ystride * Ph;
+    const int Rr = t.Y1 - t.Y0 + 1;
+    const int rfloats = t.ystride ? ((Rr + 3) & ~3) : 0;
+    t.floats = base + wfloats + t.ystride * Ph + rfloats;
     if (t.floats > smem_floats) { fits = false; return true; }
     t.wx = smem + base;
     t.wy = t.wx + t.JXa * Pw;
     t.ytab = smem + base + wfloats;
+    t.rcnt = reinterpret_cast<int*>(t.ytab + t.ystride * Ph);
     // bins without any valid sample sit at the two ends; give them a start that keeps xs / ys
     // monotone (their weights stay zero)
     const int xs_last = t.xs[pb], ys_last = t.ys[qb];
@@ -248,6 +267,7 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     for (int p = threadIdx.x; p < Ph; p += kRaThreads)
         if (t.ys[p] == INT_MAX) t.ys[p] = p < qa ? t.Y0 : ys_last;
     for (int i = threadIdx.x; i < wfloats; i += kRaThreads) t.wx[i] = 0.0f;
+    for (int i = threadIdx.x; i < rfloats; i += kRaThreads) t.rcnt[i] = 0;
     __syncthreads();
     axis_fill(Pw, W, g.rsw, g.bw, g.gw, t.xs, t.wx);
     axis_fill(Ph, H, g.rsh, g.bh, g.gh, t.ys, t.wy);
@@ -257,8 +277,12 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
         for (int i = threadIdx.x; i < Ph * t.ystride; i += kRaThreads) {
             const int ph = i / t.ystride, f = i - ph * t.ystride;
             float v = 0.0f;
-            if (f == 0) v = __int_as_float(t.ys[ph] - t.Y0);
-            else if (f <= t.JYa) v = t.wy[(f - 1) * Ph + ph];
+            if (f == 0) {
+                v = __int_as_float(t.ys[ph] - t.Y0);
+                atomicAdd(&t.rcnt[t.ys[ph] - t.Y0], 1);
+            } else if (f <= t.JYa) {
+                v = t.wy[(f - 1) * Ph + ph];
+            }
             t.ytab[i] = v;
         }
         __syncthreads();
@@ -423,85 +447,139 @@ __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0
 // to JW rows), Pw / VEC <= 32 strips per channel and a channel patch that fits the warp's slice.
 // `cpw` channels are processed per warp pass (lanes = cpw x PwV strips).
 // ---------------------------------------------------------------------------------------------
+// The warp's patches arrive as one continuous stream of patch rows (all rows of its first channel
+// batch, then of its next batch, ...) through a small ring of shared-memory row slots filled by
+// cp.async: kFwdPF rows are always in flight, so neither the start of a channel nor the slide of
+// the window ever waits for a cold load, and a warp needs ~1-3 KB of shared memory instead of a
+// whole patch.
+constexpr int kFwdPF = 5;             // patch rows in flight per warp
+constexpr int kFwdRing = kFwdPF + 2;  // + the row being read + the row other lanes may still read
+
+__device__ __forceinline__ void cp_async_w(int cw, float* dst, const float* src) {
+    if (cw == 4) cp_async<16>(dst, src);
+    else if (cw == 2) cp_async<8>(dst, src);
+    else cp_async<4>(dst, src);
+}
+
+// shared-memory floats of one ring slot: `cpw` channels x row stride
+__device__ __forceinline__ int fwd_row_stride(int X0, int X1, int cw, int jw, int& X0a, int& fwp) {
+    X0a = X0 & ~(cw - 1);              // patch rows start on a copy boundary
+    fwp = (X1 - X0a + cw) & ~(cw - 1);  // floats copied per row
+    return (fwp + jw - 1 + 3) & ~3;     // + zero pad for the padded taps
+}
+
+// Register budget matters here (three CTAs per SM = 80 registers): offsets are 32-bit (one
+// level's map and one RoI's pooled block are far below 2^31 floats), every lane owns at most one
+// copy per patch row (the caller keeps cpw * copies-per-row <= 32), and only scalars cross the
+// call boundary.
+struct FwdWarpArgs {
+    const float* src0;   // feature element (batch, c0, Y0, X0a)
+    float* obase;        // pooled element (i, c0, 0, 0)
+    const float* ytab;   // packed Y records (shared)
+    const int* rcnt;     // pooled rows per patch row (shared)
+    const int* xs;       // first feature column of every pooled column (shared)
+    const float* wx;     // folded X weights [JW][Pw] (shared)
+    float* ring;         // this warp's row slots (shared)
+    int sC, sH;          // feature strides in floats
+    int osC, osH;        // pooled strides in floats
+    int Pw, Ph, R, X0a, fws, cpr, cw, cpw, nc;
+};
+
 template <int VEC, int JW>
-__device__ void fwd_warp(const LevelDesc& Lv, const BucketDesc& B, const Tables t, float* wpatch, int cpw,
-                         int batch, int i, int c0, int nc) {
+__device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Pw = B.pw, Ph = B.ph, PwV = Pw / VEC;
-    const int fw = t.X1 - t.X0 + 1, fws = fw + JW - 1;
-    const int R = t.Y1 - t.Y0 + 1;
+    const int PwV = a.Pw / VEC;
+    const int R = a.R, cpw = a.cpw, nc = a.nc;
+    const int rowf = cpw * a.fws;  // floats per ring slot
     const int sub = lane / PwV, pv = lane - sub * PwV;
     const bool lane_on = sub < cpw;
-    const float* __restrict__ ytab = t.ytab;
-    // strip constants: the same for every channel of the RoI
-    int xo[VEC];
-    float wxr[JW][VEC];
+    const int subc = lane_on ? sub : 0;
+    const float* __restrict__ ytab = a.ytab;
+    const int* __restrict__ rcnt = a.rcnt;
+    float* const ring = a.ring;
+    // the function is not inlined: tell the compiler these all live in shared memory (LDS, not LD)
+    __builtin_assume(__isShared(ytab));
+    __builtin_assume(__isShared(rcnt));
+    __builtin_assume(__isShared(ring));
+    __builtin_assume(__isShared(a.xs));
+    __builtin_assume(__isShared(a.wx));
+    // strip constants (first patch column and X weights of this lane's VEC pooled columns) stay in
+    // shared memory and are re-read once per patch row: registers are the scarcer resource here
+    const int* const xsp = a.xs + (lane_on ? pv * VEC : 0);
+    const float* const wxp = a.wx + (lane_on ? pv * VEC : 0);
+    // the pad columns are never written by the copies: they must hold finite values
+    for (int q = lane * 4; q < kFwdRing * rowf; q += 128) *reinterpret_cast<float4*>(ring + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    // ---- producer side: this lane's copy of every patch row ---------------------------------------
+    const int step = kRaWarps * cpw;
+    const int cc_c = lane / a.cpr;                     // channel of this lane's copy inside the batch
+    const int cc_x = (lane - cc_c * a.cpr) * a.cw;     // first float of the copy inside the row
+    const float* i_src = a.src0 + (warp * cpw + cc_c) * a.sC + cc_x;  // this lane's source, next row to issue
+    float* const i_dst = ring + cc_c * a.fws + cc_x;
+    int i_cb = warp * cpw, i_r = 0, i_slot = 0;
+    auto issue = [&]() {
+        if (i_cb < nc) {
+            if (cc_c < min(cpw, nc - i_cb)) cp_async_w(a.cw, i_dst + i_slot * rowf, i_src);
+            i_src += a.sH;
+            if (++i_r == R) {
+                i_r = 0;
+                i_cb += step;
+                i_src += step * a.sC - R * a.sH;
+            }
+            i_slot = i_slot + 1 == kFwdRing ? 0 : i_slot + 1;
+        }
+        cp_async_commit();
+    };
+    // ---- consumer side: next patch row of the stream -> this lane's X-interpolated strip values ----
+    const float* pr = ring + subc * a.fws - a.X0a;  // this lane's channel in the slot being read next
+    int r_slot = 0;
+    auto consume = [&](float (&v)[VEC]) {
+        issue();
+        cp_async_wait<kFwdPF>();
+        __syncwarp();
+        int xo[VEC];
+        ld_vec_i<VEC>(xsp, xo);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-        xo[e] = lane_on ? t.xs[pv * VEC + e] - t.X0 : 0;
+        for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < JW; ++j) wxr[j][e] = lane_on ? t.wx[j * Pw + pv * VEC + e] : 0.0f;
-    }
-    const long long sC = Lv.sC, sH = Lv.sH, sW = Lv.sW, osH = B.sH;
-    const float* __restrict__ src0 = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * sC + (long long)t.Y0 * sH + (long long)t.X0 * sW;
-    float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC + (long long)(pv * VEC) * B.sW;
-    const float* mypatch = wpatch + sub * R * fws;
-    FastDiv fdR;
-    fdR.set(R, t.mR);
-    constexpr int PF = 8;  // patch rows in flight per lane while staging
-    for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
-        const int nact = min(cpw, nc - cb);
-        const int nrows = nact * R;
-        for (int x = lane; x < fws; x += 32) {
-            const float* __restrict__ sx = src0 + (long long)cb * sC + (long long)x * sW;
-            const bool live = x < fw;
-            for (int r0 = 0; r0 < nrows; r0 += PF) {
-                float v[PF];
+        for (int j = 0; j < JW; ++j) {
+            float wj[VEC];
+            ld_vec<VEC>(wxp + j * a.Pw, wj);
 #pragma unroll
-                for (int q = 0; q < PF; ++q) {
-                    const int row = r0 + q;
-                    v[q] = 0.0f;
-                    if (live && row < nrows) {
-                        const int c = fdR.div(row), r = row - c * R;
-                        v[q] = __ldg(sx + c * sC + r * sH);
-                    }
-                }
+            for (int e = 0; e < VEC; ++e) v[e] += wj[e] * pr[xo[e] + j];
+        }
+        if (++r_slot == kFwdRing) { r_slot = 0; pr -= (kFwdRing - 1) * rowf; } else { pr += rowf; }
+    };
 #pragma unroll
-                for (int q = 0; q < PF; ++q)
-                    if (r0 + q < nrows) wpatch[(r0 + q) * fws + x] = v[q];
+    for (int d = 0; d < kFwdPF; ++d) issue();
+
+    constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
+    float* o_cb = a.obase + (warp * cpw + subc) * a.osC + pv * VEC;
+    for (int cb = warp * cpw; cb < nc; cb += step, o_cb += step * a.osC) {
+        const bool on = lane_on && sub < nc - cb;
+        float win[JW][VEC];
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+            if (j < R) {
+                consume(win[j]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) win[j][e] = 0.0f;
             }
         }
-        __syncwarp();
-        if (lane_on && sub < nact) {
-            float win[JW][VEC];
-            auto xrow = [&](int r, float (&v)[VEC]) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
-                if (r < R) {
-                    const float* pr = mypatch + r * fws;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-#pragma unroll
-                        for (int j = 0; j < JW; ++j) v[e] += wxr[j][e] * pr[xo[e] + j];
-                    }
-                }
-            };
-            int base = 0;  // window row 0, relative to Y0 (ys[0] == Y0)
-#pragma unroll
-            for (int j = 0; j < JW; ++j) xrow(j, win[j]);
-            float* o = obase + (long long)(cb + sub) * B.sC;
-            for (int ph = 0; ph < Ph; ++ph) {
+        float* o = o_cb;
+        const float* yrec = ytab;
+        int left = a.Ph, base = 0;
+        // patch-row major: all pooled rows whose band starts at `base` share one window
+        for (;; ++base) {
+            const int n = rcnt[base];
+#pragma unroll 2
+            for (int k = 0; k < n; ++k) {
                 int y0;
                 float w[JW];
-                load_yrec<JW>(ytab, ph, y0, w);
-                while (base < y0) {
-#pragma unroll
-                    for (int j = 0; j + 1 < JW; ++j)
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
-                    ++base;
-                    xrow(base + JW - 1, win[JW - 1]);
-                }
+                load_yrec<JW>(yrec, 0, y0, w);
+                yrec += YS;
                 float acc[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) acc[e] = w[0] * win[0][e];
@@ -509,12 +587,29 @@ __device__ void fwd_warp(const LevelDesc& Lv, const BucketDesc& B, const Tables 
                 for (int j = 1; j < JW; ++j)
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) acc[e] += w[j] * win[j][e];
-                st_stream_vec<VEC>(o, acc);
-                o += osH;
+                if (on) st_stream_vec<VEC>(o, acc);
+                o += a.osH;
+            }
+            left -= n;
+            if (left <= 0) break;
+#pragma unroll
+            for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
+            if (base + JW < R) {
+                consume(win[JW - 1]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) win[JW - 1][e] = 0.0f;
             }
         }
-        __syncwarp();
+        // keep the stream aligned: rows of this batch the walk did not need
+        for (int r = base + JW; r < R; ++r) {
+            float dummy[VEC];
+            consume(dummy);
+        }
     }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -609,15 +704,26 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int Rfull = t.Y1 - t.Y0 + 1;
     const int wc = window_class(max(t.JX, t.JY));
     const int PwV = B.pw / VEC;
-    if (wc && PwV <= 32 && B.sW == 1) {
-        // fast path: every warp gets a private slice of shared memory for its channels' patches
+    if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
+        B.sC < (1 << 24) && B.sH < (1 << 24)) {
+        // fast path: every warp streams its channels' patch rows through a private ring of row slots
         const int slice = (avail / kRaWarps) & ~3;
-        const int cpw = min(32 / PwV, slice / (Rfull * (fw + wc - 1)));
-        if (cpw >= 1) {
-            float* wpatch = tile + (threadIdx.x >> 5) * slice;
-            if (wc == 2) fwd_warp<VEC, 2>(Lv, B, t, wpatch, cpw, batch, un.i, c0, c1 - c0);
-            else if (wc == 4) fwd_warp<VEC, 4>(Lv, B, t, wpatch, cpw, batch, un.i, c0, c1 - c0);
-            else fwd_warp<VEC, 8>(Lv, B, t, wpatch, cpw, batch, un.i, c0, c1 - c0);
+        FwdWarpArgs a;
+        int fwp;
+        a.cw = Lv.cw;
+        a.fws = fwd_row_stride(t.X0, t.X1, a.cw, wc, a.X0a, fwp);
+        a.cpr = fwp / a.cw;
+        a.cpw = min(min(32 / PwV, slice / (kFwdRing * a.fws)), 32 / a.cpr);
+        if (a.cpw >= 1) {
+            a.src0 = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + a.X0a;
+            a.obase = B.ptr + (long long)un.i * B.sN + (long long)c0 * B.sC;
+            a.ytab = t.ytab; a.rcnt = t.rcnt; a.xs = t.xs; a.wx = t.wx;
+            a.ring = tile + (threadIdx.x >> 5) * slice;
+            a.sC = (int)Lv.sC; a.sH = (int)Lv.sH; a.osC = (int)B.sC; a.osH = (int)B.sH;
+            a.Pw = B.pw; a.Ph = B.ph; a.R = Rfull; a.nc = c1 - c0;
+            if (wc == 2) fwd_warp<VEC, 2>(a);
+            else if (wc == 4) fwd_warp<VEC, 4>(a);
+            else fwd_warp<VEC, 8>(a);
             return;
         }
     }
@@ -654,60 +760,97 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // patch-gradient row is gathered from it (lane = feature column, its transposed X weights held in
 // registers) and reduced into the gradient map with one RED per element.
 constexpr int kRing = 8;   // ring depth of the grad_out prefetch, in pooled rows
-constexpr int kTWR = 16;   // transposed X weights a lane keeps in registers
+constexpr int kBwdRowBuf = 128;  // floats of the warp's row buffer: cpw rows of Pw rounded up to 4
+constexpr int kBwdPad = 84;      // zeros after the row buffer: the aligned tap windows may overrun it
 
-// Slow retire for geometries with more than 32 patch columns or more than NT taps per column.
-__device__ __noinline__ void bwd_retire_wide(const float* rowbuf, int Pw, int nact, int fw, int nt,
+// Taps the register windows of the fast retire do not cover: feature columns beyond the lanes'
+// reach and pooled columns beyond a lane's window (rare geometries).  `cover` = pooled columns a
+// lane group's windows span, `cols` = feature columns the lanes own.
+__device__ __noinline__ void bwd_retire_wide(const float* rowbuf, int Pws, int nact, int fw, int cols, int cover,
                                              const int* plo, const int* pcnt, const float* wxT, int TW,
-                                             float* drow0, long long dsC, int lane) {
+                                             float* drow0, int dsC, int lane) {
     for (int s2 = 0; s2 < nact; ++s2) {
-        const float* ur = rowbuf + s2 * Pw;
+        const float* ur = rowbuf + s2 * Pws;
         float* drow = drow0 + s2 * dsC;   // points at column 0 of the patch row
         for (int x = lane; x < fw; x += 32) {
-            const float* up = ur + plo[x];
+            const int lo = plo[x], n = pcnt[x];
+            const float* up = ur + lo;
             const float* wp = wxT + x * TW;
-            const int n = pcnt[x];
             float a = 0.0f;
-            for (int q = (x < 32 ? nt : 0); q < n; ++q) a += wp[q] * up[q];
+            for (int q = (x < cols ? min(n, (lo & ~3) + cover - lo) : 0); q < n; ++q) a += wp[q] * up[q];
             if (a != 0.0f) atomicAdd(drow + x, a);
         }
     }
 }
 
+struct BwdWarpArgs {
+    const float* gbase;  // grad_out element (i, c0, 0, 0)
+    float* dbase;        // gradient-map element (batch, c0, Y0, X0)
+    const float* ytab;   // packed Y records (shared)
+    const int* rcnt;     // pooled rows per band row (shared)
+    const int* plo;      // first pooled column touching feature column x (shared)
+    const int* pcnt;     // pooled columns touching feature column x (shared)
+    const float* wxT;    // transposed X weights [fw][TW] (shared)
+    float* wsm;          // this warp's scratch (shared)
+    int gsC, gsH, dsC, dsH;
+    int Ph, Pw, R, fw, TW, cpw, nc;
+    int split;           // lanes per feature column (1, 2 or 4): taps of one column split across lanes
+    int wide;            // some taps are outside the register windows
+};
+
 // The hot loop lives in a __noinline__ function taking plain scalars so that every instantiation
 // gets its own register allocation and nothing is re-derived from the kernel-parameter structs
 // inside the loop.  Requirements (checked by the caller): unit inner stride of grad_out and of the
-// gradient map, Pw / VEC <= 32, JY <= JW.  NT = transposed X taps a lane keeps in registers.
-template <int VEC, int JW, int NT>
-__device__ __noinline__ void bwd_warp_core(const float* gbase, long long gsC, long long gsH, float* dbase,
-                                           long long dsC, long long dsH, const float* __restrict__ ytab,
-                                           int Ph, int Pw, int R, int fw, const int* plo, const int* pcnt,
-                                           const float* wxT, int TW, float* wsm, int cpw, int nc) {
+// gradient map, Pw / VEC <= 32, JY <= JW.
+// Retire: lane group `part` of feature column x holds the X weights of the 4 * NV pooled columns
+// starting at (plo[x] & ~3) + 4 * NV * part in registers, reads them from the row buffer with NV
+// 16-byte loads, and the parts are summed with shuffles: one RED per touched feature pixel.
+template <int VEC, int JW, int NV>
+__device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Pw = a.Pw, Ph = a.Ph, R = a.R, cpw = a.cpw, nc = a.nc;
     const int PwV = Pw / VEC;
+    const int Pws = (Pw + 3) & ~3;
     const int sub = lane / PwV, pv = lane - sub * PwV;
     const bool lane_on = sub < cpw;
-    gbase += pv * VEC;
-    // warp-private shared memory: [kRing][32 lanes][VEC] prefetch ring, then [cpw][Pw] row buffer
-    // followed by kTWR zeros
-    float* const ring = wsm + lane * VEC;
-    float* const rowbuf = wsm + kRing * 32 * VEC;
-    float* const myrow = rowbuf + sub * Pw + pv * VEC;
-    for (int q = lane; q < kTWR; q += 32) rowbuf[cpw * Pw + q] = 0.0f;
-    // this lane's feature column when it acts as x-owner, with its taps in registers
-    const int xn = lane < fw ? pcnt[lane] : 0;
-    const float* const upx = rowbuf + (lane < fw ? plo[lane] : 0);
-    float wq[NT];
+    const float* __restrict__ ytab = a.ytab;
+    const int* __restrict__ rcnt = a.rcnt;
+    __builtin_assume(__isShared(ytab));
+    __builtin_assume(__isShared(rcnt));
+    __builtin_assume(__isShared(a.wsm));
+    __builtin_assume(__isShared(a.plo));
+    __builtin_assume(__isShared(a.pcnt));
+    __builtin_assume(__isShared(a.wxT));
+    // warp-private shared memory: [kRing][32 lanes][VEC] prefetch ring, then [cpw][Pws] row buffer
+    // followed by kBwdPad zeros
+    float* const ring = a.wsm + lane * VEC;
+    float* const rowbuf = a.wsm + kRing * 32 * VEC;
+    float* const myrow = rowbuf + (lane_on ? sub : 0) * Pws + pv * VEC;
+    // zero weights meet whatever lies beyond a window's taps: it must be finite
+    for (int q = lane; q < kBwdRowBuf + kBwdPad; q += 32) rowbuf[q] = 0.0f;
+    // this lane as owner of a feature column: its tap window, weights in registers
+    const int cols = 32 / a.split;
+    const int part = lane / cols, xl = lane - part * cols;
+    const bool xon = xl < a.fw;
+    const int xlo = xon ? a.plo[xl] : 0, xn = xon ? a.pcnt[xl] : 0;
+    const int pa = xon ? (xlo & ~3) + 4 * NV * part : 0;
+    const float* const upx = rowbuf + pa;
+    float wq[4 * NV];
 #pragma unroll
-    for (int q = 0; q < NT; ++q) wq[q] = (q < xn) ? wxT[lane * TW + q] : 0.0f;
-    const bool wide = fw > 32 || TW > NT;
+    for (int q = 0; q < 4 * NV; ++q) {
+        const int t = pa + q - xlo;
+        wq[q] = (t >= 0 && t < xn) ? a.wxT[xl * a.TW + t] : 0.0f;
+    }
+    const bool red_on = xon && part == 0;
     __syncwarp();
 
+    const float* gwarp = a.gbase + pv * VEC;
+    constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
     for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
-        const float* gnext = gbase + (cb + sub) * gsC;  // next pooled row to prefetch
-        float* drow = dbase + cb * dsC;                 // gradient-map row being retired (+lane)
+        const float* gnext = gwarp + (cb + (lane_on ? sub : 0)) * a.gsC;  // next pooled row to prefetch
+        float* drow = a.dbase + cb * a.dsC + xl;                           // gradient-map row being retired
         float acc[JW][VEC];
 #pragma unroll
         for (int j = 0; j < JW; ++j)
@@ -716,28 +859,64 @@ __device__ __noinline__ void bwd_warp_core(const float* gbase, long long gsC, lo
 #pragma unroll
         for (int d = 0; d < kRing - 1; ++d) {
             if (on && d < Ph) cp_async<VEC * 4>(ring + d * 32 * VEC, gnext);
-            gnext += gsH;
+            gnext += a.gsH;
             cp_async_commit();
         }
-        // band row `base` is complete for every lane of the warp: reduce it into the map
-        auto retire = [&]() {
+        int slot_w = kRing - 1;    // ring slot the next prefetch lands in
+        int slot_r = 0;            // ring slot holding the next pooled row
+        int pre = Ph - (kRing - 1);  // pooled rows still to be requested
+        const float* yrec = ytab;
+        // band-row major: once the pooled rows whose band starts at `base` are in, band row `base`
+        // is complete for every lane of the warp
+        for (int base = 0; base < R; ++base) {
+            const int n = rcnt[base];
+            for (int k = 0; k < n; ++k) {
+                if (on && pre > 0) cp_async<VEC * 4>(ring + slot_w * 32 * VEC, gnext);
+                --pre;
+                gnext += a.gsH;
+                slot_w = (slot_w + 1) & (kRing - 1);
+                cp_async_commit();
+                int y0;
+                float w[JW];
+                load_yrec<JW>(yrec, 0, y0, w);
+                yrec += YS;
+                cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
+                float gv[VEC];
+                ld_vec<VEC>(ring + slot_r * 32 * VEC, gv);
+                slot_r = (slot_r + 1) & (kRing - 1);
+#pragma unroll
+                for (int j = 0; j < JW; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * gv[e];
+            }
+            // ---- retire band row `base` -----------------------------------------------------------
             if (on) {
                 if (VEC == 1) myrow[0] = acc[0][0];
                 else if (VEC == 2) *reinterpret_cast<float2*>(myrow) = make_float2(acc[0][0], acc[0][1 % VEC]);
                 else *reinterpret_cast<float4*>(myrow) = make_float4(acc[0][0], acc[0][1 % VEC], acc[0][2 % VEC], acc[0][3 % VEC]);
             }
             __syncwarp();
-            const float* up = upx;
-            float* dp = drow;
-            for (int s2 = 0; s2 < nact; ++s2) {
-                float a = 0.0f;
+            {
+                const float* up = upx;
+                float* dp = drow;
+                for (int s2 = 0; s2 < nact; ++s2) {
+                    float r = 0.0f;
 #pragma unroll
-                for (int q = 0; q < NT; ++q) a += wq[q] * up[q];
-                if (a != 0.0f) atomicAdd(dp, a);
-                up += Pw;
-                dp += dsC;
+                    for (int v = 0; v < NV; ++v) {
+                        const float4 u = *reinterpret_cast<const float4*>(up + 4 * v);
+                        r += wq[4 * v] * u.x;
+                        r += wq[4 * v + 1] * u.y;
+                        r += wq[4 * v + 2] * u.z;
+                        r += wq[4 * v + 3] * u.w;
+                    }
+                    if (a.split >= 4) r += __shfl_down_sync(0xffffffffu, r, 16);
+                    if (a.split >= 2) r += __shfl_down_sync(0xffffffffu, r, a.split >= 4 ? 8 : 16);
+                    if (red_on && r != 0.0f) atomicAdd(dp, r);
+                    up += Pws;
+                    dp += a.dsC;
+                }
             }
-            if (wide) bwd_retire_wide(rowbuf, Pw, nact, fw, NT, plo, pcnt, wxT, TW, drow - lane, dsC, lane);
+            if (a.wide) bwd_retire_wide(rowbuf, Pws, nact, a.fw, cols, 4 * NV * a.split, a.plo, a.pcnt, a.wxT, a.TW, drow - xl, a.dsC, lane);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j + 1 < JW; ++j)
@@ -745,36 +924,7 @@ __device__ __noinline__ void bwd_warp_core(const float* gbase, long long gsC, lo
                 for (int e = 0; e < VEC; ++e) acc[j][e] = acc[j + 1][e];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
-            drow += dsH;
-        };
-        int base = 0;              // window row 0 relative to Y0
-        int slot_w = kRing - 1;    // ring slot the next prefetch lands in
-        int slot_r = 0;            // ring slot holding pooled row `ph`
-        const int Ppre = Ph - (kRing - 1);
-        for (int ph = 0; ph < Ph; ++ph) {
-            if (on && ph < Ppre) cp_async<VEC * 4>(ring + slot_w * 32 * VEC, gnext);
-            gnext += gsH;
-            slot_w = (slot_w + 1) & (kRing - 1);
-            cp_async_commit();
-            int y0;
-            float w[JW];
-            load_yrec<JW>(ytab, ph, y0, w);
-            while (base < y0) {
-                retire();
-                ++base;
-            }
-            cp_async_wait<kRing - 1>();  // this lane's copy of pooled row `ph` has landed
-            float gv[VEC];
-            ld_vec<VEC>(ring + slot_r * 32 * VEC, gv);
-            slot_r = (slot_r + 1) & (kRing - 1);
-#pragma unroll
-            for (int j = 0; j < JW; ++j)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * gv[e];
-        }
-        while (base < R) {
-            retire();
-            ++base;
+            drow += a.dsH;
         }
         cp_async_wait<0>();
         __syncwarp();
@@ -782,22 +932,14 @@ __device__ __noinline__ void bwd_warp_core(const float* gbase, long long gsC, lo
 }
 
 template <int VEC, int JW>
-__device__ __forceinline__ void bwd_warp(const LevelDesc& Lv, const BucketDesc& B, const float* ytab, int X0,
-                                         int Y0, int fw, int R, const int* plo, const int* pcnt,
-                                         const float* wxT, int TW, float* wsm, int cpw, int batch, int i,
-                                         int c0, int nc) {
-    const int lane = threadIdx.x & 31;
-    const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-    float* dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)Y0 * Lv.sH + X0 + lane;
-    // up-sampling buckets (JW == 2) can have many pooled columns per feature column; the others few
-    if (JW == 2 && TW > 4)
-        bwd_warp_core<VEC, JW, kTWR>(gbase, B.sC, B.sH, dbase, Lv.sC, Lv.sH, ytab, B.ph, B.pw, R, fw, plo, pcnt, wxT, TW, wsm, cpw, nc);
-    else
-        bwd_warp_core<VEC, JW, 4>(gbase, B.sC, B.sH, dbase, Lv.sC, Lv.sH, ytab, B.ph, B.pw, R, fw, plo, pcnt, wxT, TW, wsm, cpw, nc);
+__device__ __forceinline__ void bwd_warp(const BwdWarpArgs& a, int need) {
+    // tap windows: 8 pooled columns per lane when that covers every feature column, else 20
+    if (need <= 8 * a.split) bwd_warp_core<VEC, JW, 2>(a);
+    else bwd_warp_core<VEC, JW, 5>(a);
 }
 
 // shared-memory floats a warp needs on the fast path: ring + row buffer + zero pad
-__host__ __device__ constexpr int kBwdWarpFloats(int vec) { return kRing * 32 * vec + 32 * vec + kTWR + 4; }
+__host__ __device__ constexpr int kBwdWarpFloats(int vec) { return kRing * 32 * vec + kBwdRowBuf + kBwdPad + 4; }
 
 // Column pass, generic path for bands taller than 8 rows: shared-memory reductions into a zeroed U.
 template <int VEC>
@@ -880,7 +1022,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     int* pcnt = plo + fw;
     int* s_tw = stat + ST_TW;
     if (fits && 2 * fw <= p.smem_floats - t.floats) {
-        if (threadIdx.x == 0) *s_tw = 0;
+        if (threadIdx.x == 0) { *s_tw = 0; stat[ST_NEED] = 0; }
         __syncthreads();
         for (int x = threadIdx.x; x < fw; x += kRaThreads) {
             const int xa = x + t.X0;
@@ -900,6 +1042,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
             plo[x] = a;
             pcnt[x] = n;
             atomicMax(s_tw, n);
+            atomicMax(&stat[ST_NEED], n + (a & 3));
         }
         __syncthreads();
     }
@@ -923,14 +1066,27 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
     {
         const int PwV = B.pw / VEC;
-        if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1) {
+        if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
+            B.sC < (1 << 24) && B.sH < (1 << 24)) {
             // fast path: warp-private ring + row buffer, no CTA-wide barrier after this point
-            const int cpw = 32 / PwV;
             __syncthreads();
-            float* wsm = smem + t.floats + extra + (threadIdx.x >> 5) * kBwdWarpFloats(VEC);
-            if (wc == 2) bwd_warp<VEC, 2>(Lv, B, t.ytab, t.X0, t.Y0, fw, R, plo, pcnt, wxT, TW, wsm, cpw, batch, un.i, c0, c1 - c0);
-            else if (wc == 4) bwd_warp<VEC, 4>(Lv, B, t.ytab, t.X0, t.Y0, fw, R, plo, pcnt, wxT, TW, wsm, cpw, batch, un.i, c0, c1 - c0);
-            else bwd_warp<VEC, 8>(Lv, B, t.ytab, t.X0, t.Y0, fw, R, plo, pcnt, wxT, TW, wsm, cpw, batch, un.i, c0, c1 - c0);
+            BwdWarpArgs a;
+            a.gbase = B.ptr + (long long)un.i * B.sN + (long long)c0 * B.sC;
+            a.dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + t.X0;
+            a.ytab = t.ytab; a.rcnt = t.rcnt; a.plo = plo; a.pcnt = pcnt; a.wxT = wxT;
+            a.wsm = smem + t.floats + extra + (threadIdx.x >> 5) * kBwdWarpFloats(VEC);
+            a.gsC = (int)B.sC; a.gsH = (int)B.sH; a.dsC = (int)Lv.sC; a.dsH = (int)Lv.sH;
+            a.Ph = B.ph; a.Pw = B.pw; a.R = R; a.fw = fw; a.TW = TW; a.cpw = 32 / PwV; a.nc = c1 - c0;
+            // lanes per feature column: split the taps of narrow patches over 2 or 4 lanes
+            const int need = stat[ST_NEED];
+            a.split = 1;
+            if (need > 20 && fw <= 16) a.split = 2;
+            if (need > 40 && fw <= 8) a.split = 4;
+            const int cover = (need <= 8 * a.split ? 8 : 20) * a.split;
+            a.wide = (fw > 32 / a.split || need > cover) ? 1 : 0;
+            if (wc == 2) bwd_warp<VEC, 2>(a, need);
+            else if (wc == 4) bwd_warp<VEC, 4>(a, need);
+            else bwd_warp<VEC, 8>(a, need);
             return;
         }
     }
@@ -956,7 +1112,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __launch_bounds__(kRaThreads, 2) ra_kernel(const __grid_constant__ RaParams p) {
+__global__ void __launch_bounds__(kRaThreads, BWD ? 2 : kFwdCtasPerSm) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
@@ -1017,6 +1173,12 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
         d.sW = feat_strides[4 * l + 3];
         d.scale = spatial_scales[l];
         if (!d.ptr || d.N < 1 || d.C != p.C || d.H < 1 || d.W < 1) return DM_EINVAL;
+        d.cw = 1;
+        if (d.sW == 1) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(d.ptr);
+            if (d.W % 4 == 0 && d.sH % 4 == 0 && d.sC % 4 == 0 && d.sN % 4 == 0 && a % 16 == 0) d.cw = 4;
+            else if (d.W % 2 == 0 && d.sH % 2 == 0 && d.sC % 2 == 0 && d.sN % 2 == 0 && a % 8 == 0) d.cw = 2;
+        }
     }
     if (p.C < 1) return DM_EINVAL;
     for (int b = 0; b < nb; ++b) {
@@ -1068,7 +1230,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
 
 template <bool BWD>
 static int launch(RaParams& p, cudaStream_t st, const char* where) {
-    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 72 : 100);
+    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 72 : 72);
     const int smem_bytes = smem_kb * 1024;
     p.smem_floats = smem_bytes / 4;
     DM_CUDA_CHECK(cudaFuncSetAttribute(ra_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);

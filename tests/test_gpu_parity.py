@@ -319,7 +319,8 @@ def _dets(n, img_h, img_w, seed):
     return logits, boxes
 
 
-@pytest.mark.parametrize('shape', [(800, 1333), (427, 640)])
+# (431, 637): canvas bytes not a multiple of 16 -> flat tiling with tiles that straddle instances
+@pytest.mark.parametrize('shape', [(800, 1333), (427, 640), (431, 637), (37, 23)])
 def test_get_seg_masks_pixel_agreement(shape):
     img_h, img_w = shape
     logits, boxes = _dets(30, img_h, img_w, 41)

@@ -94,6 +94,27 @@ __global__ void red_kernel(float* __restrict__ p, size_t n) {
     }
 }
 
+// RoIAlign-forward-like write pattern: each warp (MODE 0) or each CTA (MODE 1: warp w takes rows
+// w, w+8, ...) streams whole [112][112] fp32 planes, 28 lanes x 16 B per row, persistent CTAs.
+template <int MODE>
+__global__ void plane_writer(float4* __restrict__ p, size_t nplanes) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float4 z = make_float4(1.f, 2.f, 3.f, 4.f);
+    if (MODE == 0) {
+        for (size_t pl = (size_t)blockIdx.x * nw + warp; pl < nplanes; pl += (size_t)gridDim.x * nw) {
+            float4* q = p + pl * (112 * 28) + lane;
+            if (lane < 28)
+                for (int r = 0; r < 112; ++r) __stcs(q + r * 28, z);
+        }
+    } else {
+        for (size_t pl = blockIdx.x; pl < nplanes; pl += gridDim.x) {
+            float4* q = p + pl * (112 * 28) + lane;
+            if (lane < 28)
+                for (int r = warp; r < 112; r += nw) __stcs(q + r * 28, z);
+        }
+    }
+}
+
 template <class F>
 static double time_ms(F f, int reps = 10) {
     cudaEvent_t a, b;
@@ -149,6 +170,17 @@ int main(int argc, char** argv) {
     REPORT("cudaMemcpyAsync D2D (read+write bytes)", CK(cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice)), 2 * gb);
     REPORT("red.add.f32 scalar, every address once (bytes = 4/elem)", (red_kernel<1><<<sms * 16, 256>>>((float*)a, bytes / 4)), gb);
     REPORT("red.add.v4.f32, every address once", (red_kernel<4><<<sms * 16, 256>>>((float*)a, bytes / 4)), gb);
+    {
+        const size_t nplanes = bytes / (112 * 112 * 4);
+        const double pgb = nplanes * 112.0 * 112 * 4 / 1e9;
+        for (int cps : {2, 3, 4, 8}) {
+            char nm[96];
+            snprintf(nm, 96, "plane writer, warp per plane, %d CTAs/SM x 256", cps);
+            REPORT(nm, (plane_writer<0><<<sms * cps, 256>>>((float4*)a, nplanes)), pgb);
+            snprintf(nm, 96, "plane writer, CTA per plane, %d CTAs/SM x 256", cps);
+            REPORT(nm, (plane_writer<1><<<sms * cps, 256>>>((float4*)a, nplanes)), pgb);
+        }
+    }
     // smaller-than-L2 fill for reference
     REPORT("fill st.v4 .cs 64 MiB (L2 resident)", (fill_kernel<1><<<sms * 8, 256>>>((uint4*)a, (64u << 20) / 16)), (64u << 20) / 1e9);
     return 0;
