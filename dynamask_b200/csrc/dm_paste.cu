@@ -34,10 +34,10 @@
 namespace dm {
 
 constexpr int kPasteThreads = 256;
-constexpr int kBandRows = 16;       // window rows per CTA
-constexpr int kColTab = 512;        // window columns whose x terms are staged in shared memory
-constexpr int kVRow = 256;          // floats of one warp's y-interpolated mask row (S + 2 <= 256)
-constexpr int kMaskStage = 3072;    // floats of sigmoid(mask) window staged per CTA (12 KB)
+constexpr int kBandRows = 32;       // window rows per CTA
+constexpr int kColTab = 1024;       // window columns whose x terms are staged in shared memory (8 KB)
+constexpr int kVPairs = 128;        // (value, slope) pairs of one warp's y-interpolated mask row: S + 3 <= 128
+constexpr int kMaskStage = 6144;    // floats of sigmoid(mask) window staged per CTA (24 KB)
 
 struct PasteParams {
     const float* masks;
@@ -98,6 +98,9 @@ __device__ __forceinline__ AxisTerm axis_term(float i, int S) {
     t.state = 1;
     return t;
 }
+
+// staged path: ex2.approx + approximate reciprocal (~1e-7 from the exact form)
+__device__ __forceinline__ float sigmoidf_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ float sigmoidf_exact(float v) {
     return __frcp_rn(__fadd_rn(1.0f, expf(-v)));  // == 1 / (1 + e^-v), correctly rounded
@@ -171,27 +174,44 @@ __global__ void __launch_bounds__(256) paste_fill_kernel(uint4* __restrict__ out
 }
 
 // 2. the instances' windows
+//
+// Per canvas row r the warp builds VD[i] = (V[x], V[x+1] - V[x]) for mask column x = i - 1, where
+// V[x] = wn * sigmoid(mask)[yn][x] + ws * sigmoid(mask)[yn+1][x] (zero outside the mask); a pixel
+// is then V[lo] + wh * (V[lo+1] - V[lo]) -- one 8-byte table read, one 8-byte VD read, one FMA.
+// Columns whose sample misses (-1, S) point at a (0, 0) entry, NaN columns at a (NaN, NaN) entry,
+// so the pixel loop has no branches.
 template <int MODE>
 __global__ void __launch_bounds__(kPasteThreads, 5)
 paste_window_kernel(const __grid_constant__ PasteParams p) {
-    __shared__ __align__(16) float s_mask[kMaskStage];       // sigmoid(mask) rows, one-pixel zero border
-    __shared__ float4 s_col[kColTab];                        // x terms per window column {lo, wl, wh, state}
-    __shared__ float s_vrow[(kPasteThreads / 32) * kVRow];   // per warp: mask interpolated to one canvas row
+    __shared__ __align__(16) float s_mask[kMaskStage];          // sigmoid(mask) rows, one-pixel zero border
+    __shared__ __align__(8) float2 s_col[kColTab];              // per window column {VD index, wh}
+    __shared__ __align__(8) float2 s_vd[kPasteThreads / 32][kVPairs];
+    __shared__ __align__(16) float4 s_row[kBandRows];           // per band row {lo, wl, wh, state}
+    __shared__ int s_win[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int st_w = p.sw + 2;
+    const int zero_i = p.sw + 1, nan_i = p.sw + 2;  // VD entries for "exactly zero" / "NaN" columns
     const long long T = (long long)p.rh * p.rw;
     for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
         const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
-        int xa, xb, ya, yb;
-        window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
-        // window in region coordinates, clipped to the region; this CTA's band of its rows
-        const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
-        const int r0 = wya + blockIdx.x * kBandRows;
-        if (r0 >= wyb) continue;  // CTA-uniform
-        const int r1 = min(r0 + kBandRows, wyb);  // exclusive
-        window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
-        const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
-        if (wxa >= wxb) continue;
+        // most CTAs of the grid lie below their instance's window: only warp 0 does the window
+        // arithmetic, the other warps wait for its verdict
+        if (warp == 0) {
+            int xa, xb, ya, yb;
+            window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
+            window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
+            if (lane == 0) {
+                // window in region coordinates, clipped to the region
+                s_win[0] = max(ya - p.y_lo, 0); s_win[1] = min(yb - p.y_lo, p.rh);
+                s_win[2] = max(xa - p.x_lo, 0); s_win[3] = min(xb - p.x_lo, p.rw);
+            }
+        }
+        __syncthreads();
+        const int wya = s_win[0], wyb = s_win[1], wxa = s_win[2], wxb = s_win[3];
+        __syncthreads();  // s_win may be rewritten for the next instance
+        const int r0 = wya + blockIdx.x * kBandRows;  // this CTA's band of the window's rows
+        if (r0 >= wyb || wxa >= wxb) continue;        // CTA-uniform
+        const int r1 = min(r0 + kBandRows, wyb);      // exclusive
         const long long cls = p.labels ? p.labels[n] : 0;
         const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
         // mask rows the band's canvas rows can reach (the source coordinate is monotone in py)
@@ -200,16 +220,17 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
         {
             const float ia = src_coord(p.y_lo + r0, bx.y, bx.w, p.sh);
             const float ib = src_coord(p.y_lo + r1 - 1, bx.y, bx.w, p.sh);
-            if (ia == ia && ib == ib && st_w <= kVRow) {
+            if (ia == ia && ib == ib && p.sw + 3 <= kVPairs) {
                 mlo = (int)fmaxf(floorf(fminf(ia, ib)), -1.0f);
                 const int hi = (int)fminf(floorf(fmaxf(ia, ib)) + 1.0f, (float)p.sh);
                 const int mrows = hi - mlo + 1;
                 if (mrows >= 1 && mrows * st_w <= kMaskStage) { staged = true; mtot = mrows * st_w; }
             }
         }
-        long long obase = (long long)n * T;
+        const long long obase = (long long)n * T;
         if (!staged) {
-            // direct path (mask window larger than the scratch, NaN geometry): taps from global memory
+            // direct path (small boxes: the band reaches more mask rows than the scratch holds; NaN
+            // geometry): taps from global memory
             Instance in;
             in.load(p, n);
             for (int r = r0 + warp; r < r1; r += kPasteThreads / 32)
@@ -219,65 +240,89 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
                 }
             continue;
         }
-        // ---- mask window: every load is issued before the first value is used ---------------------
-        constexpr int kPer = kMaskStage / kPasteThreads;  // 12 staged mask values per thread at most
-        float mv[kPer];
+        __syncthreads();  // the scratch of the previous instance is no longer read
+        // ---- mask window: a warp per mask row, every load of the row issued before its first use ----
         {
-            const unsigned magic = 0xFFFFFFFFu / (unsigned)st_w + 1u;  // exact q / st_w for q * st_w < 2^32
-            // outside the mask: sigmoid(-inf) == 0 exactly, so the border needs no second predicate
-            const float pad = p.apply_sigmoid ? __int_as_float(0xff800000) : 0.0f;
+            const int mrows = mtot / st_w;
+            for (int yy = warp; yy < mrows; yy += kPasteThreads / 32) {
+                const int y = mlo + yy;
+                const bool yin = y >= 0 && y < p.sh;
+                const float* __restrict__ mr = m + y * p.sw - 1;
+                float* sr = s_mask + yy * st_w;
+                float mv[4];
 #pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                const int q = threadIdx.x + k * kPasteThreads;
-                mv[k] = pad;
-                if (q < mtot) {
-                    const int yy = (int)__umulhi((unsigned)q, magic);
-                    const int y = mlo + yy, x = q - yy * st_w - 1;
-                    if (y >= 0 && y < p.sh && x >= 0 && x < p.sw) mv[k] = __ldg(m + y * p.sw + x);
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = lane + 32 * k;  // st_w <= kVPairs = 128
+                    mv[k] = 0.0f;
+                    if (yin && xx >= 1 && xx <= p.sw) mv[k] = __ldg(mr + xx);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = lane + 32 * k;
+                    if (xx < st_w) {
+                        float v = mv[k];
+                        if (p.apply_sigmoid) v = sigmoidf_fast(v);
+                        sr[xx] = (yin && xx >= 1 && xx <= p.sw) ? v : 0.0f;
+                    }
                 }
             }
         }
-        __syncthreads();  // the scratch of the previous instance is no longer read
         const int ww = wxb - wxa;
         const bool use_tab = ww <= kColTab;
+        auto col_entry = [&](int c) -> float2 {  // c in region coordinates
+            const AxisTerm a = axis_term(src_coord(p.x_lo + c, bx.x, bx.z, p.sw), p.sw);
+            const int i = a.state == 1 ? a.lo + 1 : (a.state == 0 ? zero_i : nan_i);
+            return make_float2(__int_as_float(i), a.wh);
+        };
         if (use_tab)
-            for (int c = threadIdx.x; c < ww; c += kPasteThreads) {
-                const AxisTerm a = axis_term(src_coord(p.x_lo + wxa + c, bx.x, bx.z, p.sw), p.sw);
-                s_col[c] = make_float4(__int_as_float(a.lo), a.wl, a.wh, __int_as_float(a.state));
-            }
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int q = threadIdx.x + k * kPasteThreads;
-            if (q < mtot) s_mask[q] = p.apply_sigmoid ? sigmoidf_exact(mv[k]) : mv[k];
+            for (int c = threadIdx.x; c < ww; c += kPasteThreads) s_col[c] = col_entry(wxa + c);
+        if (threadIdx.x < r1 - r0) {
+            const AxisTerm a = axis_term(src_coord(p.y_lo + r0 + threadIdx.x, bx.y, bx.w, p.sh), p.sh);
+            s_row[threadIdx.x] = make_float4(__int_as_float(a.lo), a.wl, a.wh, __int_as_float(a.state));
         }
         __syncthreads();
-        // ---- a warp per canvas row: y pass into the warp's row buffer, x pass to global memory -----
-        float* vr = s_vrow + warp * kVRow;
+        // ---- a warp per canvas row: y pass into the warp's VD buffer, x pass to global memory -------
+        float2* vd = s_vd[warp];
         for (int r = r0 + warp; r < r1; r += kPasteThreads / 32) {
-            const AxisTerm ry = axis_term(src_coord(p.y_lo + r, bx.y, bx.w, p.sh), p.sh);
-            if (ry.state == 0) continue;  // warp-uniform
+            const float4 rt = s_row[r - r0];
+            const int rstate = __float_as_int(rt.w);
+            if (rstate == 0) continue;  // warp-uniform
             __syncwarp();
-            if (ry.state == 1) {
-                const float* m0 = s_mask + (ry.lo - mlo) * st_w;
-                for (int xx = lane; xx < st_w; xx += 32) vr[xx] = ry.wl * m0[xx] + ry.wh * m0[xx + st_w];
+            if (rstate == 1) {
+                const float* m0 = s_mask + (__float_as_int(rt.x) - mlo) * st_w;
+                for (int i = lane; i < st_w; i += 32) vd[i].x = rt.y * m0[i] + rt.z * m0[i + st_w];
             } else {
-                for (int xx = lane; xx < st_w; xx += 32) vr[xx] = __int_as_float(0x7fc00000);
+                for (int i = lane; i < st_w; i += 32) vd[i].x = __int_as_float(0x7fc00000);
             }
             __syncwarp();
-            const long long orow = obase + (long long)r * p.rw;
-            for (int c = wxa + lane; c < wxb; c += 32) {
-                AxisTerm cx;
-                if (use_tab) {
-                    const float4 ct = s_col[c - wxa];
-                    cx.lo = __float_as_int(ct.x); cx.wl = ct.y; cx.wh = ct.z; cx.state = __float_as_int(ct.w);
+            for (int i = lane; i <= p.sw; i += 32) vd[i].y = vd[i + 1].x - vd[i].x;
+            if (lane == 0) {
+                vd[zero_i] = make_float2(0.0f, 0.0f);
+                vd[nan_i] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+            }
+            __syncwarp();
+            // region rows are far below 2^31 elements: 32-bit offsets from the row's first element
+            unsigned char* const orow8 = reinterpret_cast<unsigned char*>(p.out) + (obase + (long long)r * p.rw) * (MODE == DM_PASTE_F32 ? 4 : 1);
+            auto emit = [&](int c, const float2 e) {
+                const float2 pr = vd[__float_as_int(e.x)];
+                const float v = fmaf(e.y, pr.y, pr.x);
+                if (MODE == DM_PASTE_F32) {
+                    if (v != 0.0f) reinterpret_cast<float*>(orow8)[c] = v;
                 } else {
-                    cx = axis_term(src_coord(p.x_lo + c, bx.x, bx.z, p.sw), p.sw);
+                    const uint32_t b = encode<MODE>(v, p.thr);
+                    if (b) orow8[c] = (unsigned char)b;
                 }
-                if (cx.state == 0) continue;
-                float v = __int_as_float(0x7fc00000);
-                if (cx.state == 1) v = cx.wl * vr[cx.lo + 1] + cx.wh * vr[cx.lo + 2];
-                if (MODE == DM_PASTE_F32) { if (v != 0.0f) put<MODE>(p, orow + c, v); }
-                else { const uint32_t b = encode<MODE>(v, p.thr); if (b) reinterpret_cast<uint8_t*>(p.out)[orow + c] = (uint8_t)b; }
+            };
+            if (use_tab) {
+                const float2* ct = s_col - wxa;
+                int c = wxa + lane;
+                for (; c + 96 < wxb; c += 128) {
+                    const float2 e0 = ct[c], e1 = ct[c + 32], e2 = ct[c + 64], e3 = ct[c + 96];
+                    emit(c, e0); emit(c + 32, e1); emit(c + 64, e2); emit(c + 96, e3);
+                }
+                for (; c < wxb; c += 32) emit(c, ct[c]);
+            } else {
+                for (int c = wxa + lane; c < wxb; c += 32) emit(c, col_entry(c));
             }
         }
     }

@@ -152,6 +152,12 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
     else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+template <int BYTES>
+__device__ __forceinline__ void cp_async_sa(unsigned sa, const void* gsrc) {
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -452,7 +458,7 @@ __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0
 // cp.async: kFwdPF rows are always in flight, so neither the start of a channel nor the slide of
 // the window ever waits for a cold load, and a warp needs ~1-3 KB of shared memory instead of a
 // whole patch.
-constexpr int kFwdPF = 5;             // patch rows in flight per warp
+constexpr int kFwdPF = 12;            // patch rows in flight per warp (~2 us of lead at full load)
 constexpr int kFwdRing = kFwdPF + 2;  // + the row being read + the row other lanes may still read
 
 __device__ __forceinline__ void cp_async_w(int cw, float* dst, const float* src) {
@@ -824,6 +830,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     // warp-private shared memory: [kRing][32 lanes][VEC] prefetch ring, then [cpw][Pws] row buffer
     // followed by kBwdPad zeros
     float* const ring = a.wsm + lane * VEC;
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
     float* const rowbuf = a.wsm + kRing * 32 * VEC;
     float* const myrow = rowbuf + (lane_on ? sub : 0) * Pws + pv * VEC;
     // zero weights meet whatever lies beyond a window's taps: it must be finite
@@ -856,25 +863,28 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
         for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
+        // ring slots by byte offset: the ring is a power of two in size
+        constexpr unsigned kSlotB = 32 * VEC * 4, kRingMask = kRing * kSlotB - 1;
+        int pre = on ? Ph : 0;  // pooled rows this lane still has to request
 #pragma unroll
         for (int d = 0; d < kRing - 1; ++d) {
-            if (on && d < Ph) cp_async<VEC * 4>(ring + d * 32 * VEC, gnext);
+            if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + d * kSlotB, gnext);
+            --pre;
             gnext += a.gsH;
             cp_async_commit();
         }
-        int slot_w = kRing - 1;    // ring slot the next prefetch lands in
-        int slot_r = 0;            // ring slot holding the next pooled row
-        int pre = Ph - (kRing - 1);  // pooled rows still to be requested
+        unsigned off_w = (kRing - 1) * kSlotB;  // ring slot the next prefetch lands in
+        unsigned off_r = 0;                     // ring slot holding the next pooled row
         const float* yrec = ytab;
         // band-row major: once the pooled rows whose band starts at `base` are in, band row `base`
         // is complete for every lane of the warp
         for (int base = 0; base < R; ++base) {
             const int n = rcnt[base];
             for (int k = 0; k < n; ++k) {
-                if (on && pre > 0) cp_async<VEC * 4>(ring + slot_w * 32 * VEC, gnext);
+                if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + off_w, gnext);
                 --pre;
                 gnext += a.gsH;
-                slot_w = (slot_w + 1) & (kRing - 1);
+                off_w = (off_w + kSlotB) & kRingMask;
                 cp_async_commit();
                 int y0;
                 float w[JW];
@@ -882,8 +892,8 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                 yrec += YS;
                 cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
                 float gv[VEC];
-                ld_vec<VEC>(ring + slot_r * 32 * VEC, gv);
-                slot_r = (slot_r + 1) & (kRing - 1);
+                ld_vec<VEC>(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring) + off_r), gv);
+                off_r = (off_r + kSlotB) & kRingMask;
 #pragma unroll
                 for (int j = 0; j < JW; ++j)
 #pragma unroll
@@ -899,21 +909,34 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
             {
                 const float* up = upx;
                 float* dp = drow;
-                for (int s2 = 0; s2 < nact; ++s2) {
+                auto taps = [&](const float* u4) {
                     float r = 0.0f;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        const float4 u = *reinterpret_cast<const float4*>(up + 4 * v);
+                        const float4 u = *reinterpret_cast<const float4*>(u4 + 4 * v);
                         r += wq[4 * v] * u.x;
                         r += wq[4 * v + 1] * u.y;
                         r += wq[4 * v + 2] * u.z;
                         r += wq[4 * v + 3] * u.w;
                     }
-                    if (a.split >= 4) r += __shfl_down_sync(0xffffffffu, r, 16);
-                    if (a.split >= 2) r += __shfl_down_sync(0xffffffffu, r, a.split >= 4 ? 8 : 16);
-                    if (red_on && r != 0.0f) atomicAdd(dp, r);
-                    up += Pws;
-                    dp += a.dsC;
+                    return r;
+                };
+                if (a.split == 1) {
+                    for (int s2 = 0; s2 < nact; ++s2) {
+                        const float r = taps(up);
+                        if (xon && r != 0.0f) atomicAdd(dp, r);
+                        up += Pws;
+                        dp += a.dsC;
+                    }
+                } else {
+                    for (int s2 = 0; s2 < nact; ++s2) {
+                        float r = taps(up);
+                        if (a.split >= 4) r += __shfl_down_sync(0xffffffffu, r, 16);
+                        r += __shfl_down_sync(0xffffffffu, r, a.split >= 4 ? 8 : 16);
+                        if (red_on && r != 0.0f) atomicAdd(dp, r);
+                        up += Pws;
+                        dp += a.dsC;
+                    }
                 }
             }
             if (a.wide) bwd_retire_wide(rowbuf, Pws, nact, a.fw, cols, 4 * NV * a.split, a.plo, a.pcnt, a.wxT, a.TW, drow - xl, a.dsC, lane);
