@@ -67,6 +67,16 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on the C2 workload, from the
+    committed ncu capture (profiles/roofline_traffic.json); None when no capture is recorded."""
+    p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    try:
+        return float(json.load(open(p))[kernel]['dram_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 # algorithmic bytes (SURVEY.md section 8d)
 # ----------------------------------------------------------------------------------------------
@@ -351,7 +361,7 @@ def main():
     dom = 'dm_roi_align_bwd(+zero-init)' if bwd_ms >= fwd_ms else 'dm_roi_align_fwd'
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kern[dom]['achieved_gbs'], 'peak': peak,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': kern[dom]['achieved_gbs'] / peak,
-                'traffic': None}
+                'traffic': ncu_traffic(dom)}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -411,15 +421,17 @@ def run_extras(dm, ops, dev, rank, peak):
     ex['dm_paste_masks'] = {'workload': 'C4 per GPU: 800 instances (8 img x 100 dets), 112x112 -> 800x1333 bool',
                             'ms': ms, 'instances_per_s': n / ms * 1e3, 'algorithmic_bytes': by,
                             'achieved_gbs': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak}
-    # write-only reference point: the same number of output bytes zero-filled by cudaMemsetAsync
-    out.zero_()
+    # write-only reference point: the same output bytes zero-filled 16 bytes per thread (torch fills a
+    # bool tensor one byte per thread, which is far from the write ceiling; an int32 view is not)
+    o32 = out.flatten()[:(out.numel() // 4) * 4].view(torch.int32)
+    o32.zero_()
     torch.cuda.synchronize()
     a.record()
     for _ in range(reps):
-        out.zero_()
+        o32.zero_()
     b.record()
     torch.cuda.synchronize()
-    ex['dm_paste_masks']['memset_same_bytes_ms'] = a.elapsed_time(b) / reps
+    ex['dm_paste_masks']['fill_same_bytes_ms'] = a.elapsed_time(b) / reps
     del out, logits
     # mask targets: C3 shape, 2 images x 128 positives, all four sizes in one launch
     rng = np.random.default_rng(7 + rank)
