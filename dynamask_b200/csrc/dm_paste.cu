@@ -34,7 +34,8 @@
 namespace dm {
 
 constexpr int kPasteThreads = 256;
-constexpr int kBandRows = 32;       // window rows per CTA
+constexpr int kBandRows = 32;       // window rows per band
+constexpr int kBandCtas = 8;        // CTAs per instance (grid.x); CTA b takes bands b, b + 8, ...
 constexpr int kColTab = 1024;       // window columns whose x terms are staged in shared memory (8 KB)
 constexpr int kVPairs = 128;        // (value, slope) pairs of one warp's y-interpolated mask row: S + 3 <= 128
 constexpr int kMaskStage = 6144;    // floats of sigmoid(mask) window staged per CTA (24 KB)
@@ -187,30 +188,22 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
     __shared__ __align__(8) float2 s_col[kColTab];              // per window column {VD index, wh}
     __shared__ __align__(8) float2 s_vd[kPasteThreads / 32][kVPairs];
     __shared__ __align__(16) float4 s_row[kBandRows];           // per band row {lo, wl, wh, state}
-    __shared__ int s_win[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int st_w = p.sw + 2;
     const int zero_i = p.sw + 1, nan_i = p.sw + 2;  // VD entries for "exactly zero" / "NaN" columns
     const long long T = (long long)p.rh * p.rw;
     for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
         const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
-        // most CTAs of the grid lie below their instance's window: only warp 0 does the window
-        // arithmetic, the other warps wait for its verdict
-        if (warp == 0) {
-            int xa, xb, ya, yb;
-            window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
-            window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
-            if (lane == 0) {
-                // window in region coordinates, clipped to the region
-                s_win[0] = max(ya - p.y_lo, 0); s_win[1] = min(yb - p.y_lo, p.rh);
-                s_win[2] = max(xa - p.x_lo, 0); s_win[3] = min(xb - p.x_lo, p.rw);
-            }
-        }
-        __syncthreads();
-        const int wya = s_win[0], wyb = s_win[1], wxa = s_win[2], wxb = s_win[3];
-        __syncthreads();  // s_win may be rewritten for the next instance
-        const int r0 = wya + blockIdx.x * kBandRows;  // this CTA's band of the window's rows
-        if (r0 >= wyb || wxa >= wxb) continue;        // CTA-uniform
+        int xa, xb, ya, yb;
+        window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
+        // window in region coordinates, clipped to the region
+        const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
+        if (wya + (int)blockIdx.x * kBandRows >= wyb) continue;  // CTA-uniform: no band for this CTA
+        window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
+        const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
+        if (wxa >= wxb) continue;
+        // this CTA takes bands blockIdx.x, blockIdx.x + gridDim.x, ... of the window's rows
+      for (int r0 = wya + blockIdx.x * kBandRows; r0 < wyb; r0 += gridDim.x * kBandRows) {
         const int r1 = min(r0 + kBandRows, wyb);      // exclusive
         const long long cls = p.labels ? p.labels[n] : 0;
         const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
@@ -325,6 +318,7 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
                 for (int c = wxa + lane; c < wxb; c += 32) emit(c, col_entry(c));
             }
         }
+      }  // bands
     }
 }
 
@@ -374,7 +368,9 @@ extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t
         dm::paste_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(out), n16, nbytes);
         DM_LAUNCH_CHECK("dm_paste_masks/fill");
     }
-    dim3 grid((unsigned)((p.rh + dm::kBandRows - 1) / dm::kBandRows), (unsigned)(N < 65535 ? N : 65535));
+    // 8 CTAs per instance, each taking every 8th band of the window: few CTAs find nothing to do
+    const int bands = (p.rh + dm::kBandRows - 1) / dm::kBandRows;
+    dim3 grid((unsigned)(bands < dm::kBandCtas ? bands : dm::kBandCtas), (unsigned)(N < 65535 ? N : 65535));
     switch (out_mode) {
         case DM_PASTE_BOOL: dm::paste_window_kernel<DM_PASTE_BOOL><<<grid, dm::kPasteThreads, 0, st>>>(p); break;
         case DM_PASTE_U8: dm::paste_window_kernel<DM_PASTE_U8><<<grid, dm::kPasteThreads, 0, st>>>(p); break;
