@@ -44,9 +44,12 @@
 
 namespace dm {
 
-constexpr int kRaThreads = 256;
-constexpr int kRaWarps = kRaThreads / 32;
-constexpr int kFwdCtasPerSm = 3;  // forward: 24 warps per SM at <= 80 registers
+// CTA size differs per direction (register budget): device code reads it from blockDim
+constexpr int kBwdThreads = 256;   // backward: 2 CTAs/SM x 8 warps at 128 registers
+constexpr int kFwdThreads = 224;   // forward: 3 CTAs/SM x 7 warps at 96 registers
+#define RA_THREADS ((int)blockDim.x)
+#define RA_WARPS ((int)(blockDim.x >> 5))
+constexpr int kFwdCtasPerSm = 3;
 
 struct LevelDesc {
     float* ptr;  // const for forward, accumulated into for backward
@@ -91,7 +94,7 @@ struct FastDiv {
 
 // fraction of thread slots doing work when n items are dealt round-robin to the CTA
 __device__ __forceinline__ float cta_util(int n) {
-    return (float)n / (float)(((n + kRaThreads - 1) / kRaThreads) * kRaThreads);
+    return (float)n / (float)(((n + RA_THREADS - 1) / RA_THREADS) * RA_THREADS);
 }
 
 __device__ __forceinline__ int pow2_shift_ge(int n) {  // smallest s with (1 << s) >= n
@@ -186,7 +189,7 @@ __device__ __forceinline__ int window_class(int j) { return j <= 2 ? 2 : (j <= 4
 
 __device__ __forceinline__ void axis_scan(int P, int size, float start, float bin, int grid,
                                           int* s_start, int* stat) {
-    for (int p = threadIdx.x; p < P; p += kRaThreads) {
+    for (int p = threadIdx.x; p < P; p += RA_THREADS) {
         int first = INT_MAX, last = -1;
         for (int i = 0; i < grid; ++i) {
             int lo, hi;
@@ -210,7 +213,7 @@ __device__ __forceinline__ void axis_scan(int P, int size, float start, float bi
 __device__ __forceinline__ void axis_fill(int P, int size, float start, float bin, int grid,
                                           const int* s_start, float* w) {
     const float inv = 1.0f / (float)grid;
-    for (int p = threadIdx.x; p < P; p += kRaThreads) {
+    for (int p = threadIdx.x; p < P; p += RA_THREADS) {
         const int st = s_start[p];
         for (int i = 0; i < grid; ++i) {
             int lo, hi;
@@ -268,19 +271,19 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
         stat[ST_MR] = (int)(R > 1 ? 0xFFFFFFFFu / R + 1u : 0u);
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < Pw; p += kRaThreads)
+    for (int p = threadIdx.x; p < Pw; p += RA_THREADS)
         if (t.xs[p] == INT_MAX) t.xs[p] = p < pa ? t.X0 : xs_last;
-    for (int p = threadIdx.x; p < Ph; p += kRaThreads)
+    for (int p = threadIdx.x; p < Ph; p += RA_THREADS)
         if (t.ys[p] == INT_MAX) t.ys[p] = p < qa ? t.Y0 : ys_last;
-    for (int i = threadIdx.x; i < wfloats; i += kRaThreads) t.wx[i] = 0.0f;
-    for (int i = threadIdx.x; i < rfloats; i += kRaThreads) t.rcnt[i] = 0;
+    for (int i = threadIdx.x; i < wfloats; i += RA_THREADS) t.wx[i] = 0.0f;
+    for (int i = threadIdx.x; i < rfloats; i += RA_THREADS) t.rcnt[i] = 0;
     __syncthreads();
     axis_fill(Pw, W, g.rsw, g.bw, g.gw, t.xs, t.wx);
     axis_fill(Ph, H, g.rsh, g.bh, g.gh, t.ys, t.wy);
     __syncthreads();
     t.mR = (unsigned)stat[ST_MR];
     if (t.ystride) {
-        for (int i = threadIdx.x; i < Ph * t.ystride; i += kRaThreads) {
+        for (int i = threadIdx.x; i < Ph * t.ystride; i += RA_THREADS) {
             const int ph = i / t.ystride, f = i - ph * t.ystride;
             float v = 0.0f;
             if (f == 0) {
@@ -359,7 +362,7 @@ __device__ __forceinline__ Unit decode_unit(const RaParams& p, const int* s_seg,
 __device__ void zero_unit(const BucketDesc& B, int i, int c0, int c1) {
     const int per_c = B.ph * B.pw;
     const int n = (c1 - c0) * per_c;
-    for (int e = threadIdx.x; e < n; e += kRaThreads) {
+    for (int e = threadIdx.x; e < n; e += RA_THREADS) {
         const int c = e / per_c, r = e - c * per_c;
         const int ph = r / B.pw, pw = r - ph * B.pw;
         B.ptr[(long long)i * B.sN + (long long)(c0 + c) * B.sC + (long long)ph * B.sH + (long long)pw * B.sW] = 0.0f;
@@ -373,7 +376,7 @@ __device__ void direct_unit(const LevelDesc& Lv, const BucketDesc& B, const RoiG
     const int n = (c1 - c0) * per_c;
     const int cnt = g.gh * g.gw;
     const float inv_count = 1.0f / (float)(cnt > 1 ? cnt : 1);
-    for (int e = threadIdx.x; e < n; e += kRaThreads) {
+    for (int e = threadIdx.x; e < n; e += RA_THREADS) {
         const int c = e / per_c, r = e - c * per_c;
         const int ph = r / B.pw, pw = r - ph * B.pw;
         float* o = B.ptr + (long long)i * B.sN + (long long)(c0 + c) * B.sC + (long long)ph * B.sH + (long long)pw * B.sW;
@@ -428,11 +431,11 @@ __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0
     for (int x = lane; x < fws; x += 32) {
         const float* __restrict__ sx = src + (long long)x * sW;
         const bool live = x < fw;
-        for (int r0 = warp; r0 < nrows; r0 += PF * kRaWarps) {
+        for (int r0 = warp; r0 < nrows; r0 += PF * RA_WARPS) {
             float v[PF];
 #pragma unroll
             for (int q = 0; q < PF; ++q) {
-                const int row = r0 + q * kRaWarps;
+                const int row = r0 + q * RA_WARPS;
                 v[q] = 0.0f;
                 if (live && row < nrows) {
                     const int c = fdR.div(row), r = row - c * R;
@@ -441,7 +444,7 @@ __device__ void stage_patch(const LevelDesc& Lv, float* patch, int batch, int c0
             }
 #pragma unroll
             for (int q = 0; q < PF; ++q) {
-                const int row = r0 + q * kRaWarps;
+                const int row = r0 + q * RA_WARPS;
                 if (row < nrows) patch[row * fws + x] = v[q];
             }
         }
@@ -518,7 +521,7 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     __syncwarp();
 
     // ---- producer side: this lane's copy of every patch row ---------------------------------------
-    const int step = kRaWarps * cpw;
+    const int step = RA_WARPS * cpw;
     const int cc_c = lane / a.cpr;                     // channel of this lane's copy inside the batch
     const int cc_x = (lane - cc_c * a.cpr) * a.cw;     // first float of the copy inside the row
     const float* i_src = a.src0 + (warp * cpw + cc_c) * a.sC + cc_x;  // this lane's source, next row to issue
@@ -637,7 +640,7 @@ __device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables 
         const int sh = pow2_shift_ge(Pw);
         const int items = (cs * R) << sh;
         const int JX = t.JX;
-        for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
+        for (int vi = threadIdx.x; vi < items; vi += RA_THREADS) {
             const int row = vi >> sh, pw = vi & ((1 << sh) - 1);
             if (pw >= Pw) continue;
             const float* prow = patch + row * fw;
@@ -657,7 +660,7 @@ __device__ void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const Tables 
         FastDiv fdP;
         fdP.init(nph);
         float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-        for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
+        for (int vi = threadIdx.x; vi < items; vi += RA_THREADS) {
             const int row = vi >> sh, pv = vi & ((1 << sh) - 1);
             if (pv >= PwV) continue;
             const int c = fdP.div(row), ph = p0 + (row - c * nph);
@@ -713,7 +716,7 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
         B.sC < (1 << 24) && B.sH < (1 << 24)) {
         // fast path: every warp streams its channels' patch rows through a private ring of row slots
-        const int slice = (avail / kRaWarps) & ~3;
+        const int slice = (avail / RA_WARPS) & ~3;
         FwdWarpArgs a;
         int fwp;
         a.cw = Lv.cw;
@@ -853,7 +856,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
 
     const float* gwarp = a.gbase + pv * VEC;
     constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
-    for (int cb = warp * cpw; cb < nc; cb += kRaWarps * cpw) {
+    for (int cb = warp * cpw; cb < nc; cb += RA_WARPS * cpw) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
         const float* gnext = gwarp + (cb + (lane_on ? sub : 0)) * a.gsC;  // next pooled row to prefetch
@@ -972,10 +975,10 @@ __device__ void bwd_column_pass_generic(const BucketDesc& B, const Tables t, flo
     const int R = t.Y1 - t.Y0 + 1;
     const int per_c = Ph * PwV;
     const int items = cs * per_c;
-    for (int e = threadIdx.x; e < cs * R * Pw; e += kRaThreads) U[e] = 0.0f;
+    for (int e = threadIdx.x; e < cs * R * Pw; e += RA_THREADS) U[e] = 0.0f;
     __syncthreads();
     const float* gbase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
-    for (int it = threadIdx.x; it < items; it += kRaThreads) {
+    for (int it = threadIdx.x; it < items; it += RA_THREADS) {
         const int c = it / per_c, rem = it - c * per_c;
         const int ph = rem / PwV, pv = rem - ph * PwV;
         float gv[VEC];
@@ -1006,7 +1009,7 @@ __device__ void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, const Tab
     FastDiv fdR;
     fdR.init(R);
     float* dst = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + (long long)t.X0 * Lv.sW;
-    for (int vi = threadIdx.x; vi < items; vi += kRaThreads) {
+    for (int vi = threadIdx.x; vi < items; vi += RA_THREADS) {
         const int row = vi >> sh, x = vi & ((1 << sh) - 1);
         if (x >= fw) continue;
         const float* up = U + row * Pw + plo[x];
@@ -1047,7 +1050,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     if (fits && 2 * fw <= p.smem_floats - t.floats) {
         if (threadIdx.x == 0) { *s_tw = 0; stat[ST_NEED] = 0; }
         __syncthreads();
-        for (int x = threadIdx.x; x < fw; x += kRaThreads) {
+        for (int x = threadIdx.x; x < fw; x += RA_THREADS) {
             const int xa = x + t.X0;
             // xs is monotone: first bin whose band reaches xa, last bin whose band starts at or before xa
             int lo = 0, hi = B.pw;
@@ -1072,12 +1075,12 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int TW = fits ? (*s_tw | 1) : 0;  // odd stride: conflict-free column-wise reads
     const int extra = (2 * fw + fw * TW + 3) & ~3;
     const long long avail = (long long)p.smem_floats - (fits ? t.floats : 0) - extra;
-    if (!fits || avail < (long long)kRaWarps * kBwdWarpFloats(VEC)) {
+    if (!fits || avail < (long long)RA_WARPS * kBwdWarpFloats(VEC)) {
         direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
         return;
     }
     float* wxT = reinterpret_cast<float*>(pcnt + fw);
-    for (int e = threadIdx.x; e < fw * TW; e += kRaThreads) {
+    for (int e = threadIdx.x; e < fw * TW; e += RA_THREADS) {
         const int x = e / TW, q = e - x * TW;
         float w = 0.0f;
         if (q < pcnt[x]) {
@@ -1135,7 +1138,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __launch_bounds__(kRaThreads, BWD ? 2 : kFwdCtasPerSm) ra_kernel(const __grid_constant__ RaParams p) {
+__global__ void __maxnreg__(BWD ? 128 : 96) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
@@ -1255,13 +1258,14 @@ template <bool BWD>
 static int launch(RaParams& p, cudaStream_t st, const char* where) {
     const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 72 : 72);
     const int smem_bytes = smem_kb * 1024;
+    const int threads = BWD ? kBwdThreads : kFwdThreads;
     p.smem_floats = smem_bytes / 4;
     DM_CUDA_CHECK(cudaFuncSetAttribute(ra_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
     int occ = 0;
-    DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_kernel<BWD>, kRaThreads, smem_bytes), where);
+    DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_kernel<BWD>, threads, smem_bytes), where);
     if (occ < 1) return DM_EUNSUPPORTED;
     const int grid = sm_count() * occ;
-    ra_kernel<BWD><<<grid, kRaThreads, smem_bytes, st>>>(p);
+    ra_kernel<BWD><<<grid, threads, smem_bytes, st>>>(p);
     DM_LAUNCH_CHECK(where);
     return DM_OK;
 }
