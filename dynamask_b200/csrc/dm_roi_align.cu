@@ -46,7 +46,13 @@ namespace dm {
 
 // CTA size differs per direction (register budget): device code reads it from blockDim
 constexpr int kBwdThreads = 256;   // backward: 2 CTAs/SM x 8 warps at 128 registers
-constexpr int kFwdThreads = 224;   // forward: 3 CTAs/SM x 7 warps at 96 registers
+#ifndef DM_FWD_THREADS
+#define DM_FWD_THREADS 224
+#endif
+#ifndef DM_FWD_REGS
+#define DM_FWD_REGS 96
+#endif
+constexpr int kFwdThreads = DM_FWD_THREADS;   // forward: 3 CTAs/SM x 7 warps at 96 registers
 #define RA_THREADS ((int)blockDim.x)
 #define RA_WARPS ((int)(blockDim.x >> 5))
 constexpr int kFwdCtasPerSm = 3;
@@ -147,6 +153,51 @@ __device__ __forceinline__ void st_stream_vec(float* p, const float (&a)[VEC]) {
     else st_stream(p, a[0]);
 }
 
+// Packed FP32 pairs (FFMA2 / FMUL2 on sm_100a): two FMAs per issued instruction.  The hot loops are
+// issue-bound, not FP-bound, so halving the FP instruction count is worth the inline PTX.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+// acc = w * x  /  acc += w * x  over VEC lanes' worth of columns, w broadcast as the pair (w, w)
+template <int VEC>
+__device__ __forceinline__ void vmul(float (&acc)[VEC], float2 ww, const float (&x)[VEC]) {
+    if (VEC == 1) {
+        acc[0] = ww.x * x[0];
+    } else {
+#pragma unroll
+        for (int e = 0; e + 1 < VEC; e += 2) {
+            const float2 r = fmul2(ww, make_float2(x[e], x[e + 1]));
+            acc[e] = r.x;
+            acc[e + 1] = r.y;
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void vfma(float (&acc)[VEC], float2 ww, const float (&x)[VEC]) {
+    if (VEC == 1) {
+        acc[0] += ww.x * x[0];
+    } else {
+#pragma unroll
+        for (int e = 0; e + 1 < VEC; e += 2) {
+            const float2 r = ffma2(ww, make_float2(x[e], x[e + 1]), make_float2(acc[e], acc[e + 1]));
+            acc[e] = r.x;
+            acc[e + 1] = r.y;
+        }
+    }
+}
+
 // Ampere-style asynchronous global->shared copies (LDGSTS): used as a register-free prefetch ring.
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
@@ -179,7 +230,7 @@ struct Tables {
     int JXa, JYa;  // rows allocated for wx / wy (>= JX / JY, zero padded up to the window class)
     unsigned mR;   // FastDiv magic of R = Y1 - Y0 + 1
     float* ytab;   // packed per-pooled-row records {ys - Y0, wy[0..JYa)} when JYa is a window class
-    int ystride;   // floats per record (4, 8 or 12), 0 when there is no packed table
+    int ystride;   // floats per record (2 * JYa: the weights as broadcast pairs), 0 when there is no packed table
     int* rcnt;     // [R] pooled rows whose band starts at patch row r (only with a packed table)
     int floats;    // shared-memory floats consumed (multiple of 4)
 };
@@ -254,7 +305,7 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     t.JXa = wc ? wc : (window_class(t.JX) ? window_class(t.JX) : t.JX);
     t.JYa = wc ? wc : (window_class(t.JY) ? window_class(t.JY) : t.JY);
     const int wfloats = (t.JXa * Pw + t.JYa * Ph + 3) & ~3;
-    t.ystride = (t.JYa == 2) ? 4 : (t.JYa == 4 ? 8 : (t.JYa == 8 ? 12 : 0));
+    t.ystride = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? 2 * t.JYa : 0;
     const int Rr = t.Y1 - t.Y0 + 1;
     const int rfloats = t.ystride ? ((Rr + 3) & ~3) : 0;
     t.floats = base + wfloats + t.ystride * Ph + rfloats;
@@ -286,12 +337,8 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
         for (int i = threadIdx.x; i < Ph * t.ystride; i += RA_THREADS) {
             const int ph = i / t.ystride, f = i - ph * t.ystride;
             float v = 0.0f;
-            if (f == 0) {
-                v = __int_as_float(t.ys[ph] - t.Y0);
-                atomicAdd(&t.rcnt[t.ys[ph] - t.Y0], 1);
-            } else if (f <= t.JYa) {
-                v = t.wy[(f - 1) * Ph + ph];
-            }
+            if (f == 0) atomicAdd(&t.rcnt[t.ys[ph] - t.Y0], 1);
+            v = t.wy[(f >> 1) * Ph + ph];
             t.ytab[i] = v;
         }
         __syncthreads();
@@ -299,21 +346,15 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     return true;
 }
 
-// one packed Y record: window-relative start row and the JW row weights
+// one packed Y record: the JW row weights of a pooled row as broadcast pairs (w_j, w_j)
 template <int JW>
-__device__ __forceinline__ void load_yrec(const float* __restrict__ ytab, int ph, int& y0, float (&w)[JW]) {
-    constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
-    const float4* r = reinterpret_cast<const float4*>(ytab + ph * YS);
-    const float4 a = r[0];
-    y0 = __float_as_int(a.x);
-    w[0] = a.y; w[1] = a.z;
-    if (JW >= 4) {
-        const float4 b = r[1];
-        w[2 % JW] = a.w; w[3 % JW] = b.x;
-        if (JW == 8) {
-            const float4 c = r[2];
-            w[4 % JW] = b.y; w[5 % JW] = b.z; w[6 % JW] = b.w; w[7 % JW] = c.x;
-        }
+__device__ __forceinline__ void load_yrec(const float* __restrict__ rec, float2 (&w)[JW]) {
+    const float4* r = reinterpret_cast<const float4*>(rec);
+#pragma unroll
+    for (int j = 0; j < JW; j += 2) {
+        const float4 a = r[j >> 1];
+        w[j] = make_float2(a.x, a.y);
+        w[j + 1] = make_float2(a.z, a.w);
     }
 }
 
@@ -529,7 +570,9 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     int i_cb = warp * cpw, i_r = 0, i_slot = 0;
     auto issue = [&]() {
         if (i_cb < nc) {
+#if !defined(DM_DIAG_NO_READS)
             if (cc_c < min(cpw, nc - i_cb)) cp_async_w(a.cw, i_dst + i_slot * rowf, i_src);
+#endif
             i_src += a.sH;
             if (++i_r == R) {
                 i_r = 0;
@@ -550,20 +593,29 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
         int xo[VEC];
         ld_vec_i<VEC>(xsp, xo);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
-#pragma unroll
         for (int j = 0; j < JW; ++j) {
-            float wj[VEC];
+            float wj[VEC], pj[VEC];
             ld_vec<VEC>(wxp + j * a.Pw, wj);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] += wj[e] * pr[xo[e] + j];
+            for (int e = 0; e < VEC; ++e) pj[e] = pr[xo[e] + j];
+            if (VEC == 1) {
+                v[0] = j == 0 ? wj[0] * pj[0] : v[0] + wj[0] * pj[0];
+            } else {
+#pragma unroll
+                for (int e = 0; e + 1 < VEC; e += 2) {
+                    const float2 r = j == 0 ? fmul2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]))
+                                            : ffma2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]), make_float2(v[e], v[e + 1]));
+                    v[e] = r.x;
+                    v[e + 1] = r.y;
+                }
+            }
         }
         if (++r_slot == kFwdRing) { r_slot = 0; pr -= (kFwdRing - 1) * rowf; } else { pr += rowf; }
     };
 #pragma unroll
     for (int d = 0; d < kFwdPF; ++d) issue();
 
-    constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
+    constexpr int YS = 2 * JW;
     float* o_cb = a.obase + (warp * cpw + subc) * a.osC + pv * VEC;
     for (int cb = warp * cpw; cb < nc; cb += step, o_cb += step * a.osC) {
         const bool on = lane_on && sub < nc - cb;
@@ -585,18 +637,20 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
             const int n = rcnt[base];
 #pragma unroll 2
             for (int k = 0; k < n; ++k) {
-                int y0;
-                float w[JW];
-                load_yrec<JW>(yrec, 0, y0, w);
+                float2 w[JW];
+                load_yrec<JW>(yrec, w);
                 yrec += YS;
                 float acc[VEC];
+                vmul<VEC>(acc, w[0], win[0]);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[e] = w[0] * win[0][e];
-#pragma unroll
-                for (int j = 1; j < JW; ++j)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[e] += w[j] * win[j][e];
+                for (int j = 1; j < JW; ++j) vfma<VEC>(acc, w[j], win[j]);
+#if defined(DM_DIAG_NO_STORES)
+                if (on && acc[0] == 123.456f) st_stream_vec<VEC>(o, acc);
+#elif defined(DM_DIAG_PLAIN_STORES)
+                if (on) { if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]); else st_stream_vec<VEC>(o, acc); }
+#else
                 if (on) st_stream_vec<VEC>(o, acc);
+#endif
                 o += a.osH;
             }
             left -= n;
@@ -855,7 +909,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     __syncwarp();
 
     const float* gwarp = a.gbase + pv * VEC;
-    constexpr int YS = JW == 2 ? 4 : (JW == 4 ? 8 : 12);
+    constexpr int YS = 2 * JW;
     for (int cb = warp * cpw; cb < nc; cb += RA_WARPS * cpw) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
@@ -889,18 +943,15 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                 gnext += a.gsH;
                 off_w = (off_w + kSlotB) & kRingMask;
                 cp_async_commit();
-                int y0;
-                float w[JW];
-                load_yrec<JW>(yrec, 0, y0, w);
+                float2 w[JW];
+                load_yrec<JW>(yrec, w);
                 yrec += YS;
                 cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
                 float gv[VEC];
                 ld_vec<VEC>(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring) + off_r), gv);
                 off_r = (off_r + kSlotB) & kRingMask;
 #pragma unroll
-                for (int j = 0; j < JW; ++j)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[j][e] += w[j] * gv[e];
+                for (int j = 0; j < JW; ++j) vfma<VEC>(acc[j], w[j], gv);
             }
             // ---- retire band row `base` -----------------------------------------------------------
             if (on) {
@@ -913,16 +964,14 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                 const float* up = upx;
                 float* dp = drow;
                 auto taps = [&](const float* u4) {
-                    float r = 0.0f;
+                    float2 r2 = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
                         const float4 u = *reinterpret_cast<const float4*>(u4 + 4 * v);
-                        r += wq[4 * v] * u.x;
-                        r += wq[4 * v + 1] * u.y;
-                        r += wq[4 * v + 2] * u.z;
-                        r += wq[4 * v + 3] * u.w;
+                        r2 = ffma2(make_float2(wq[4 * v], wq[4 * v + 1]), make_float2(u.x, u.y), r2);
+                        r2 = ffma2(make_float2(wq[4 * v + 2], wq[4 * v + 3]), make_float2(u.z, u.w), r2);
                     }
-                    return r;
+                    return r2.x + r2.y;
                 };
                 if (a.split == 1) {
                     for (int s2 = 0; s2 < nact; ++s2) {
@@ -1138,7 +1187,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __maxnreg__(BWD ? 128 : 96) ra_kernel(const __grid_constant__ RaParams p) {
+__global__ void __maxnreg__(BWD ? 128 : DM_FWD_REGS) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
