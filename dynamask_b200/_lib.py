@@ -29,6 +29,10 @@ SIGNATURES = {
     'dm_paste_masks': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
                             _i, _vp, _vp]),
     'dm_mask_target': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    'dm_paste_rle': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
+                          _i, _vp, _vp, _vp, _vp, _vp]),
+    'dm_rle_from_canvas': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'dm_rle_compress_host': (_i64, [_vp, _i64, _i64, _vp, _i64]),
 }
 
 _lib = None

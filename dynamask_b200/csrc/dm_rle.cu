@@ -1,0 +1,363 @@
+// Next row of the path: run-length encoding of the pasted instance
+// masks on the device, so the [N,H,W] canvases never cross PCIe -- or, fused with the paste, never
+// exist at all.
+//
+// Replaces the host loop  encode_mask_results(get_seg_masks(...))  of the reference:
+//   DynaMaskHead.get_seg_masks -> N numpy bool [H,W]   (mmdet/models/roi_heads/mask_heads/dynamask_head.py:341)
+//   encode_mask_results -> pycocotools mask.encode     (mmdet/core/mask/utils.py:36-63, mmdet/apis/test.py:54-57)
+// pycocotools (third party, not in the reference tree) encodes a mask in COLUMN-major order as
+// alternating run lengths starting with a run of zeros.  A run list is fully described by the
+// sorted flat indices (x * H + y) at which the value changes, so the kernels emit those
+// "transitions"; turning them into counts and into pycocotools' compressed string is a few
+// microseconds of host work per instance (dm_rle_compress_host below).
+//
+// Two passes over the same pixels (count, then write at exclusive-scan offsets):
+//   dm_paste_rle        pixels are evaluated from the mask logits exactly as paste_window_kernel does
+//                       (same tables, same FMA), one thread per canvas column walking down the
+//                       instance's window; the canvas is never written.
+//   dm_rle_from_canvas  pixels are read from an existing [N,H,W] uint8/bool canvas.
+// Every column is encoded on its own, starting from 0 and returning to 0 after its last window row;
+// where a run really continues into the next column the two coinciding transitions cancel on the
+// host.
+#include <cstdlib>
+#include <cstring>
+
+#include "dm_paste_common.cuh"
+
+namespace dm {
+
+struct RleParams {
+    PasteParams p;
+    int32_t* col_counts;          // [N][rw] transitions per column (window columns only are defined)
+    int32_t* inst_totals;         // [N] transitions per instance (pass 1 adds into it: zero it first)
+    const int64_t* inst_offsets;  // [N] exclusive scan of inst_totals (pass 2)
+    int32_t* trans;               // [sum] transitions, instance after instance (pass 2)
+    const uint8_t* canvas;        // canvas source, or null
+};
+
+constexpr int kRleThreads = 256;
+
+// exclusive scan of one int per thread over the CTA; returns the thread's prefix, `total` = CTA sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    __syncthreads();  // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < kRleThreads / 32; ++w) {
+        const int t = s_warp[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    return base + inc - v;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kRleThreads, 4)
+paste_rle_kernel(const __grid_constant__ RleParams q) {
+    const PasteParams& p = q.p;
+    __shared__ __align__(16) float s_mask[kMaskStage];
+    __shared__ __align__(8) float2 s_vd[kRleThreads / 32][kVPairs];
+    __shared__ int s_warp[kRleThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int st_w = p.sw + 2;
+    const int zero_i = p.sw + 1, nan_i = p.sw + 2;
+    for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
+        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
+        int xa, xb, ya, yb;
+        window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
+        const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
+        const int c0 = wxa + blockIdx.x * kRleThreads;  // this CTA's first column
+        if (c0 >= wxb) continue;                         // CTA-uniform
+        window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
+        const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
+        const int x = c0 + threadIdx.x;
+        const bool live = x < wxb;
+        // this thread's column: VD index and weight, constant down the column
+        int ci = zero_i;
+        float cw = 0.0f;
+        if (live) {
+            const AxisTerm a = axis_term(src_coord(p.x_lo + x, bx.x, bx.z, p.sw), p.sw);
+            ci = a.state == 1 ? a.lo + 1 : (a.state == 0 ? zero_i : nan_i);
+            cw = a.wh;
+        }
+        int32_t* out = nullptr;
+        if (PASS == 2) {
+            // transitions of the instance's earlier columns: those of earlier CTAs + a scan inside this one
+            int part = 0;
+            for (int c = wxa + threadIdx.x; c < c0; c += kRleThreads) part += q.col_counts[(size_t)n * p.rw + c];
+            int before = 0, dummy = 0;
+            block_exclusive_scan(part, s_warp, before);
+            const int mine = live ? q.col_counts[(size_t)n * p.rw + x] : 0;
+            const int pre = block_exclusive_scan(mine, s_warp, dummy);
+            out = q.trans + q.inst_offsets[n] + before + pre;
+        }
+        const long long cls = p.labels ? p.labels[n] : 0;
+        const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
+        // band height: as many canvas rows as keep the reachable mask rows inside the scratch
+        int hb = kBandRows;
+        {
+            const float ratio = fabsf((float)p.sh / (bx.w - bx.y));  // mask rows per canvas row
+            const int cap = kMaskStage / st_w - 3;
+            if (ratio == ratio && ratio * (float)hb > (float)cap) hb = max(1, (int)((float)cap / ratio));
+        }
+        Instance in;
+        in.load(p, n);
+        int prev = 0, cnt = 0;
+        const int col_base = x * p.rh;
+        auto step = [&](int row, bool b) {
+            if ((int)b != prev) {
+                if (PASS == 1) ++cnt;
+                else *out++ = col_base + row;
+                prev = (int)b;
+            }
+        };
+        for (int r0 = wya; r0 < wyb; r0 += hb) {
+            const int r1 = min(r0 + hb, wyb);
+            bool staged = false;
+            int mlo = 0, mrows = 0;
+            {
+                const float ia = src_coord(p.y_lo + r0, bx.y, bx.w, p.sh);
+                const float ib = src_coord(p.y_lo + r1 - 1, bx.y, bx.w, p.sh);
+                if (ia == ia && ib == ib && p.sw + 3 <= kVPairs) {
+                    mlo = (int)fmaxf(floorf(fminf(ia, ib)), -1.0f);
+                    const int hi = (int)fminf(floorf(fmaxf(ia, ib)) + 1.0f, (float)p.sh);
+                    mrows = hi - mlo + 1;
+                    staged = mrows >= 1 && mrows * st_w <= kMaskStage;
+                }
+            }
+            if (!staged) {  // CTA-uniform: per-pixel evaluation from global memory
+                for (int row = r0; row < r1; ++row) step(row, live && in.eval(p.x_lo + x, p.y_lo + row) >= p.thr);
+                continue;
+            }
+            __syncthreads();  // scratch of the previous band is no longer read
+            for (int yy = warp; yy < mrows; yy += kRleThreads / 32) {
+                const int y = mlo + yy;
+                const bool yin = y >= 0 && y < p.sh;
+                const float* __restrict__ mr = m + y * p.sw - 1;
+                float* sr = s_mask + yy * st_w;
+                float mv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = lane + 32 * k;
+                    mv[k] = 0.0f;
+                    if (yin && xx >= 1 && xx <= p.sw) mv[k] = __ldg(mr + xx);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = lane + 32 * k;
+                    if (xx < st_w) {
+                        float v = mv[k];
+                        if (p.apply_sigmoid) v = sigmoidf_fast(v);
+                        sr[xx] = (yin && xx >= 1 && xx <= p.sw) ? v : 0.0f;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int s0 = r0; s0 < r1; s0 += kRleThreads / 32) {
+                // warp w prepares the (value, slope) row of canvas row s0 + w
+                const int row = s0 + warp;
+                float2* vd = s_vd[warp];
+                if (row < r1) {
+                    const AxisTerm ry = axis_term(src_coord(p.y_lo + row, bx.y, bx.w, p.sh), p.sh);
+                    if (ry.state == 1) {
+                        const float* m0 = s_mask + (ry.lo - mlo) * st_w;
+                        for (int i = lane; i < st_w; i += 32) vd[i].x = ry.wl * m0[i] + ry.wh * m0[i + st_w];
+                    } else {
+                        const float f = ry.state == 0 ? 0.0f : __int_as_float(0x7fc00000);
+                        for (int i = lane; i < st_w; i += 32) vd[i].x = f;
+                    }
+                    __syncwarp();
+                    for (int i = lane; i <= p.sw; i += 32) vd[i].y = vd[i + 1].x - vd[i].x;
+                    if (lane == 0) {
+                        vd[zero_i] = make_float2(0.0f, 0.0f);
+                        vd[nan_i] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+                    }
+                }
+                __syncthreads();
+                const int nk = min(kRleThreads / 32, r1 - s0);
+                for (int k = 0; k < nk; ++k) {
+                    const float2 pr = s_vd[k][ci];
+                    const float v = fmaf(cw, pr.y, pr.x);
+                    step(s0 + k, live && v >= p.thr);
+                }
+                __syncthreads();
+            }
+        }
+        if (prev) step(wyb, false);  // every column returns to 0 after its last window row
+        if (PASS == 1) {
+            if (live) q.col_counts[(size_t)n * p.rw + x] = cnt;
+            int total = 0;
+            block_exclusive_scan(cnt, s_warp, total);
+            if (threadIdx.x == 0 && total) atomicAdd(q.inst_totals + n, total);
+        }
+    }
+}
+
+// Same encoding from an existing canvas [N][H][W] (one byte per pixel, non-zero = foreground).
+template <int PASS>
+__global__ void __launch_bounds__(kRleThreads)
+canvas_rle_kernel(const __grid_constant__ RleParams q) {
+    const PasteParams& p = q.p;  // only N, rh, rw are used
+    __shared__ int s_warp[kRleThreads / 32];
+    const int c0 = blockIdx.x * kRleThreads;
+    for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
+        const int x = c0 + threadIdx.x;
+        const bool live = x < p.rw;
+        int32_t* out = nullptr;
+        if (PASS == 2) {
+            int part = 0;
+            for (int c = threadIdx.x; c < c0; c += kRleThreads) part += q.col_counts[(size_t)n * p.rw + c];
+            int before = 0, dummy = 0;
+            block_exclusive_scan(part, s_warp, before);
+            const int mine = live ? q.col_counts[(size_t)n * p.rw + x] : 0;
+            const int pre = block_exclusive_scan(mine, s_warp, dummy);
+            out = q.trans + q.inst_offsets[n] + before + pre;
+        }
+        const uint8_t* __restrict__ src = q.canvas + (size_t)n * p.rh * p.rw + x;
+        int prev = 0, cnt = 0;
+        const int col_base = x * p.rh;
+        if (live) {
+            for (int y = 0; y < p.rh; ++y) {
+                const int b = __ldcs(src + (size_t)y * p.rw) != 0;
+                if (b != prev) {
+                    if (PASS == 1) ++cnt;
+                    else *out++ = col_base + y;
+                    prev = b;
+                }
+            }
+            if (prev) {
+                if (PASS == 1) ++cnt;
+                else *out++ = col_base + p.rh;
+            }
+        }
+        if (PASS == 1) {
+            if (live) q.col_counts[(size_t)n * p.rw + x] = cnt;
+            int total = 0;
+            block_exclusive_scan(cnt, s_warp, total);
+            if (threadIdx.x == 0 && total) atomicAdd(q.inst_totals + n, total);
+        }
+    }
+}
+
+}  // namespace dm
+
+static int rle_fill(dm::RleParams& q, int N, int rh, int rw, int pass, int32_t* col_counts, int32_t* inst_totals,
+                    const int64_t* inst_offsets, int32_t* transitions) {
+    if (pass != 1 && pass != 2) return DM_EINVAL;
+    if (!col_counts || !inst_totals) return DM_EINVAL;
+    if (pass == 2 && (!inst_offsets || !transitions)) return DM_EINVAL;
+    if ((long long)rh * rw >= (1ll << 30)) return DM_EUNSUPPORTED;
+    q.p.N = N;
+    q.p.rh = rh;
+    q.p.rw = rw;
+    q.col_counts = col_counts;
+    q.inst_totals = inst_totals;
+    q.inst_offsets = inst_offsets;
+    q.trans = transitions;
+    q.canvas = nullptr;
+    return DM_OK;
+}
+
+extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                            const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                            const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                            int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
+                            const int64_t* inst_offsets, int32_t* transitions, dm_stream_t stream) {
+    if (N < 0 || S_h < 1 || S_w < 1 || img_h < 0 || img_w < 0) return DM_EINVAL;
+    if (x_lo < 0 || y_lo < 0 || x_hi > img_w || y_hi > img_h || x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
+    dm::RleParams q;
+    memset(&q, 0, sizeof(q));
+    const int rc = rle_fill(q, N, y_hi - y_lo, x_hi - x_lo, pass, col_counts, inst_totals, inst_offsets, transitions);
+    if (rc != DM_OK) return rc;
+    if (N == 0 || q.p.rh == 0 || q.p.rw == 0) return DM_OK;
+    if (!masks || !boxes || (reinterpret_cast<uintptr_t>(boxes) & 15u)) return DM_EINVAL;
+    q.p.masks = masks;
+    q.p.stride_n = mask_stride_n;
+    q.p.stride_c = mask_stride_c;
+    q.p.labels = labels;
+    q.p.sh = S_h;
+    q.p.sw = S_w;
+    q.p.apply_sigmoid = apply_sigmoid;
+    q.p.boxes = boxes;
+    q.p.img_h = img_h;
+    q.p.img_w = img_w;
+    q.p.x_lo = x_lo;
+    q.p.y_lo = y_lo;
+    q.p.thr = thr;
+    q.p.total = (long long)q.p.rh * q.p.rw * N;
+    dim3 grid((unsigned)((q.p.rw + dm::kRleThreads - 1) / dm::kRleThreads), (unsigned)(N < 65535 ? N : 65535));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pass == 1) dm::paste_rle_kernel<1><<<grid, dm::kRleThreads, 0, st>>>(q);
+    else dm::paste_rle_kernel<2><<<grid, dm::kRleThreads, 0, st>>>(q);
+    DM_LAUNCH_CHECK("dm_paste_rle");
+    return DM_OK;
+}
+
+extern "C" int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int32_t* col_counts,
+                                  int32_t* inst_totals, const int64_t* inst_offsets, int32_t* transitions,
+                                  dm_stream_t stream) {
+    if (N < 0 || H < 0 || W < 0) return DM_EINVAL;
+    dm::RleParams q;
+    memset(&q, 0, sizeof(q));
+    const int rc = rle_fill(q, N, H, W, pass, col_counts, inst_totals, inst_offsets, transitions);
+    if (rc != DM_OK) return rc;
+    if (N == 0 || H == 0 || W == 0) return DM_OK;
+    if (!canvas) return DM_EINVAL;
+    q.canvas = canvas;
+    dim3 grid((unsigned)((W + dm::kRleThreads - 1) / dm::kRleThreads), (unsigned)(N < 65535 ? N : 65535));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pass == 1) dm::canvas_rle_kernel<1><<<grid, dm::kRleThreads, 0, st>>>(q);
+    else dm::canvas_rle_kernel<2><<<grid, dm::kRleThreads, 0, st>>>(q);
+    DM_LAUNCH_CHECK("dm_rle_from_canvas");
+    return DM_OK;
+}
+
+// Host side: transitions of ONE instance -> pycocotools' compressed counts string.
+// counts = run lengths alternating from a run of zeros; the string is rleToString's base-32 varint
+// code with each count beyond the second stored as a difference from the count two before.
+// Returns the string length (no terminator), or -1 when `cap` is too small.
+extern "C" int64_t dm_rle_compress_host(const int32_t* transitions, int64_t n, int64_t total_pixels, char* out,
+                                        int64_t cap) {
+    int64_t len = 0, k = 0;          // k = counts emitted so far
+    int64_t c1 = 0, c2 = 0;          // counts one and two before the current one
+    int64_t last = 0;                // flat index where the current run starts
+    auto emit = [&](int64_t cnt) -> bool {
+        int64_t x = cnt;
+        if (k > 2) x -= c2;
+        bool more = true;
+        while (more) {
+            char c = (char)(x & 0x1f);
+            x >>= 5;
+            more = (c & 0x10) ? x != -1 : x != 0;
+            if (more) c |= 0x20;
+            c += 48;
+            if (len >= cap) return false;
+            out[len++] = c;
+        }
+        c2 = c1;
+        c1 = cnt;
+        ++k;
+        return true;
+    };
+    int64_t i = 0;
+    while (i < n) {
+        // two coinciding transitions (a run continuing across a column boundary) cancel
+        if (i + 1 < n && transitions[i] == transitions[i + 1]) { i += 2; continue; }
+        const int64_t t = transitions[i++];
+        if (!emit(t - last)) return -1;
+        last = t;
+    }
+    if (last < total_pixels || k == 0) {
+        if (!emit(total_pixels - last)) return -1;
+    }
+    return len;
+}

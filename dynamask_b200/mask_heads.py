@@ -93,6 +93,59 @@ def get_seg_masks(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape, s
     return [host[i] for i in range(host.shape[0])]
 
 
+def get_seg_masks_rle(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape, scale_factor,
+                      rescale):
+    """``encode_mask_results`` of ``get_seg_masks`` in one device pass.
+
+    Same arguments as :func:`get_seg_masks`; returns n COCO RLE dicts ``{'size': [h, w], 'counts':
+    bytes}`` -- what ``pycocotools.mask.encode`` returns for each pasted mask
+    (``mmdet/core/mask/utils.py:36-63``) -- without materialising or copying the ``[n, h, w]``
+    canvases: only the run boundaries cross PCIe.
+    """
+    if rcnn_test_cfg.mask_thr_binary < 0:
+        raise ValueError('RLE needs a binary mask: mask_thr_binary must be >= 0')
+    bboxes = det_bboxes[:, :4]
+    if rescale:
+        img_h, img_w = ori_shape[:2]
+    else:
+        img_h = np.round(ori_shape[0] * scale_factor).astype(np.int32)
+        img_w = np.round(ori_shape[1] * scale_factor).astype(np.int32)
+        scale_factor = 1.0
+    if not isinstance(scale_factor, (float, torch.Tensor)):
+        scale_factor = bboxes.new_tensor(scale_factor)
+    bboxes = bboxes / scale_factor
+    img_h, img_w = int(img_h), int(img_w)
+    labels = det_labels if mask_pred.shape[1] > 1 else None
+    return ops.paste_rle(mask_pred.to(torch.float32), bboxes, labels, img_h, img_w,
+                         [0, 0, img_w, img_h], True, float(rcnn_test_cfg.mask_thr_binary))
+
+
+def encode_mask_results(mask_results):
+    """Drop-in for ``mmdet.core.mask.utils.encode_mask_results`` (``utils.py:36-63``) for results
+    that are still on the device: ``mask_results`` is a per-class list of lists of ``[H, W]`` bool /
+    uint8 CUDA tensors (or a ``(segms, scores)`` tuple); returns the same nesting of RLE dicts."""
+    if isinstance(mask_results, tuple):
+        cls_segms, cls_mask_scores = mask_results
+    else:
+        cls_segms = mask_results
+    flat = [m for segs in cls_segms for m in segs]
+    encoded = []
+    if flat:
+        shapes = {tuple(m.shape) for m in flat}
+        if len(shapes) == 1:
+            encoded = ops.rle_from_canvas(torch.stack([m.to(torch.bool) for m in flat]))
+        else:
+            for m in flat:
+                encoded.extend(ops.rle_from_canvas(m.to(torch.bool)[None]))
+    out, k = [], 0
+    for segs in cls_segms:
+        out.append(encoded[k:k + len(segs)])
+        k += len(segs)
+    if isinstance(mask_results, tuple):
+        return out, cls_mask_scores
+    return out
+
+
 class DynaMaskHeadMixin(object):
     """``get_targets`` / ``get_seg_masks`` with the reference ``DynaMaskHead`` signatures."""
 

@@ -312,3 +312,100 @@ def _(gt_blob, img_offsets, img_ghw, boxes, inds, roi_img, clip, sizes_hw):
     K = boxes.size(0)
     return [torch.empty((K, sizes_hw[2 * s], sizes_hw[2 * s + 1]), dtype=torch.float32,
                         device=boxes.device) for s in range(len(sizes_hw) // 2)]
+
+
+# --------------------------------------------------------------------------------------------
+# dm_paste_rle / dm_rle_from_canvas / dm_rle_compress_host  
+# --------------------------------------------------------------------------------------------
+def _rle_finish(N, rh, rw, totals, run_pass2):
+    """Shared tail of the two RLE entry points: scan the per-instance totals, run pass 2, bring the
+    transitions to the host (a few KB per instance) and compress them to pycocotools strings."""
+    import numpy as np
+    totals_h = totals.cpu().numpy().astype(np.int64)         # one small D2H + sync
+    offsets_h = np.zeros(N + 1, np.int64)
+    np.cumsum(totals_h, out=offsets_h[1:])
+    total = int(offsets_h[-1])
+    dev = totals.device
+    offsets = torch.from_numpy(offsets_h[:-1].copy()).to(dev)
+    trans = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    run_pass2(offsets, trans)
+    trans_h = trans[:total].cpu().numpy()
+    lib = _lib.load()
+    out = []
+    buf = ctypes.create_string_buffer(64)
+    for n in range(N):
+        t = np.ascontiguousarray(trans_h[offsets_h[n]:offsets_h[n + 1]])
+        cap = 6 * (t.size + 1) + 8
+        if cap > len(buf):
+            buf = ctypes.create_string_buffer(cap)
+        ln = lib.dm_rle_compress_host(ctypes.c_void_p(t.ctypes.data), int(t.size), int(rh) * int(rw),
+                                      ctypes.cast(buf, ctypes.c_void_p), len(buf))
+        if ln < 0:
+            raise RuntimeError('dm_rle_compress_host: buffer too small')
+        out.append({'size': [int(rh), int(rw)], 'counts': buf.raw[:ln]})
+    return out
+
+
+def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,
+              region: Sequence[int], apply_sigmoid: bool, thr: float):
+    """Fused paste -> COCO RLE: same arguments as :func:`paste_masks` in bool mode, but returns a
+    list of N ``{'size': [h, w], 'counts': bytes}`` dicts (what ``pycocotools.mask.encode`` gives for
+    each pasted canvas) without ever materialising the canvases."""
+    if masks.dim() != 4:
+        raise ValueError('masks must be [N,C,S_h,S_w]')
+    if not masks.is_cuda:
+        raise NotImplementedError('dynamask::paste_rle has no CPU implementation')
+    masks = _f32c(masks, 'masks')
+    if masks.stride(3) != 1 or masks.stride(2) != masks.size(3):
+        masks = masks.contiguous()
+    N, _, sh, sw = masks.shape
+    dev = masks.device
+    boxes = _f32c(boxes, 'boxes')[:, :4].contiguous()
+    if boxes.size(0) != N:
+        raise ValueError('boxes must be [N,4]')
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    x_lo, y_lo, x_hi, y_hi = [int(v) for v in region]
+    rh, rw = y_hi - y_lo, x_hi - x_lo
+    if N == 0:
+        return []
+    col_counts = torch.empty((N, max(rw, 1)), dtype=torch.int32, device=dev)
+    totals = torch.zeros(N, dtype=torch.int32, device=dev)
+
+    def run(pass_no, offsets, trans):
+        with torch.cuda.device(dev):
+            rc = _lib.load().dm_paste_rle(_ptr(masks), masks.stride(0), masks.stride(1), _ptr(labels), N,
+                                          sh, sw, int(bool(apply_sigmoid)), _ptr(boxes), int(img_h),
+                                          int(img_w), x_lo, y_lo, x_hi, y_hi, float(thr), pass_no,
+                                          _ptr(col_counts), _ptr(totals), _ptr(offsets), _ptr(trans),
+                                          _stream(dev))
+        _lib.check(rc, 'dm_paste_rle')
+
+    run(1, None, None)
+    return _rle_finish(N, rh, rw, totals, lambda off, tr: run(2, off, tr))
+
+
+def rle_from_canvas(canvas: Tensor):
+    """COCO RLE of an existing ``[N,H,W]`` bool / uint8 device canvas (non-zero = foreground)."""
+    if canvas.dim() != 3:
+        raise ValueError('canvas must be [N,H,W]')
+    if not canvas.is_cuda:
+        raise NotImplementedError('dynamask::rle_from_canvas has no CPU implementation')
+    if canvas.dtype not in (torch.bool, torch.uint8):
+        raise TypeError('canvas must be bool or uint8')
+    canvas = canvas.contiguous()
+    N, H, W = canvas.shape
+    dev = canvas.device
+    if N == 0:
+        return []
+    col_counts = torch.empty((N, max(W, 1)), dtype=torch.int32, device=dev)
+    totals = torch.zeros(N, dtype=torch.int32, device=dev)
+
+    def run(pass_no, offsets, trans):
+        with torch.cuda.device(dev):
+            rc = _lib.load().dm_rle_from_canvas(_ptr(canvas), N, H, W, pass_no, _ptr(col_counts), _ptr(totals),
+                                                _ptr(offsets), _ptr(trans), _stream(dev))
+        _lib.check(rc, 'dm_rle_from_canvas')
+
+    run(1, None, None)
+    return _rle_finish(N, H, W, totals, lambda off, tr: run(2, off, tr))

@@ -137,6 +137,38 @@ int dm_mask_target(const uint8_t* gt_blob, const int64_t* img_offsets, const int
                    int clip, const int32_t* sizes_hw, int n_sizes, float* const* out_ptrs,
                    dm_stream_t stream);
 
+/*
+ * Next row: COCO run-length encoding of the pasted masks on the device.
+ * Replaces encode_mask_results(get_seg_masks(...)) -- mmdet/core/mask/utils.py:36-63 applied to the
+ * N numpy canvases of mmdet/models/roi_heads/mask_heads/dynamask_head.py:341 (pycocotools
+ * mask.encode on the host after an N*H*W-byte device->host copy).
+ *
+ * A column-major run list is described by the sorted flat indices x*H + y at which the value
+ * changes ("transitions").  Two passes over the same pixels:
+ *   pass 1  writes col_counts [N, rw] int32 (transitions per column; only an instance's window
+ *           columns are defined) and ADDS into inst_totals [N] int32 (zero it first);
+ *   pass 2  given inst_offsets [N] int64 (exclusive scan of inst_totals) writes the transitions of
+ *           instance n at transitions + inst_offsets[n], sorted.
+ * dm_paste_rle evaluates the pixels from the mask logits exactly like dm_paste_masks in
+ * DM_PASTE_BOOL mode (same arguments), never writing a canvas; dm_rle_from_canvas reads an existing
+ * [N,H,W] one-byte-per-pixel canvas.
+ */
+int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                 const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                 const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi, int y_hi,
+                 float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
+                 const int64_t* inst_offsets, int32_t* transitions, dm_stream_t stream);
+int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int32_t* col_counts,
+                       int32_t* inst_totals, const int64_t* inst_offsets, int32_t* transitions,
+                       dm_stream_t stream);
+/*
+ * HOST function: the transitions of one instance (host memory) -> pycocotools' compressed "counts"
+ * string (rleToString).  Coinciding transition pairs cancel.  Returns the length written to `out`
+ * (no terminator) or -1 if `cap` is too small.
+ */
+int64_t dm_rle_compress_host(const int32_t* transitions, int64_t n, int64_t total_pixels, char* out,
+                             int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -348,3 +348,82 @@ def get_seg_masks(mask_pred, det_bboxes, det_labels, mask_thr_binary, ori_shape,
             chunk = (chunk * 255).to(torch.uint8)
         canvas[(torch.tensor([i]),) + sl] = chunk
     return [canvas[i].numpy() for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# COCO run-length encoding.  The reference calls pycocotools
+# (mmdet/core/mask/utils.py:36-63: mask_util.encode(np.array(m[:, :, None], order='F', dtype='uint8'))[0]);
+# pycocotools (2.0.x, third party, absent from the reference tree and from this image) is restated
+# here from its published algorithm (common/maskApi.c: rleEncode, rleToString, rleFrString,
+# rleDecode).  PARITY UNPINNED against the real library: no pycocotools, no golden strings in the
+# reference's tests; pinned only by encode/decode round trips and hand-checked small cases.
+# ------------------------------------------------------------------------------------------------
+def rle_counts(mask):
+    """rleEncode: run lengths of the column-major flattening, starting with a run of zeros."""
+    flat = np.asarray(mask).astype(np.uint8).reshape(-1, order='F') != 0
+    if flat.size == 0:
+        return [0]
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    bounds = np.concatenate([[0], change, [flat.size]])
+    counts = np.diff(bounds).tolist()
+    if flat[0]:
+        counts = [0] + counts
+    return counts
+
+
+def rle_to_string(counts):
+    """rleToString: base-32 varint, each count beyond the second stored relative to two before."""
+    out = bytearray()
+    for i, c in enumerate(counts):
+        x = int(c)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            ch = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            out.append(ch + 48)
+    return bytes(out)
+
+
+def rle_from_string(s):
+    """rleFrString: inverse of rle_to_string."""
+    counts = []
+    p = 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(counts) > 2:
+            x += counts[-2]
+        counts.append(x)
+    return counts
+
+
+def rle_encode(mask):
+    """pycocotools.mask.encode for one [H,W] mask: {'size': [h, w], 'counts': bytes}."""
+    h, w = np.asarray(mask).shape
+    return {'size': [int(h), int(w)], 'counts': rle_to_string(rle_counts(mask))}
+
+
+def rle_decode(rle):
+    """pycocotools.mask.decode for one RLE dict -> [H,W] uint8."""
+    h, w = rle['size']
+    counts = rle_from_string(rle['counts'])
+    flat = np.zeros(h * w, np.uint8)
+    pos, v = 0, 0
+    for c in counts:
+        if v:
+            flat[pos:pos + c] = 1
+        pos += c
+        v ^= 1
+    return flat.reshape((h, w), order='F')

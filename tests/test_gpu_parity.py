@@ -382,6 +382,66 @@ def test_do_paste_mask_values(skip_empty):
 
 
 # ------------------------------------------------------------------------------------------
+# next row: COCO RLE of the pasted masks on the device
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(800, 1333), (431, 637), (64, 48)])
+def test_get_seg_masks_rle_equals_encoding_of_pasted_masks(shape):
+    img_h, img_w = shape
+    n = 24
+    logits, boxes = _dets(n, img_h, img_w, 51)
+    boxes[1] = torch.tensor([-20.0, -30.0, img_w + 15.0, img_h + 25.0])   # covers the canvas: runs cross columns
+    boxes[2] = torch.tensor([5.0, -10.0, 40.0, img_h + 10.0])             # full height
+    boxes[3] = torch.tensor([3.0, 4.0, 3.0, 30.0])                        # degenerate width
+    logits[1] = logits[1].abs() + 1.0                                     # all foreground
+    det = torch.cat([boxes, torch.ones(n, 1)], 1).cuda()
+    labels = torch.zeros(n, dtype=torch.long).cuda()
+    cfg = _Cfg(0.5)
+    masks = dm().get_seg_masks(logits.cuda(), det, labels, cfg, (img_h, img_w, 3), 1.0, False)
+    rles = dm().get_seg_masks_rle(logits.cuda(), det, labels, cfg, (img_h, img_w, 3), 1.0, False)
+    assert len(rles) == n
+    for i in range(n):
+        assert rles[i]['size'] == [img_h, img_w]
+        # the fused kernel evaluates the same arithmetic as the paste kernel: bit-identical masks
+        assert np.array_equal(O.rle_decode(rles[i]).astype(bool), masks[i]), i
+        assert rles[i]['counts'] == O.rle_encode(masks[i])['counts'], i
+    assert int(masks[1].sum()) == img_h * img_w
+
+
+def test_get_seg_masks_rle_multiclass_and_rescale():
+    img_h, img_w = 240, 320
+    logits, boxes = _dets(9, int(img_h * 1.5), int(img_w * 1.5), 52)
+    logits = torch.cat([logits, -logits], 1)
+    labels = torch.tensor([0, 1, 0, 1, 1, 0, 0, 1, 0]).cuda()
+    det = torch.cat([boxes, torch.ones(9, 1)], 1).cuda()
+    sf = np.array([1.5] * 4, np.float32)
+    masks = dm().get_seg_masks(logits.cuda(), det, labels, _Cfg(0.3), (img_h, img_w, 3), sf, True)
+    rles = dm().get_seg_masks_rle(logits.cuda(), det, labels, _Cfg(0.3), (img_h, img_w, 3), sf, True)
+    for m, r in zip(masks, rles):
+        assert r == O.rle_encode(m)
+    assert dm().get_seg_masks_rle(logits[:0].cuda(), det[:0], labels[:0], _Cfg(0.3), (img_h, img_w, 3), sf, True) == []
+
+
+def test_rle_from_canvas_and_encode_mask_results():
+    g = gen(53)
+    canv = torch.rand(7, 93, 131, generator=g) < torch.rand(7, 1, 1, generator=g)
+    canv[0] = False
+    canv[1] = True
+    canv[2, :, 10:20] = True        # full-height columns: runs continue across column boundaries
+    rles = dm().ops.rle_from_canvas(canv.cuda())
+    for i in range(7):
+        assert rles[i] == O.rle_encode(canv[i].numpy()), i
+    u8 = dm().ops.rle_from_canvas((canv.to(torch.uint8) * 255).cuda())
+    assert u8 == rles
+    # the reference's nesting: per class, a list of masks (mmdet/core/mask/utils.py:36-63)
+    per_class = [[canv[0].cuda(), canv[3].cuda()], [], [canv[5].cuda()]]
+    enc = dm().encode_mask_results(per_class)
+    assert [len(e) for e in enc] == [2, 0, 1]
+    assert enc[0][1] == rles[3] and enc[2][0] == rles[5]
+    enc2, scores = dm().encode_mask_results((per_class, 'scores'))
+    assert enc2 == enc and scores == 'scores'
+
+
+# ------------------------------------------------------------------------------------------
 # stage 4: mask targets
 # ------------------------------------------------------------------------------------------
 def _target_case(seed, img_h, img_w, g_n, k):

@@ -195,3 +195,74 @@ def test_sharding_helpers():
     a = torch.arange(12, dtype=torch.float32)
     assert dm.checksum64(a) == dm.checksum64(a.clone()) != dm.checksum64(a.flip(0))
     assert dm.gather_checksums([1, 2]) == [[1, 2]]
+
+
+# ------------------------------------------------------------------------------------------
+# COCO RLE (next row): the host half of the path runs without a GPU
+# ------------------------------------------------------------------------------------------
+def _transitions(mask):
+    """What the kernels emit: every column on its own, from 0 and back to 0 after its last row."""
+    h, w = mask.shape
+    out = []
+    for x in range(w):
+        col = np.concatenate([[0], mask[:, x].astype(np.int64), [0]])
+        out.extend((x * h + np.flatnonzero(col[1:] != col[:-1])).tolist())
+    return np.asarray(out, np.int32)
+
+
+def _compress(trans, total):
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(6 * (len(trans) + 1) + 8)
+    t = np.ascontiguousarray(trans, np.int32)
+    n = lib.dm_rle_compress_host(ctypes.c_void_p(t.ctypes.data), int(t.size), int(total),
+                                 ctypes.cast(buf, ctypes.c_void_p), len(buf))
+    assert n >= 0
+    return buf.raw[:n]
+
+
+def test_oracle_rle_round_trip_and_small_known_cases():
+    from oracle import oracle as O
+    assert O.rle_counts(np.array([[0, 1], [1, 1]])) == [1, 3]          # column-major 0,1,1,1
+    assert O.rle_counts(np.ones((3, 3))) == [0, 9]                      # starts with an empty zero run
+    assert O.rle_counts(np.zeros((5, 7))) == [35]
+    assert O.rle_encode(np.array([[0, 1], [1, 1]]))['counts'] == b'13'
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        h, w = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+        m = (rng.random((h, w)) < rng.random()).astype(np.uint8)
+        r = O.rle_encode(m)
+        assert r['size'] == [h, w]
+        assert O.rle_from_string(r['counts']) == O.rle_counts(m)
+        assert np.array_equal(O.rle_decode(r), m)
+
+
+def test_rle_compress_host_matches_oracle_strings():
+    from oracle import oracle as O
+    rng = np.random.default_rng(4)
+    cases = [np.zeros((6, 9), np.uint8), np.ones((6, 9), np.uint8)]
+    full = np.zeros((8, 5), np.uint8)
+    full[:, 1:4] = 1                      # runs that continue across column boundaries (pairs cancel)
+    cases.append(full)
+    big = np.zeros((800, 1333), np.uint8)
+    big[100:300, 200:500] = 1             # counts far above 2^15: multi-character varints, negative deltas
+    big[0:800, 900] = 1
+    cases.append(big)
+    for _ in range(60):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        cases.append((rng.random((h, w)) < rng.random()).astype(np.uint8))
+    for m in cases:
+        got = _compress(_transitions(m), m.size)
+        assert got == O.rle_encode(m)['counts'], m.shape
+    # too small a buffer is reported, not overrun
+    lib = _lib.load()
+    t = _transitions(big)
+    buf = ctypes.create_string_buffer(4)
+    assert lib.dm_rle_compress_host(ctypes.c_void_p(t.ctypes.data), int(t.size), int(big.size),
+                                    ctypes.cast(buf, ctypes.c_void_p), 4) == -1
+
+
+def test_rle_ops_refuse_cpu_tensors():
+    with pytest.raises(NotImplementedError):
+        ops.rle_from_canvas(torch.zeros(1, 4, 4, dtype=torch.bool))
+    with pytest.raises(NotImplementedError):
+        ops.paste_rle(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4), None, 8, 8, [0, 0, 8, 8], True, 0.5)
