@@ -432,7 +432,25 @@ def run_extras(dm, ops, dev, rank, peak):
     b.record()
     torch.cuda.synchronize()
     ex['dm_paste_masks']['fill_same_bytes_ms'] = a.elapsed_time(b) / reps
-    del out, logits
+    # inference tail on the same 800 instances, end to end with host results (what mmdet/apis/test.py:54-57
+    # needs): (a) reference flow -- paste, copy the N x H x W canvases to the host (RLE would follow on the
+    # CPU); (b) fused paste -> RLE on the device, only run boundaries cross PCIe, strings built on the host
+    det = torch.cat([boxes, torch.ones(n, 1, device=dev)], 1)
+    labels0 = torch.zeros(n, dtype=torch.long, device=dev)
+
+    class _Cfg:
+        mask_thr_binary = 0.5
+    import time as _time
+    for fn, key in ((dm.get_seg_masks, 'get_seg_masks_to_host_ms'), (dm.get_seg_masks_rle, 'get_seg_masks_rle_to_host_ms')):
+        fn(logits, det, labels0, _Cfg, (800, 1333, 3), 1.0, False)
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(3):
+            res = fn(logits, det, labels0, _Cfg, (800, 1333, 3), 1.0, False)
+        torch.cuda.synchronize()
+        ex['dm_paste_masks'][key] = (_time.perf_counter() - t0) / 3 * 1e3
+    ex['dm_paste_masks']['rle_bytes_to_host'] = int(sum(len(r['counts']) for r in res))
+    del out, logits, res
     # mask targets: C3 shape, 2 images x 128 positives, all four sizes in one launch
     rng = np.random.default_rng(7 + rank)
     masks_l, props, inds = [], [], []
