@@ -34,14 +34,21 @@ int sm_count();  // cached per device, read-only after first query
 
 // ---- RoI geometry shared by forward / backward ----------------------------------------------
 // Mirrors the setup of the aligned avg-pool RoIAlign.
+// mode 0: RoIAlign (sampling grid, clamped border).  mode 1 / 2: SimpleRoIAlign point sampling
+// (one sample per bin, zero padding; 1 = align_corners False, 2 = align_corners True), in which
+// case (rsw, rsh) is the RoI corner and (bw, bh) its extent in input-image pixels.
 struct RoiGeom {
     float rsw, rsh, bw, bh;
     int gw, gh;
+    int mode;
+    float scale;
 };
 
 __device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi5, float scale, int ph,
                                             int pw, int sampling_ratio, int aligned) {
     RoiGeom g;
+    g.mode = 0;
+    g.scale = scale;
     const float off = aligned ? 0.5f : 0.0f;
     g.rsw = __fsub_rn(__fmul_rn(roi5[1], scale), off);
     g.rsh = __fsub_rn(__fmul_rn(roi5[2], scale), off);
@@ -79,6 +86,61 @@ __device__ __forceinline__ bool axis_tap(float v, int size, int& lo, int& hi, fl
     l = __fsub_rn(v, (float)lo);
     h = __fsub_rn(1.0f, l);
     return true;
+}
+
+// ---- SimpleRoIAlign (mmcv.ops.point_sample.SimpleRoIAlign as used by SFMStage,
+// mmdet/models/roi_heads/mask_heads/dynamask_head.py:74,104-105) ---------------------------------
+// One grid_sample point per bin.  The coordinate follows the fp32 op sequence of the mmcv helpers
+// (generate_grid -> rel_roi_point_to_rel_img_point -> point_sample -> grid_sample unnormalise).
+__device__ __forceinline__ RoiGeom point_geom(const float* __restrict__ roi5, float scale, int aligned) {
+    RoiGeom g;
+    g.mode = aligned ? 1 : 2;
+    g.scale = scale;
+    g.rsw = roi5[1];
+    g.rsh = roi5[2];
+    g.bw = __fsub_rn(roi5[3], roi5[1]);
+    g.bh = __fsub_rn(roi5[4], roi5[2]);
+    g.gw = g.gh = 1;
+    return g;
+}
+
+// pixel coordinate of bin p's point on an axis of `size` pixels, P bins
+__device__ __forceinline__ float point_coord(float corner, float extent, float scale, int mode, int P, int size, int p) {
+    // generate_grid: F.affine_grid's base grid is linspace(-1, 1, P) * (P - 1) / P (evaluated from
+    // whichever end is nearer, as ATen's linspace does), then normalised to [0, 1]
+    float lin = -1.0f;
+    if (P > 1) {
+        const float step = __fdiv_rn(2.0f, (float)(P - 1));
+        lin = p < P / 2 ? __fadd_rn(-1.0f, __fmul_rn(step, (float)p))
+                        : __fsub_rn(1.0f, __fmul_rn(step, (float)(P - p - 1)));
+    }
+    const float rel = __fdiv_rn(__fadd_rn(__fdiv_rn(__fmul_rn(lin, (float)(P - 1)), (float)P), 1.0f), 2.0f);
+    const float ab = __fadd_rn(__fmul_rn(rel, extent), corner);                    // rel -> abs image
+    const float q = __fmul_rn(__fdiv_rn(ab, (float)size), scale);                  // abs -> rel image
+    const float gc = __fsub_rn(__fmul_rn(q, 2.0f), 1.0f);                          // denormalize
+    if (mode == 1) return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gc, 1.0f), (float)size), 1.0f), 2.0f);
+    return __fmul_rn(__fdiv_rn(__fadd_rn(gc, 1.0f), 2.0f), (float)(size - 1));
+}
+
+// bilinear taps with zero padding: an out-of-range tap keeps weight 0 and a clamped index
+__device__ __forceinline__ bool point_tap(float v, int size, int& lo, int& hi, float& l, float& h) {
+    if (!(v > -1.0f && v < (float)size)) return false;
+    const float fl = floorf(v);
+    lo = (int)fl;
+    hi = lo + 1;
+    l = __fsub_rn(v, fl);
+    h = __fsub_rn(1.0f, l);
+    if (lo < 0) { lo = 0; h = 0.0f; }
+    if (hi > size - 1) { hi = size - 1; l = 0.0f; }
+    return true;
+}
+
+// One axis of sample (bin p, sub-sample i) under either mode.  axis 0 = x, 1 = y.
+__device__ __forceinline__ bool geom_tap(const RoiGeom& g, int axis, int P, int size, int p, int i,
+                                         int& lo, int& hi, float& l, float& h) {
+    const float start = axis ? g.rsh : g.rsw, bin = axis ? g.bh : g.bw;
+    if (g.mode == 0) return axis_tap(sample_coord(start, bin, axis ? g.gh : g.gw, p, i), size, lo, hi, l, h);
+    return point_tap(point_coord(start, bin, g.scale, g.mode, P, size, p), size, lo, hi, l, h);
 }
 
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }

@@ -84,6 +84,7 @@ struct RaParams {
     const int32_t* perm;
     const int32_t* seg;
     int sampling_ratio, aligned;
+    int mode;  // 0 RoIAlign, 1 SimpleRoIAlign (one zero-padded grid_sample point per bin)
     int smem_floats;
 };
 
@@ -238,14 +239,14 @@ struct Tables {
 // register-window class for a band width: 2, 4, 8, or 0 when wider than 8
 __device__ __forceinline__ int window_class(int j) { return j <= 2 ? 2 : (j <= 4 ? 4 : (j <= 8 ? 8 : 0)); }
 
-__device__ __forceinline__ void axis_scan(int P, int size, float start, float bin, int grid,
+__device__ __forceinline__ void axis_scan(const RoiGeom& g, int axis, int P, int size, int grid,
                                           int* s_start, int* stat) {
     for (int p = threadIdx.x; p < P; p += RA_THREADS) {
         int first = INT_MAX, last = -1;
         for (int i = 0; i < grid; ++i) {
             int lo, hi;
             float l, h;
-            if (axis_tap(sample_coord(start, bin, grid, p, i), size, lo, hi, l, h)) {
+            if (geom_tap(g, axis, P, size, p, i, lo, hi, l, h)) {
                 first = min(first, lo);
                 last = max(last, hi);
             }
@@ -261,7 +262,7 @@ __device__ __forceinline__ void axis_scan(int P, int size, float start, float bi
     }
 }
 
-__device__ __forceinline__ void axis_fill(int P, int size, float start, float bin, int grid,
+__device__ __forceinline__ void axis_fill(const RoiGeom& g, int axis, int P, int size, int grid,
                                           const int* s_start, float* w) {
     const float inv = 1.0f / (float)grid;
     for (int p = threadIdx.x; p < P; p += RA_THREADS) {
@@ -269,7 +270,7 @@ __device__ __forceinline__ void axis_fill(int P, int size, float start, float bi
         for (int i = 0; i < grid; ++i) {
             int lo, hi;
             float l, h;
-            if (axis_tap(sample_coord(start, bin, grid, p, i), size, lo, hi, l, h)) {
+            if (geom_tap(g, axis, P, size, p, i, lo, hi, l, h)) {
                 w[(lo - st) * P + p] += h * inv;
                 w[(hi - st) * P + p] += l * inv;
             }
@@ -291,8 +292,8 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     __syncthreads();
     if (g.gw <= 0 || g.gh <= 0) return false;
     if (Pw + Ph > smem_floats) { fits = false; return true; }
-    axis_scan(Pw, W, g.rsw, g.bw, g.gw, t.xs, stat + ST_JX);
-    axis_scan(Ph, H, g.rsh, g.bh, g.gh, t.ys, stat + ST_JY);
+    axis_scan(g, 0, Pw, W, g.gw, t.xs, stat + ST_JX);
+    axis_scan(g, 1, Ph, H, g.gh, t.ys, stat + ST_JY);
     __syncthreads();
     t.JX = stat[ST_JX]; t.X0 = stat[ST_X0]; t.X1 = stat[ST_X1];
     t.JY = stat[ST_JY]; t.Y0 = stat[ST_Y0]; t.Y1 = stat[ST_Y1];
@@ -329,8 +330,8 @@ __device__ bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, flo
     for (int i = threadIdx.x; i < wfloats; i += RA_THREADS) t.wx[i] = 0.0f;
     for (int i = threadIdx.x; i < rfloats; i += RA_THREADS) t.rcnt[i] = 0;
     __syncthreads();
-    axis_fill(Pw, W, g.rsw, g.bw, g.gw, t.xs, t.wx);
-    axis_fill(Ph, H, g.rsh, g.bh, g.gh, t.ys, t.wy);
+    axis_fill(g, 0, Pw, W, g.gw, t.xs, t.wx);
+    axis_fill(g, 1, Ph, H, g.gh, t.ys, t.wy);
     __syncthreads();
     t.mR = (unsigned)stat[ST_MR];
     if (t.ystride) {
@@ -427,11 +428,11 @@ __device__ void direct_unit(const LevelDesc& Lv, const BucketDesc& B, const RoiG
         for (int iy = 0; iy < g.gh; ++iy) {
             int yl, yh;
             float ly, hy;
-            if (!axis_tap(sample_coord(g.rsh, g.bh, g.gh, ph, iy), Lv.H, yl, yh, ly, hy)) continue;
+            if (!geom_tap(g, 1, B.ph, Lv.H, ph, iy, yl, yh, ly, hy)) continue;
             for (int ix = 0; ix < g.gw; ++ix) {
                 int xl, xh;
                 float lx, hx;
-                if (!axis_tap(sample_coord(g.rsw, g.bw, g.gw, pw, ix), Lv.W, xl, xh, lx, hx)) continue;
+                if (!geom_tap(g, 0, B.pw, Lv.W, pw, ix, xl, xh, lx, hx)) continue;
                 float* p1 = f + (long long)yl * Lv.sH + (long long)xl * Lv.sW;
                 float* p2 = f + (long long)yl * Lv.sH + (long long)xh * Lv.sW;
                 float* p3 = f + (long long)yh * Lv.sH + (long long)xl * Lv.sW;
@@ -749,7 +750,13 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
         return;
     }
     const LevelDesc& Lv = p.lv[lv];
-    const RoiGeom g = roi_geom(roi, Lv.scale, B.ph, B.pw, p.sampling_ratio, p.aligned);
+    const RoiGeom g = p.mode ? point_geom(roi, Lv.scale, p.aligned) : roi_geom(roi, Lv.scale, B.ph, B.pw, p.sampling_ratio, p.aligned);
+    if (g.mode && !(g.bw >= 0.0f && g.bh >= 0.0f)) {
+        // SimpleRoIAlign on a box with x2 < x1 or y2 < y1: the points run backwards, so the bands
+        // are not monotone -- evaluate sample by sample
+        direct_unit<false>(Lv, B, g, batch, un.i, c0, c1);
+        return;
+    }
     Tables t;
     bool fits;
     if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) {
@@ -1085,7 +1092,11 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     if (lv < 0 || lv >= p.L) return;
     const LevelDesc& Lv = p.lv[lv];
     if (batch < 0 || batch >= Lv.N) return;
-    const RoiGeom g = roi_geom(roi, Lv.scale, B.ph, B.pw, p.sampling_ratio, p.aligned);
+    const RoiGeom g = p.mode ? point_geom(roi, Lv.scale, p.aligned) : roi_geom(roi, Lv.scale, B.ph, B.pw, p.sampling_ratio, p.aligned);
+    if (g.mode && !(g.bw >= 0.0f && g.bh >= 0.0f)) {
+        direct_unit<true>(Lv, B, g, batch, un.i, c0, c1);
+        return;
+    }
     Tables t;
     bool fits;
     if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) return;
@@ -1300,6 +1311,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
     p.seg = seg;
     p.sampling_ratio = sampling_ratio;
     p.aligned = aligned ? 1 : 0;
+    p.mode = 0;
     return DM_OK;
 }
 
@@ -1365,4 +1377,50 @@ extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* fea
     }
     if (K == 0) return DM_OK;
     return dm::launch<true>(p, st, "dm_roi_align_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// SimpleRoIAlign: one zero-padded grid_sample point per bin.  Same separable
+// banded map as RoIAlign with a one-sample grid, so it runs through the same persistent kernels
+// with the tables built by point_geom / point_tap.
+// ---------------------------------------------------------------------------------------------
+extern "C" int dm_simple_roi_align_fwd(const float* feat, const int32_t* feat_shape,
+                                       const int64_t* feat_strides, float spatial_scale,
+                                       const float* rois, int K, int out_h, int out_w, float* out,
+                                       const int64_t* out_strides, int aligned, dm_stream_t stream) {
+    if (!feat || !feat_shape || !feat_strides || !out_strides || (K > 0 && !out)) return DM_EINVAL;
+    dm::RaParams p;
+    float* fp = const_cast<float*>(feat);
+    const int32_t hw[2] = {out_h, out_w};
+    const int rc = dm::fill_params(p, &fp, feat_shape, feat_strides, &spatial_scale, 1, rois, K, nullptr,
+                                   nullptr, nullptr, 1, hw, &out, out_strides, 0, aligned);
+    if (rc != DM_OK) return rc;
+    if (K == 0) return DM_OK;
+    p.mode = 1;
+    return dm::launch<false>(p, (cudaStream_t)stream, "dm_simple_roi_align_fwd");
+}
+
+extern "C" int dm_simple_roi_align_bwd(float* grad_feat, const int32_t* feat_shape,
+                                       const int64_t* feat_strides, float spatial_scale,
+                                       const float* rois, int K, int out_h, int out_w,
+                                       const float* grad_out, const int64_t* grad_out_strides,
+                                       int aligned, int zero_init, dm_stream_t stream) {
+    if (!grad_feat || !feat_shape || !feat_strides || !grad_out_strides || (K > 0 && !grad_out)) return DM_EINVAL;
+    dm::RaParams p;
+    float* go = const_cast<float*>(grad_out);
+    const int32_t hw[2] = {out_h, out_w};
+    const int rc = dm::fill_params(p, &grad_feat, feat_shape, feat_strides, &spatial_scale, 1, rois, K,
+                                   nullptr, nullptr, nullptr, 1, hw, &go, grad_out_strides, 0, aligned);
+    if (rc != DM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (zero_init) {
+        const dm::LevelDesc& d = p.lv[0];
+        const long long n = (long long)d.N * d.C * d.H * d.W;
+        const long long span = (d.N - 1) * d.sN + (d.C - 1) * d.sC + (d.H - 1) * d.sH + (d.W - 1) * d.sW + 1;
+        if (span != n) return DM_EINVAL;
+        DM_CUDA_CHECK(cudaMemsetAsync(d.ptr, 0, sizeof(float) * (size_t)n, st), "dm_simple_roi_align_bwd/memset");
+    }
+    if (K == 0) return DM_OK;
+    p.mode = 1;
+    return dm::launch<true>(p, st, "dm_simple_roi_align_bwd");
 }

@@ -146,6 +146,27 @@ def encode_mask_results(mask_results):
     return out
 
 
+def refine_stage_instance_preds(stage_instance_preds):
+    """The coarse-to-fine refinement loop of ``DynaMaskRoIHead.simple_test_mask``
+    (``mmdet/models/roi_heads/dynamask_roi_head.py:136-148``) as one launch.
+
+    ``stage_instance_preds`` is the list the reference builds at ``:136``
+    (``mask_results['stage_instance_preds'][1:]``: the 28 / 56 / 112 logits, each ``[N,1,S,S]``).
+    Like the reference it refines the tensors **in place** -- non-boundary pixels of every finer
+    stage are overwritten with the bilinearly up-sampled (already refined) coarser stage -- and
+    returns the last one, the ``instance_pred`` handed to ``get_seg_masks`` at ``:148-151``.
+    Non-contiguous inputs are refined through a contiguous copy that is written back."""
+    preds = list(stage_instance_preds)
+    if len(preds) == 0:
+        raise ValueError('need at least one stage')
+    work = [p if p.is_contiguous() else p.contiguous() for p in preds]
+    ops.refine_stages_(work)
+    for p, w in zip(preds, work):
+        if w is not p:
+            p.copy_(w)
+    return preds[-1]
+
+
 class DynaMaskHeadMixin(object):
     """``get_targets`` / ``get_seg_masks`` with the reference ``DynaMaskHead`` signatures."""
 

@@ -206,3 +206,225 @@ class BitmapMasks(object):
         else:
             resized_masks = []
         return BitmapMasks(resized_masks, *out_shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# Polygon ground truth (reference type: ``PolygonMasks``, ``mmdet/core/mask/structures.py:314-558``)
+# SURVEY.md row A10 / 8f rank 4.
+# ---------------------------------------------------------------------------------------------
+def pack_polygons(polys_per_image, hw_per_image, device):
+    """Flatten the polygons of a batch for ``dm_polygon_target``.
+
+    ``polys_per_image``: per image, a list (objects) of lists (polygons) of 1-D float arrays
+    ``(x0, y0, x1, y1, ...)``.  Returns ``(xy float64 [2V], vert_offsets int64 [P+1],
+    obj_poly_offsets int32 [G+1], img_meta int32 [B*3])`` on ``device``.
+    """
+    flat, voff, ooff, meta = [], [0], [0], []
+    for objs, (h, w) in zip(polys_per_image, hw_per_image):
+        meta += [len(ooff) - 1, int(h), int(w)]
+        for polys in objs:
+            for p in polys:
+                a = np.asarray(p, dtype=np.float64).reshape(-1)
+                flat.append(a[:2 * (a.size // 2)])
+                voff.append(voff[-1] + a.size // 2)
+            ooff.append(len(voff) - 1)
+    xy = np.concatenate(flat) if flat else np.zeros(0, np.float64)
+    pin = torch.device(device).type == 'cuda'
+
+    def up(a, dt):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
+        if pin:
+            t = t.pin_memory()
+        return t.to(device, non_blocking=True)
+
+    xy_d = up(xy if xy.size else np.zeros(2, np.float64), np.float64)
+    return xy_d, up(np.asarray(voff), np.int64), up(np.asarray(ooff), np.int32), up(np.asarray(meta), np.int32)
+
+
+class PolygonMasks(object):
+    """Masks in the form of polygons: a list (objects) of lists (polygons of the object) of 1-D
+    coordinate arrays ``(x0, y0, x1, y1, ...)``.
+
+    Same constructor, container protocol, host transforms and ``crop_and_resize`` /
+    ``to_ndarray`` results as the reference class; rasterisation runs on the device
+    (``dm_polygon_target``) instead of pycocotools on the host, and
+    :meth:`crop_and_resize_device` produces the float targets of every size in one launch.
+    """
+
+    def __init__(self, masks, height, width):
+        assert isinstance(masks, list)
+        if len(masks) > 0:
+            assert isinstance(masks[0], list)
+            assert isinstance(masks[0][0], np.ndarray)
+        self.height = height
+        self.width = width
+        self.masks = masks
+        self._device_cache = {}
+
+    # ---- container protocol -------------------------------------------------------------
+    def __getitem__(self, index):
+        if isinstance(index, np.ndarray):
+            index = index.tolist()
+        if isinstance(index, list):
+            masks = [self.masks[i] for i in index]
+        else:
+            try:
+                masks = self.masks[index]
+            except Exception:
+                raise ValueError(f'Unsupported input of type {type(index)} for indexing!')
+        if len(masks) and isinstance(masks[0], np.ndarray):
+            masks = [masks]  # keep three levels
+        return PolygonMasks(masks, self.height, self.width)
+
+    def __iter__(self):
+        return iter(self.masks)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(num_masks={len(self.masks)}, '
+                f'height={self.height}, width={self.width})')
+
+    def __len__(self):
+        return len(self.masks)
+
+    # ---- host-side transforms (data pipeline; not on the hot path) --------------------------
+    def _map(self, fn, height, width):
+        return PolygonMasks([[fn(p.copy()) for p in obj] for obj in self.masks], height, width)
+
+    def resize(self, out_shape, interpolation=None):
+        if len(self.masks) == 0:
+            return PolygonMasks([], *out_shape)
+        h_scale = out_shape[0] / self.height
+        w_scale = out_shape[1] / self.width
+
+        def fn(p):
+            p[0::2] *= w_scale
+            p[1::2] *= h_scale
+            return p
+        return self._map(fn, *out_shape)
+
+    def rescale(self, scale, interpolation=None):
+        if isinstance(scale, (float, int)):
+            factor = float(scale)
+        else:
+            long_e, short_e = max(scale), min(scale)
+            factor = min(long_e / max(self.height, self.width), short_e / min(self.height, self.width))
+        new_w = int(self.width * factor + 0.5)
+        new_h = int(self.height * factor + 0.5)
+        return self.resize((new_h, new_w))
+
+    def flip(self, flip_direction='horizontal'):
+        assert flip_direction in ('horizontal', 'vertical')
+        dim, idx = (self.width, 0) if flip_direction == 'horizontal' else (self.height, 1)
+
+        def fn(p):
+            p[idx::2] = dim - p[idx::2]
+            return p
+        return self._map(fn, self.height, self.width)
+
+    def crop(self, bbox):
+        assert isinstance(bbox, np.ndarray)
+        assert bbox.ndim == 1
+        bbox = bbox.copy()
+        bbox[0::2] = np.clip(bbox[0::2], 0, self.width)
+        bbox[1::2] = np.clip(bbox[1::2], 0, self.height)
+        x1, y1, x2, y2 = bbox
+        w = np.maximum(x2 - x1, 1)
+        h = np.maximum(y2 - y1, 1)
+
+        def fn(p):
+            p[0::2] -= bbox[0]
+            p[1::2] -= bbox[1]
+            return p
+        return self._map(fn, h, w)
+
+    def pad(self, out_shape, pad_val=0):
+        """padding has no effect on polygons"""
+        return PolygonMasks(self.masks, *out_shape)
+
+    def expand(self, *args, **kwargs):
+        raise NotImplementedError
+
+    @property
+    def areas(self):
+        """Shoelace area of every object (sum over its polygons)."""
+        out = []
+        for obj in self.masks:
+            a = 0.0
+            for p in obj:
+                x, y = p[0::2], p[1::2]
+                a += 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+            out.append(a)
+        return np.asarray(out)
+
+    # ---- hot path -----------------------------------------------------------------------
+    def to_device(self, device):
+        """Upload the flattened polygons once per device; returns the ``pack_polygons`` tuple."""
+        device = torch.device(device)
+        key = (device.type, device.index)
+        hit = self._device_cache.get(key)
+        if hit is None:
+            hit = pack_polygons([self.masks], [(self.height, self.width)], device)
+            self._device_cache[key] = hit
+        return hit
+
+    def crop_and_resize_device(self, bboxes, out_shapes, inds, device, clip=False):
+        """Float ``[K,h,w]`` {0,1} targets for several output shapes in one launch, on the device."""
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise NotImplementedError('dynamask_b200 has no CPU path: pass a CUDA device')
+        if isinstance(bboxes, np.ndarray):
+            bboxes = torch.from_numpy(np.ascontiguousarray(bboxes, dtype=np.float32))
+        if isinstance(inds, np.ndarray):
+            inds = torch.from_numpy(np.ascontiguousarray(inds).astype(np.int64))
+        bboxes = bboxes.to(device=device, dtype=torch.float32, non_blocking=True)
+        inds = inds.to(device=device, dtype=torch.int64, non_blocking=True)
+        xy, voff, ooff, meta = self.to_device(device)
+        sizes = [int(v) for hw in out_shapes for v in hw]
+        return ops.polygon_target(xy, voff, ooff, meta, bboxes, inds, None, bool(clip), sizes)
+
+    def crop_and_resize(self, bboxes, out_shape, inds, device='cpu', interpolation='bilinear'):
+        """Same return type as the reference: a new ``PolygonMasks`` whose polygons are shifted by
+        the box corner and scaled to ``out_shape`` (host arithmetic identical to
+        ``structures.py:478-499``); rasterise it with :meth:`to_ndarray`."""
+        out_h, out_w = out_shape
+        if len(self.masks) == 0:
+            return PolygonMasks([], out_h, out_w)
+        resized_masks = []
+        for i in range(len(bboxes)):
+            bbox = bboxes[i, :]
+            x1, y1, x2, y2 = bbox
+            w = np.maximum(x2 - x1, 1)
+            h = np.maximum(y2 - y1, 1)
+            h_scale = out_h / max(h, 0.1)
+            w_scale = out_w / max(w, 0.1)
+            obj = []
+            for p in self.masks[inds[i]]:
+                p = p.copy()
+                p[0::2] = (p[0::2] - bbox[0]) * w_scale
+                p[1::2] = (p[1::2] - bbox[1]) * h_scale
+                obj.append(p)
+            resized_masks.append(obj)
+        return PolygonMasks(resized_masks, *out_shape)
+
+    def to_ndarray(self, device=None):
+        """Rasterise every object at ``(height, width)`` on the device -> bool ``[N,H,W]`` ndarray
+        (reference: pycocotools ``frPyObjects -> merge -> decode`` per object on the host)."""
+        if len(self.masks) == 0:
+            return np.empty((0, self.height, self.width), dtype=np.uint8)
+        if device is None:
+            if not torch.cuda.is_available():
+                raise NotImplementedError('dynamask_b200 has no CPU rasteriser: a CUDA device is required')
+            device = torch.device('cuda', torch.cuda.current_device())
+        n = len(self.masks)
+        # identity crop: box (0, 0, W, H) scaled to (H, W) is exactly scale 1.0 and offset 0.0
+        boxes = np.tile(np.asarray([[0, 0, self.width, self.height]], np.float32), (n, 1))
+        t = self.crop_and_resize_device(boxes, [(int(self.height), int(self.width))], np.arange(n), device)[0]
+        return t.to(torch.bool).cpu().numpy()
+
+    def to_bitmap(self):
+        return BitmapMasks(self.to_ndarray(), self.height, self.width)
+
+    def to_tensor(self, dtype, device):
+        if len(self.masks) == 0:
+            return torch.empty((0, self.height, self.width), dtype=dtype, device=device)
+        return torch.tensor(self.to_ndarray(), dtype=dtype, device=device)

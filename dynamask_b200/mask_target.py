@@ -11,7 +11,7 @@ import torch
 from torch.nn.modules.utils import _pair
 
 from . import ops
-from .mask_structures import BitmapMasks
+from .mask_structures import BitmapMasks, PolygonMasks, pack_polygons
 
 
 def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list, sizes):
@@ -23,10 +23,13 @@ def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_lis
     sizes_hw = [int(v) for s in sizes for v in _pair(s)]
     if not keep:
         return [pos_proposals_list[0].new_zeros((0, ) + tuple(_pair(s))) for s in sizes]
+    if all(isinstance(gt_masks_list[i], PolygonMasks) for i in keep):
+        return _batched_polygon_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list,
+                                        keep, sizes_hw, device)
     for i in keep:
         if not isinstance(gt_masks_list[i], BitmapMasks):
-            raise TypeError('dynamask_b200.mask_target handles BitmapMasks; got %s' %
-                            type(gt_masks_list[i]).__name__)
+            raise TypeError('dynamask_b200.mask_target handles a batch of BitmapMasks or of '
+                            'PolygonMasks; got %s' % type(gt_masks_list[i]).__name__)
     if len(keep) == 1:
         blob, offs, ghw = gt_masks_list[keep[0]].to_device(device)
         roi_img = None
@@ -52,6 +55,25 @@ def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_lis
     boxes = torch.cat([pos_proposals_list[i][:, :4] for i in keep]).float()
     inds = torch.cat([pos_assigned_gt_inds_list[i] for i in keep])
     return ops.mask_target(blob, offs, ghw, boxes, inds, roi_img, True, sizes_hw)
+
+
+def _batched_polygon_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list, keep,
+                             sizes_hw, device):
+    """Polygon ground truth (the shipped COCO config, ``poly2mask=False``): one
+    ``dm_polygon_target`` launch for all images and sizes."""
+    if len(keep) == 1:
+        xy, voff, ooff, meta = gt_masks_list[keep[0]].to_device(device)
+        roi_img = None
+    else:
+        xy, voff, ooff, meta = pack_polygons([gt_masks_list[i].masks for i in keep],
+                                             [(gt_masks_list[i].height, gt_masks_list[i].width) for i in keep],
+                                             device)
+        counts = torch.tensor([pos_proposals_list[i].size(0) for i in keep])
+        roi_img = torch.repeat_interleave(torch.arange(len(keep), dtype=torch.int32), counts).to(
+            device, non_blocking=True)
+    boxes = torch.cat([pos_proposals_list[i][:, :4] for i in keep]).float()
+    inds = torch.cat([pos_assigned_gt_inds_list[i] for i in keep])
+    return ops.polygon_target(xy, voff, ooff, meta, boxes, inds, roi_img, True, sizes_hw)
 
 
 def mask_target_single(pos_proposals, pos_assigned_gt_inds, gt_masks, cfg):

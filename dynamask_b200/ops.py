@@ -14,7 +14,7 @@ from torch import Tensor
 from . import _lib
 
 __all__ = ['assign', 'roi_align_forward', 'roi_align_backward', 'paste_masks', 'mask_target',
-           'multilevel_roi_align']
+           'multilevel_roi_align', 'simple_roi_align_forward', 'simple_roi_align_backward', 'refine_stages_', 'polygon_target']
 
 PASTE_BOOL, PASTE_U8, PASTE_F32 = 0, 1, 2
 
@@ -409,3 +409,148 @@ def rle_from_canvas(canvas: Tensor):
 
     run(1, None, None)
     return _rle_finish(N, H, W, totals, lambda off, tr: run(2, off, tr))
+
+
+# --------------------------------------------------------------------------------------------
+# dm_simple_roi_align_fwd / _bwd  
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op('dynamask::simple_roi_align_forward', mutates_args=(), device_types='cuda')
+def simple_roi_align_forward(feat: Tensor, rois: Tensor, out_h: int, out_w: int,
+                             spatial_scale: float, aligned: bool) -> Tensor:
+    """feat [N,C,H,W] fp32, rois [K,5] -> [K,C,out_h,out_w]: one zero-padded bilinear point per bin."""
+    if feat.dim() != 4:
+        raise ValueError('features must be [N,C,H,W]')
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError('rois must be [K,5]')
+    _f32c(feat, 'features')
+    rois = _f32c(rois, 'rois').contiguous()
+    dev = feat.device
+    K = rois.size(0)
+    out = torch.empty((K, feat.size(1), int(out_h), int(out_w)), dtype=torch.float32, device=dev)
+    if K == 0:
+        return out
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_simple_roi_align_fwd(
+            _ptr(feat), _arr(ctypes.c_int32, list(feat.shape)), _arr(ctypes.c_int64, list(feat.stride())),
+            float(spatial_scale), _ptr(rois), K, int(out_h), int(out_w), _ptr(out),
+            _arr(ctypes.c_int64, list(out.stride())), int(bool(aligned)), _stream(dev))
+    _lib.check(rc, 'dm_simple_roi_align_fwd')
+    return out
+
+
+@simple_roi_align_forward.register_fake
+def _(feat, rois, out_h, out_w, spatial_scale, aligned):
+    return torch.empty((rois.size(0), feat.size(1), out_h, out_w), dtype=torch.float32, device=feat.device)
+
+
+@torch.library.custom_op('dynamask::simple_roi_align_backward', mutates_args=(), device_types='cuda')
+def simple_roi_align_backward(grad_out: Tensor, rois: Tensor, feat_shape: Sequence[int],
+                              spatial_scale: float, aligned: bool) -> Tensor:
+    """Gradient w.r.t. the feature map (zero-initialised here, then reduced into)."""
+    grad_out = _f32c(grad_out, 'grad_out')
+    rois = _f32c(rois, 'rois').contiguous()
+    dev = grad_out.device
+    grad = torch.empty([int(v) for v in feat_shape], dtype=torch.float32, device=dev)
+    K = rois.size(0)
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_simple_roi_align_bwd(
+            _ptr(grad), _arr(ctypes.c_int32, list(grad.shape)), _arr(ctypes.c_int64, list(grad.stride())),
+            float(spatial_scale), _ptr(rois), K, int(grad_out.size(2)), int(grad_out.size(3)),
+            _ptr(grad_out), _arr(ctypes.c_int64, list(grad_out.stride())), int(bool(aligned)), 1,
+            _stream(dev))
+    _lib.check(rc, 'dm_simple_roi_align_bwd')
+    return grad
+
+
+@simple_roi_align_backward.register_fake
+def _(grad_out, rois, feat_shape, spatial_scale, aligned):
+    return torch.empty([int(v) for v in feat_shape], dtype=torch.float32, device=grad_out.device)
+
+
+def _sra_setup_context(ctx, inputs, output):
+    feat, rois, out_h, out_w, spatial_scale, aligned = inputs
+    ctx.save_for_backward(rois)
+    ctx.feat_shape = [int(v) for v in feat.shape]
+    ctx.scale = spatial_scale
+    ctx.aligned = aligned
+
+
+def _sra_backward(ctx, grad_out):
+    (rois,) = ctx.saved_tensors
+    g = simple_roi_align_backward(grad_out, rois, ctx.feat_shape, ctx.scale, ctx.aligned)
+    return g, None, None, None, None, None
+
+
+simple_roi_align_forward.register_autograd(_sra_backward, setup_context=_sra_setup_context)
+
+
+# --------------------------------------------------------------------------------------------
+# dm_refine_stages  (SURVEY.md 8f rank 3)
+# --------------------------------------------------------------------------------------------
+def refine_stages_(stage_preds: Sequence[Tensor]) -> Sequence[Tensor]:
+    """In-place coarse-to-fine refinement of ``[N,1,S_s,S_s]`` (or ``[N,S_s,S_s]``) stage logits;
+    stage 0 is left as is, every later stage is overwritten where the reference overwrites it."""
+    if len(stage_preds) < 2:
+        return stage_preds
+    N = stage_preds[0].size(0)
+    dev = stage_preds[0].device
+    sizes = []
+    for t in stage_preds:
+        if not t.is_cuda:
+            raise NotImplementedError('dynamask::refine_stages has no CPU implementation')
+        _f32c(t, 'stage prediction')
+        if t.dim() == 4 and t.size(1) != 1:
+            raise ValueError('stage predictions must be class-selected: [N,1,S,S]')
+        if t.size(0) != N or not t.is_contiguous():
+            raise ValueError('stage predictions must be contiguous [N,1,S,S] tensors of one batch')
+        sizes += [int(t.size(-2)), int(t.size(-1))]
+    if N == 0:
+        return stage_preds
+    ptrs = _arr(ctypes.c_void_p, [t.data_ptr() for t in stage_preds])
+    outs = _arr(ctypes.c_void_p, [None] + [t.data_ptr() for t in stage_preds[1:]])
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_refine_stages(ptrs, _arr(ctypes.c_int32, sizes), len(stage_preds), N, outs,
+                                          _stream(dev))
+    _lib.check(rc, 'dm_refine_stages')
+    return stage_preds
+
+
+# --------------------------------------------------------------------------------------------
+# dm_polygon_target  (SURVEY.md 8f rank 4 / row A10)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op('dynamask::polygon_target', mutates_args=(), device_types='cuda')
+def polygon_target(poly_xy: Tensor, vert_offsets: Tensor, obj_poly_offsets: Tensor, img_meta: Tensor,
+                   boxes: Tensor, inds: Tensor, roi_img: Optional[Tensor], clip: bool,
+                   sizes_hw: Sequence[int]) -> List[Tensor]:
+    """Polygon ground truth -> one ``[K,h,w]`` float32 {0,1} target tensor per size."""
+    if poly_xy.dtype != torch.float64:
+        raise TypeError('poly_xy must be float64')
+    if vert_offsets.dtype != torch.int64 or obj_poly_offsets.dtype != torch.int32 or img_meta.dtype != torch.int32:
+        raise TypeError('vert_offsets must be int64, obj_poly_offsets and img_meta int32')
+    if roi_img is not None and roi_img.dtype != torch.int32:
+        raise TypeError('roi_img must be int32')
+    dev = boxes.device
+    boxes = _f32c(boxes, 'boxes')[:, :4].contiguous()
+    K = boxes.size(0)
+    inds = inds.to(torch.int64).contiguous()
+    n_sizes = len(sizes_hw) // 2
+    outs = [torch.empty((K, int(sizes_hw[2 * s]), int(sizes_hw[2 * s + 1])), dtype=torch.float32,
+                        device=dev) for s in range(n_sizes)]
+    if K == 0:
+        return outs
+    optrs = _arr(ctypes.c_void_p, [o.data_ptr() for o in outs])
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_polygon_target(_ptr(poly_xy), _ptr(vert_offsets), _ptr(obj_poly_offsets),
+                                           obj_poly_offsets.numel() - 1, _ptr(img_meta),
+                                           img_meta.numel() // 3, _ptr(boxes), _ptr(inds), _ptr(roi_img), K,
+                                           int(bool(clip)), _arr(ctypes.c_int32, [int(v) for v in sizes_hw]),
+                                           n_sizes, optrs, _stream(dev))
+    _lib.check(rc, 'dm_polygon_target')
+    return outs
+
+
+@polygon_target.register_fake
+def _(poly_xy, vert_offsets, obj_poly_offsets, img_meta, boxes, inds, roi_img, clip, sizes_hw):
+    K = boxes.size(0)
+    return [torch.empty((K, sizes_hw[2 * s], sizes_hw[2 * s + 1]), dtype=torch.float32,
+                        device=boxes.device) for s in range(len(sizes_hw) // 2)]

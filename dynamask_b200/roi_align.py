@@ -60,3 +60,36 @@ class RoIAlign(nn.Module):
                 f'spatial_scale={self.spatial_scale}, sampling_ratio={self.sampling_ratio}, '
                 f'pool_mode={self.pool_mode}, aligned={self.aligned}, '
                 f'use_torchvision={self.use_torchvision})')
+
+
+class SimpleRoIAlign(nn.Module):
+    """Drop-in for ``mmcv.ops.SimpleRoIAlign`` as built by ``SFMStage``
+    (``mmdet/models/roi_heads/mask_heads/dynamask_head.py:74``: ``SimpleRoIAlign(output_size=out_size,
+    spatial_scale=1.0/semantic_out_stride)``) and called at ``:104-105`` with
+    ``(semantic_feat [B,C,H,W], rois [K,5])``.
+
+    One bilinear ``grid_sample`` point per output bin (zero padding, ``align_corners = not
+    aligned``) at the bin centre of the RoI; no sampling-grid average and no border clamp.  The
+    reference materialises a ``[K, P*P, 2]`` point grid per image and calls ``F.grid_sample``
+    image by image; here it is one launch of the banded RoIAlign kernels in point mode.  Output
+    rows follow the RoI order (identical to mmcv's per-image concatenation for RoIs sorted by image,
+    which is what ``bbox2roi`` produces).  Differentiable w.r.t. ``features``.
+    """
+
+    def __init__(self, output_size, spatial_scale, aligned=True):
+        super().__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = float(spatial_scale)
+        # kept for signature parity with mmcv (the class carries the flag, never reads it)
+        self.use_torchvision = False
+        self.aligned = aligned
+
+    def forward(self, features, rois):
+        if rois.size(1) != 5:
+            raise AssertionError('RoI must be (idx, x1, y1, x2, y2)!')
+        return ops.simple_roi_align_forward(features, rois, self.output_size[0], self.output_size[1],
+                                            self.spatial_scale, bool(self.aligned))
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(output_size={self.output_size}, '
+                f'spatial_scale={self.spatial_scale})')

@@ -169,6 +169,67 @@ int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int
 int64_t dm_rle_compress_host(const int32_t* transitions, int64_t n, int64_t total_pixels, char* out,
                              int64_t cap);
 
+/*
+ * Next row: SimpleRoIAlign, the per-RoI semantic-feature gather of SFMStage
+ * (mmdet/models/roi_heads/mask_heads/dynamask_head.py:74 construction, :104-105 call; the three
+ * stages sample strides 16/8/4 maps with spatial_scale 1/4, :185-194,228).  Replaces
+ * mmcv.ops.SimpleRoIAlign = generate_grid + rel_roi_point_to_rel_img_point + point_sample
+ * (F.grid_sample, bilinear, zero padding, align_corners = !aligned): one sample per output bin at
+ *   x = x1 + (pw + 0.5) / out_w * (x2 - x1),  pixel = x / W * spatial_scale * W - 0.5   (aligned)
+ * taps outside the map contribute zero (no border clamp, unlike RoIAlign).
+ *   feat        device [N,C,H,W] fp32, feat_shape host [4], feat_strides host [4] (elements)
+ *   rois        device [K,5] (batch_idx, x1, y1, x2, y2) in input-image pixels
+ *   out         device [K,C,out_h,out_w], out_strides host [4]; row k belongs to RoI k
+ * The backward adds into grad_feat (cleared first when zero_init != 0).
+ */
+int dm_simple_roi_align_fwd(const float* feat, const int32_t* feat_shape,
+                            const int64_t* feat_strides, float spatial_scale, const float* rois,
+                            int K, int out_h, int out_w, float* out, const int64_t* out_strides,
+                            int aligned, dm_stream_t stream);
+int dm_simple_roi_align_bwd(float* grad_feat, const int32_t* feat_shape,
+                            const int64_t* feat_strides, float spatial_scale, const float* rois,
+                            int K, int out_h, int out_w, const float* grad_out,
+                            const int64_t* grad_out_strides, int aligned, int zero_init,
+                            dm_stream_t stream);
+
+/*
+ * Next row: inference-time stage-to-stage refinement, fused.  Replaces the
+ * loop of DynaMaskRoIHead.simple_test_mask, mmdet/models/roi_heads/dynamask_roi_head.py:137-149
+ * (sigmoid >= 0.5, generate_block_target(boundary_width=1) of
+ * mmdet/models/losses/cross_entropy_loss.py:123-154, two bilinear align_corners=True
+ * interpolations and a masked overwrite per stage pair).
+ *   stage_ptrs  host [n_stages] device pointers, stage s is [N, h_s, w_s] fp32 logits, dense
+ *   sizes_hw    host [n_stages*2]
+ *   out_ptrs    host [n_stages] device pointers for the refined stages; out_ptrs[s] may alias
+ *               stage_ptrs[s] (the reference refines in place) and may be NULL for every stage but
+ *               the last (stage 0 is never changed)
+ * For s = 0 .. n_stages-2: pixels of stage s+1 whose up-sampled non-boundary mask of (refined)
+ * stage s is >= 0.5 take the up-sampled stage-s logit.  One CTA per instance, one launch.
+ */
+int dm_refine_stages(const float* const* stage_ptrs, const int32_t* sizes_hw, int n_stages, int N,
+                     float* const* out_ptrs, dm_stream_t stream);
+
+/*
+ * Next row: mask targets from POLYGON ground truth, all RoIs and all
+ * sizes in one launch.  Replaces PolygonMasks.crop_and_resize (mmdet/core/mask/structures.py:465-499)
+ * + PolygonMasks.to_ndarray / polygon_to_bitmap (structures.py:541-575: pycocotools frPyObjects ->
+ * merge -> decode) + the clip / float / upload of mask_target_single (mmdet/core/mask/mask_target.py:49-58)
+ * and of DynaMaskHead.get_targets (mmdet/models/roi_heads/mask_heads/dynamask_head.py:248-261).
+ *   poly_xy          device float64, interleaved (x, y) vertices of every polygon of the batch
+ *   vert_offsets     device [P+1] int64: polygon q owns vertices [vert_offsets[q], vert_offsets[q+1])
+ *   obj_poly_offsets device [G+1] int32: object g owns polygons [obj_poly_offsets[g], obj_poly_offsets[g+1])
+ *   img_meta         device [B*3] int32: (first object of the image, H, W) -- H, W bound the clip
+ *   boxes / inds / roi_img / clip / sizes_hw / out_ptrs   as in dm_mask_target
+ * Per RoI: vertex' = (vertex - box corner) * (out / max(box extent, 1)) in float64 with a float32
+ * scale, then pycocotools' rleFrPoly rule (x5 up-sampling, run ends on column centres), union over
+ * the object's polygons.  Integer / float64 arithmetic without contraction: bit-exact.
+ */
+int dm_polygon_target(const double* poly_xy, const int64_t* vert_offsets,
+                      const int32_t* obj_poly_offsets, int G, const int32_t* img_meta, int B,
+                      const float* boxes, const int64_t* inds, const int32_t* roi_img, int K,
+                      int clip, const int32_t* sizes_hw, int n_sizes, float* const* out_ptrs,
+                      dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

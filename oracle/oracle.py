@@ -427,3 +427,207 @@ def rle_decode(rle):
         pos += c
         v ^= 1
     return flat.reshape((h, w), order='F')
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY 8f rank 2  SimpleRoIAlign -- constructed at dynamask_head.py:74, called at :104-105.
+# The class lives in mmcv (mmcv/ops/point_sample.py: generate_grid, rel_roi_point_to_abs_img_point,
+# abs_img_point_to_rel_img_point, point_sample, SimpleRoIAlign), a third-party dependency absent
+# from /root/reference: this restates its published algorithm with the same torch calls
+# (F.affine_grid, F.grid_sample); PARITY UNPINNED at the mmcv boundary, pinned only to torch's own
+# grid_sample.  Output rows follow the input RoI order (mmcv concatenates per image, which is the
+# same thing for RoIs sorted by image as bbox2roi produces).
+# --------------------------------------------------------------------------------------------
+def _generate_grid(num_grid, size):
+    affine = torch.tensor([[[1., 0., 0.], [0., 1., 0.]]])
+    grid = F.affine_grid(affine, torch.Size((1, 1, *size)), align_corners=False)
+    grid = (grid + 1.0) / 2.0                                   # normalize
+    return grid.view(1, -1, 2).expand(num_grid, -1, -1)
+
+
+def _rel_roi_point_to_rel_img_point(rois, rel_roi_points, img_hw, spatial_scale):
+    r = rois[:, 1:] if rois.size(1) == 5 else rois
+    xs = rel_roi_points[:, :, 0] * (r[:, None, 2] - r[:, None, 0])
+    ys = rel_roi_points[:, :, 1] * (r[:, None, 3] - r[:, None, 1])
+    xs = xs + r[:, None, 0]
+    ys = ys + r[:, None, 1]
+    abs_pts = torch.stack([xs, ys], dim=2)
+    h, w = img_hw
+    scale = torch.tensor([w, h], dtype=torch.float).view(1, 1, 2)
+    return abs_pts / scale * spatial_scale
+
+
+def _point_sample(inp, points, align_corners=False):
+    add_dim = points.dim() == 3
+    if add_dim:
+        points = points.unsqueeze(2)
+    out = F.grid_sample(inp, points * 2.0 - 1.0, align_corners=align_corners)
+    return out.squeeze(3) if add_dim else out
+
+
+def simple_roi_align(features, rois, output_size, spatial_scale, aligned=True):
+    """features [B,C,H,W], rois [K,5] -> [K,C,ph,pw] (mmcv SimpleRoIAlign.forward)."""
+    features = torch.as_tensor(features, dtype=torch.float32)
+    rois = torch.as_tensor(rois, dtype=torch.float32)
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    K, C = rois.size(0), features.size(1)
+    out = features.new_zeros((K, C, ph, pw))
+    rel = _generate_grid(K, (ph, pw))
+    for b in range(features.size(0)):
+        inds = rois[:, 0].long() == b
+        if inds.any():
+            feat = features[b:b + 1]
+            pts = _rel_roi_point_to_rel_img_point(rois[inds], rel[inds], feat.shape[2:],
+                                                  spatial_scale).unsqueeze(0)
+            pf = _point_sample(feat, pts, align_corners=not aligned)        # [1,C,k,ph*pw]
+            out[inds] = pf.squeeze(0).transpose(0, 1).reshape(-1, C, ph, pw)
+    return out
+
+
+def simple_roi_align_backward(grad_out, feat_shape, rois, spatial_scale, aligned=True):
+    """Gradient of simple_roi_align w.r.t. the feature map, by torch autograd on the CPU."""
+    f = torch.zeros(tuple(feat_shape), dtype=torch.float32, requires_grad=True)
+    go = torch.as_tensor(grad_out, dtype=torch.float32)
+    out = simple_roi_align(f, rois, tuple(go.shape[2:]), spatial_scale, aligned)
+    out.backward(go)
+    return f.grad
+
+
+def simple_roi_align_f64(features, rois, output_size, spatial_scale, aligned=True):
+    """Closed form of simple_roi_align in float64 (no normalised-coordinate round trip): the
+    yardstick for how much of a difference is fp32 coordinate noise."""
+    f = torch.as_tensor(features).double().numpy()
+    r = torch.as_tensor(rois).double().numpy()
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    B, C, H, W = f.shape
+    out = np.zeros((r.shape[0], C, ph, pw))
+    for k in range(r.shape[0]):
+        b = int(r[k, 0])
+        if not 0 <= b < B:
+            continue
+        x = (r[k, 1] + (np.arange(pw) + .5) / pw * (r[k, 3] - r[k, 1])) * spatial_scale
+        y = (r[k, 2] + (np.arange(ph) + .5) / ph * (r[k, 4] - r[k, 2])) * spatial_scale
+        if aligned:
+            x, y = x - .5, y - .5
+        else:
+            x, y = x / W * (W - 1), y / H * (H - 1)
+        x0, y0 = np.floor(x).astype(np.int64), np.floor(y).astype(np.int64)
+        lx, ly = x - x0, y - y0
+        acc = np.zeros((C, ph, pw))
+        for yy, wy in ((y0, 1 - ly), (y0 + 1, ly)):
+            for xx, wx in ((x0, 1 - lx), (x0 + 1, lx)):
+                oky = (yy >= 0) & (yy < H)
+                okx = (xx >= 0) & (xx < W)
+                v = f[b][:, np.clip(yy, 0, H - 1)][:, :, np.clip(xx, 0, W - 1)]
+                acc += v * (wy * oky)[None, :, None] * (wx * okx)[None, None, :]
+        out[k] = acc
+    return torch.from_numpy(out)
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY 8f rank 3  stage-to-stage refinement at inference --
+# mmdet/models/roi_heads/dynamask_roi_head.py:136-148 with generate_block_target,
+# mmdet/models/losses/cross_entropy_loss.py:123-154.  Pinned by tests/golden/refine.npz (the
+# reference's own source lines executed through ref_shim.load_refine).
+# --------------------------------------------------------------------------------------------
+def generate_block_target(mask_target, boundary_width=3):
+    """0 = background, 1 = boundary band, 2 = interior foreground (two box-Laplacian convolutions)."""
+    mask_target = torch.as_tensor(mask_target).float()
+    k = 2 * boundary_width + 1
+    lap = -torch.ones(1, 1, k, k)
+    lap[0, 0, boundary_width, boundary_width] = k ** 2 - 1
+    pad = F.pad(mask_target.unsqueeze(1), (boundary_width,) * 4, 'constant', 0)
+    pos = F.conv2d(pad, lap, padding=0).clamp(min=0) / float(k ** 2)
+    pos = (pos > 0.1).float().squeeze(1)
+    neg = F.conv2d(1 - pad, lap, padding=0).clamp(min=0) / float(k ** 2)
+    neg = (neg > 0.1).float().squeeze(1)
+    block = torch.zeros_like(mask_target).long()
+    block[(pos + neg) > 0] = 1
+    block[(mask_target - pos) > 0] = 2
+    return block
+
+
+def non_boundary_3x3(m):
+    """Closed form of ``generate_block_target(m, 1) != 1`` used by the kernel: a foreground pixel is
+    boundary when its zero-padded 3x3 window holds a 0, a background pixel when it holds a 1."""
+    m = np.asarray(m).astype(np.int32)
+    n, h, w = m.shape
+    pad = np.zeros((n, h + 2, w + 2), np.int32)
+    pad[:, 1:-1, 1:-1] = m
+    ones = sum(pad[:, dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3))
+    boundary = np.where(m == 1, ones < 9, ones > 0)
+    return ~boundary
+
+
+def refine_stage_preds(stage_preds):
+    """``stage_preds``: list of [N,1,S,S] logits (coarse to fine, e.g. 28/56/112).  Returns the
+    refined copies (stage 0 unchanged); the last one is what get_seg_masks receives."""
+    preds = [torch.as_tensor(p, dtype=torch.float32).clone() for p in stage_preds]
+    for idx in range(len(preds) - 1):
+        inst = preds[idx].squeeze(1).sigmoid() >= 0.5
+        nb = (generate_block_target(inst, boundary_width=1) != 1).unsqueeze(1)
+        nb = F.interpolate(nb.float(), preds[idx + 1].shape[-2:], mode='bilinear', align_corners=True) >= 0.5
+        pre = F.interpolate(preds[idx], preds[idx + 1].shape[-2:], mode='bilinear', align_corners=True)
+        preds[idx + 1][nb] = pre[nb]
+    return preds
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY row A10 / 8f rank 4  polygon ground truth -> mask targets
+#   PolygonMasks.crop_and_resize   mmdet/core/mask/structures.py:465-499
+#   PolygonMasks.to_ndarray / polygon_to_bitmap   structures.py:541-575 (pycocotools, absent:
+#   restated in dm_oracle.c from common/maskApi.c -- PARITY UNPINNED against the real library)
+# --------------------------------------------------------------------------------------------
+def polygon_to_bitmap(polygons, height, width):
+    """frPyObjects -> merge -> decode of one object's polygons: bool [height,width]."""
+    polys = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1) for p in polygons]
+    polys = [p[:2 * (p.size // 2)] for p in polys]
+    voff = np.zeros(len(polys) + 1, np.int64)
+    np.cumsum([p.size // 2 for p in polys], out=voff[1:])
+    xy = np.concatenate(polys) if polys else np.zeros(0, np.float64)
+    out = np.zeros((int(height), int(width)), np.uint8)
+    f = lib().orc_polygons_to_bitmap
+    f.restype = ctypes.c_int
+    rc = f(xy.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _p(voff, _i64p), ctypes.c_long(len(polys)),
+           ctypes.c_long(int(height)), ctypes.c_long(int(width)), _p(out, _u8p))
+    assert rc == 0
+    return out.astype(bool)
+
+
+def polygon_crop_and_resize(masks, bboxes, out_shape, inds):
+    """The host arithmetic of PolygonMasks.crop_and_resize: list (per box) of lists of polygons."""
+    out_h, out_w = out_shape
+    bboxes = np.asarray(bboxes, dtype=np.float32)
+    res = []
+    for i in range(len(bboxes)):
+        bbox = bboxes[i, :]
+        x1, y1, x2, y2 = bbox
+        w = np.maximum(x2 - x1, 1)
+        h = np.maximum(y2 - y1, 1)
+        h_scale = out_h / max(h, 0.1)
+        w_scale = out_w / max(w, 0.1)
+        obj = []
+        for p in masks[int(inds[i])]:
+            p = np.array(p, dtype=np.float64)
+            p[0::2] -= bbox[0]
+            p[1::2] -= bbox[1]
+            p[0::2] *= w_scale
+            p[1::2] *= h_scale
+            obj.append(p)
+        res.append(obj)
+    return res
+
+
+def polygon_mask_target_single(pos_proposals, pos_assigned_gt_inds, masks, height, width, mask_size):
+    """mask_target_single (mask_target.py:30-62) for PolygonMasks: float32 [K,S,S] in {0,1}."""
+    S = (mask_size, mask_size) if isinstance(mask_size, int) else tuple(mask_size)
+    prop = _np32(pos_proposals)[:, :4].copy()
+    K = prop.shape[0]
+    if K == 0:
+        return torch.zeros((0, ) + S)
+    prop[:, [0, 2]] = np.clip(prop[:, [0, 2]], 0, width)
+    prop[:, [1, 3]] = np.clip(prop[:, [1, 3]], 0, height)
+    inds = np.asarray(pos_assigned_gt_inds).astype(np.int64)
+    resized = polygon_crop_and_resize(masks, prop, S, inds)
+    out = np.stack([polygon_to_bitmap(obj, S[0], S[1]) for obj in resized])
+    return torch.from_numpy(out).float()

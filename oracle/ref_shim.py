@@ -150,3 +150,50 @@ def load():
     )
     _loaded = ns
     return ns
+
+
+def load_refine():
+    """The inference-time stage refinement of the reference, runnable on plain tensors:
+    returns ``(generate_block_target, refine)`` where ``refine(stage_instance_preds)`` executes
+    the *source lines* of the loop in ``DynaMaskRoIHead.simple_test_mask``
+    (``mmdet/models/roi_heads/dynamask_roi_head.py:136-148``; the method itself needs a whole
+    detector, the loop only needs the list of stage logits) and returns the refined last stage."""
+    import textwrap
+    import torch.nn.functional as F
+    load()
+    _pkg_stub('mmdet.models.losses', 'mmdet/models/losses')
+    sys.modules['mmdet.models.builder'].LOSSES = _Registry('loss')
+    cel = importlib.import_module('mmdet.models.losses.cross_entropy_loss')
+    path = os.path.join(REF_ROOT, 'mmdet/models/roi_heads/dynamask_roi_head.py')
+    lines = open(path).read().split('\n')
+    start = next(i for i, l in enumerate(lines) if '# refine instance masks from stage 1' in l)
+    end = next(i for i in range(start, len(lines)) if 'instance_pred = stage_instance_preds[-1]' in lines[i])
+    src = textwrap.dedent('\n'.join(lines[start:end + 1]))
+    code = compile(src, path, 'exec')
+
+    def refine(stage_instance_preds):
+        env = dict(mask_results={'stage_instance_preds': list(stage_instance_preds)}, F=F,
+                   generate_block_target=cel.generate_block_target, len=len, range=range)
+        exec(code, env)
+        return env['instance_pred'], env['stage_instance_preds']
+
+    return cel.generate_block_target, refine
+
+
+def load_polygon():
+    """The reference's own ``PolygonMasks`` (``mmdet/core/mask/structures.py:314-558``) and
+    ``mask_target_single``, with the absent pycocotools supplied by the oracle's restatement of
+    rleFrPoly / merge / decode (``oracle.polygon_to_bitmap``): everything around the rasteriser --
+    clip, crop, scale, dtype promotions -- is then the reference's unmodified Python."""
+    import numpy as np
+    from oracle import oracle as O
+    ns = load()
+    if not hasattr(np, 'bool'):
+        np.bool = bool          # structures.py:574 predates numpy 1.24
+    mu = sys.modules['pycocotools.mask']
+    # an "RLE" here is just the polygon list + size; merge concatenates, decode rasterises
+    mu.frPyObjects = lambda polys, h, w: [dict(polys=[p], size=(h, w)) for p in polys]
+    mu.merge = lambda rles: dict(polys=[p for r in rles for p in r['polys']], size=rles[0]['size'])
+    mu.decode = lambda rle: O.polygon_to_bitmap(rle['polys'], rle['size'][0], rle['size'][1]).astype(np.uint8)
+    structures = sys.modules['mmdet.core.mask.structures']
+    return structures.PolygonMasks, ns.mask_target_single

@@ -90,3 +90,36 @@ def jitter_boxes_from_masks(masks, k, rng, jitter=15.0):
         bx1, by1 = max(x1 + d[2], bx0 + 2), max(y1 + d[3], by0 + 2)
         boxes[j] = (bx0, by0, bx1, by1)
     return boxes, inds.astype(np.int64)
+
+
+def make_polygons(g, img_h, img_w, rng, max_parts=3):
+    """COCO-shaped polygon ground truth: per object 1..max_parts star-shaped polygons with 5..40
+    float64 vertices (two decimals, like the dataset's json), some reaching past the image."""
+    objs = []
+    for _ in range(g):
+        parts = []
+        for _ in range(int(rng.integers(1, max_parts + 1))):
+            cx, cy = rng.uniform(0, img_w), rng.uniform(0, img_h)
+            rad = rng.uniform(4, min(img_h, img_w) / 3)
+            n = int(rng.integers(5, 41))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+            r = rad * rng.uniform(0.5, 1.0, n)
+            p = np.empty(2 * n, np.float64)
+            p[0::2] = np.round(cx + r * np.cos(ang), 2)
+            p[1::2] = np.round(cy + r * np.sin(ang), 2)
+            parts.append(p)
+        objs.append(parts)
+    return objs
+
+
+def jitter_boxes_from_polygons(objs, k, rng, jitter=15.0):
+    """k positive proposals: bounding boxes of random objects' polygons jittered by +-jitter px."""
+    inds = rng.integers(0, len(objs), size=k)
+    boxes = np.zeros((k, 4), np.float32)
+    for j, gi in enumerate(inds):
+        xs = np.concatenate([p[0::2] for p in objs[gi]])
+        ys = np.concatenate([p[1::2] for p in objs[gi]])
+        d = rng.uniform(-jitter, jitter, size=4)
+        bx0, by0 = xs.min() + d[0], ys.min() + d[1]
+        boxes[j] = (bx0, by0, max(xs.max() + d[2], bx0 + 2), max(ys.max() + d[3], by0 + 2))
+    return boxes, inds.astype(np.int64)

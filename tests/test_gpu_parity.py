@@ -669,3 +669,272 @@ def test_full_size_paste_and_targets_properties():
         assert float(t.min()) == 1.0
     for t in dm().multi_size_mask_targets([pb], [pi], [zeros]):
         assert float(t.max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# next row: SimpleRoIAlign -- dynamask_head.py:74,104-105
+# ------------------------------------------------------------------------------------------
+def _sra_atol(feat):
+    """The reference samples through grid_sample: pixel coordinates are rebuilt from NORMALISED
+    fp32 coordinates, so they carry ~W * 2^-23 px of rounding noise whose sign depends on ATen
+    implementation details (the CPU and CUDA linspace / unnormalise code paths already differ in
+    the last ulp).  On N(0,1) features (|gradient| up to ~4 per px) that is 1e-6 * W in the output;
+    the float64 closed form is checked as well."""
+    return max(FWD_ATOL, 1e-6 * max(feat.shape[2:]))
+
+
+def _sra_inputs(seed, B=2, C=8, H=50, W=84, K=40, img=(800, 1344)):
+    g = gen(seed)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = synth.make_rois(B, K // B, img[0], img[1], g)
+    return feat, rois, g
+
+
+@pytest.mark.parametrize('out_size,scale', [(14, 1.0 / 16), (28, 1.0 / 16), (56, 1.0 / 16), (14, 0.25), ((5, 9), 1.0 / 8)])
+def test_simple_roi_align_forward_matches_oracle(out_size, scale):
+    # scale 1/4 on a stride-16 map is the reference's own quirk (every SFMStage is built with
+    # semantic_out_stride[-1], dynamask_head.py:192): most points then fall outside the map
+    feat, rois, _ = _sra_inputs(71)
+    layer = dm().SimpleRoIAlign(out_size, scale)
+    out = layer(feat.cuda(), rois.cuda())
+    ref = O.simple_roi_align(feat, rois, out_size, scale)
+    assert_close(out, ref, FWD_RTOL, _sra_atol(feat), 'SimpleRoIAlign fwd %s' % (out_size,))
+    # and the kernel is no further from the float64 closed form than the reference's own fp32 path
+    exact = O.simple_roi_align_f64(feat, rois, out_size, scale)
+    err_k = float((out.cpu().double() - exact).abs().max())
+    err_r = float((ref.double() - exact).abs().max())
+    assert err_k <= max(2.0 * err_r, 1e-5), (err_k, err_r)
+
+
+def test_simple_roi_align_edges_and_align_corners():
+    g = gen(72)
+    feat = torch.randn(2, 4, 23, 31, generator=g)
+    rois = torch.tensor([[0, -40., -30., 20., 25.],      # partly left / above the map
+                         [1, 100., 60., 400., 300.],     # runs off the right / bottom edge
+                         [0, 500., 500., 600., 600.],    # entirely outside -> zeros
+                         [1, 10., 10., 10., 10.],        # zero extent: every point on one pixel
+                         [0, 30., 20., 12., 8.],         # negative extent
+                         [1, 0., 0., 124., 92.]])        # the whole map
+    for aligned in (True, False):
+        out = dm().SimpleRoIAlign(7, 0.25, aligned=aligned)(feat.cuda(), rois.cuda())
+        ref = O.simple_roi_align(feat, rois, 7, 0.25, aligned=aligned)
+        assert_close(out, ref, FWD_RTOL, _sra_atol(feat), 'SimpleRoIAlign edges aligned=%s' % aligned)
+        assert float(out[2].abs().max()) == 0.0
+    assert dm().SimpleRoIAlign(7, 0.25)(feat.cuda(), rois[:0].cuda()).shape == (0, 4, 7, 7)
+    fc = feat.cuda().requires_grad_()
+    out = dm().SimpleRoIAlign(7, 0.25)(fc, rois.cuda())
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go.cuda())
+    assert_close(fc.grad, O.simple_roi_align_backward(go, feat.shape, rois, 0.25), BWD_RTOL, BWD_ATOL,
+                 'SimpleRoIAlign edges grad')
+
+
+@pytest.mark.parametrize('out_size', [14, 56])
+def test_simple_roi_align_backward_matches_oracle(out_size):
+    feat, rois, g = _sra_inputs(73, C=4, K=24)
+    fc = feat.cuda().requires_grad_()
+    out = dm().SimpleRoIAlign(out_size, 1.0 / 16)(fc, rois.cuda())
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go.cuda())
+    ref = O.simple_roi_align_backward(go, feat.shape, rois, 1.0 / 16)
+    assert_close(fc.grad, ref, BWD_RTOL, BWD_ATOL, 'SimpleRoIAlign grad')
+
+
+def test_simple_roi_align_full_size_adjoint():
+    # SFMStage sizes: 100 RoIs x 256 ch at 14 / 28 / 56 from the stride 16 / 8 / 4 maps of 800x1344
+    g = gen(74)
+    rois = synth.make_rois(1, 100, 800, 1344, g).cuda()
+    for P, s in ((14, 16), (28, 8), (56, 4)):
+        H, W = 800 // s, 1344 // s
+        f = torch.randn(1, 256, H, W, generator=g).cuda().requires_grad_()
+        out = dm().SimpleRoIAlign(P, 1.0 / s)(f, rois)
+        go = torch.randn(out.shape, generator=g).cuda()
+        out.backward(go)
+        lhs = float((out.double() * go.double()).sum())
+        rhs = float((f.grad.double() * f.detach().double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-2, (P, lhs, rhs)
+        const = dm().SimpleRoIAlign(P, 1.0 / s)(torch.full_like(f, 3.0), rois)
+        inside = (rois[:, 1] >= 1) & (rois[:, 2] >= 1) & (rois[:, 3] <= 1343) & (rois[:, 4] <= 799)
+        assert_close(const[inside], torch.full_like(const[inside], 3.0), 1e-5, 1e-5, 'constant map')
+
+
+# ------------------------------------------------------------------------------------------
+# next row (SURVEY 8f rank 3): fused stage-to-stage refinement -- dynamask_roi_head.py:136-148
+# ------------------------------------------------------------------------------------------
+def _stage_logits(n, g, sizes=(28, 56, 112), noise=1.5):
+    cx = torch.rand(n, generator=g) * 0.6 - 0.3
+    cy = torch.rand(n, generator=g) * 0.6 - 0.3
+    rr = torch.rand(n, generator=g) * 0.5 + 0.3
+    out = []
+    for s in sizes:
+        lin = (torch.arange(s, dtype=torch.float32) + 0.5) / s * 2 - 1
+        d2 = (lin[None, None, :] - cx[:, None, None]) ** 2 + (lin[None, :, None] - cy[:, None, None]) ** 2
+        blob = 6.0 * (1.0 - d2 / (rr[:, None, None] ** 2))
+        out.append((blob + noise * torch.randn(n, s, s, generator=g))[:, None].contiguous())
+    return out
+
+
+def _assert_refined(got, ref, what):
+    """Refined logits: identical up to FMA-free rounding wherever the overwrite decision agrees;
+    a decision can only differ where the up-sampled mask is within rounding of 0.5."""
+    got, ref = got.cpu(), ref.cpu()
+    bad = (got - ref).abs() > 1e-5 + 1e-5 * ref.abs()
+    assert float(bad.float().mean()) <= 1e-4, '%s: %d / %d pixels differ' % (what, int(bad.sum()), bad.numel())
+    assert float(((got >= 0) != (ref >= 0)).float().mean()) <= 1e-4
+
+
+def test_golden_refine_gpu():
+    gd = np.load(os.path.join(GOLD, 'refine.npz'))
+    preds = [torch.from_numpy(gd['in_%d' % i]).cuda() for i in (1, 2, 3)]
+    keep0 = preds[0].clone()
+    final = dm().refine_stage_instance_preds(preds)
+    assert final.data_ptr() == preds[2].data_ptr()          # in place, like the reference
+    assert torch.equal(preds[0], keep0)
+    _assert_refined(preds[1], torch.from_numpy(gd['out_56']), 'golden 56')
+    _assert_refined(final, torch.from_numpy(gd['out_112']), 'golden 112')
+
+
+@pytest.mark.parametrize('n,sizes', [(100, (28, 56, 112)), (7, (14, 28, 56, 112)), (3, (28, 56)), (5, (10, 25, 33))])
+def test_refine_stages_matches_oracle(n, sizes):
+    g = gen(81 + n)
+    preds = _stage_logits(n, g, sizes)
+    ref = O.refine_stage_preds(preds)
+    dev = [p.cuda() for p in preds]
+    final = dm().refine_stage_instance_preds(dev)
+    for s in range(1, len(sizes)):
+        _assert_refined(dev[s], ref[s], 'stage %d' % sizes[s])
+    assert final is dev[-1]
+    # the refinement must actually do something on these inputs
+    assert float((ref[-1] != preds[-1]).float().mean()) > 0.3
+
+
+def test_refine_then_paste_agrees_with_reference_chain():
+    """simple_test_mask tail: refine -> get_seg_masks, against the oracle chain."""
+    g = gen(91)
+    preds = _stage_logits(20, g)
+    boxes = synth.make_boxes(20, 300, 400, g, s_hi=250.0)
+    det = torch.cat([boxes, torch.ones(20, 1)], 1)
+    labels = torch.zeros(20, dtype=torch.long)
+
+    class Cfg:
+        mask_thr_binary = 0.5
+    ref_final = O.refine_stage_preds(preds)[-1]
+    ref = O.get_seg_masks(ref_final, det, labels, 0.5, (300, 400, 3), 1.0, False)
+    final = dm().refine_stage_instance_preds([p.cuda() for p in preds])
+    out = dm().get_seg_masks(final, det.cuda(), labels.cuda(), Cfg, (300, 400, 3), 1.0, False)
+    agree = sum(int((a == b).sum()) for a, b in zip(out, ref)) / (20 * 300 * 400)
+    assert agree >= 0.9999, agree
+
+
+# ------------------------------------------------------------------------------------------
+# next row (SURVEY row A10 / 8f rank 4): mask targets from polygon ground truth
+# ------------------------------------------------------------------------------------------
+def _golden_polygons():
+    gd = np.load(os.path.join(GOLD, 'polygon.npz'))
+    xy, voff, ooff = gd['xy'], gd['voff'], gd['ooff']
+    objs = [[xy[2 * voff[q]:2 * voff[q + 1]].copy() for q in range(ooff[g], ooff[g + 1])]
+            for g in range(len(ooff) - 1)]
+    return gd, objs
+
+
+def test_golden_polygon_targets_gpu():
+    gd, objs = _golden_polygons()
+    H, W = [int(v) for v in gd['hw']]
+    pm = dm().PolygonMasks(objs, H, W)
+    t = dm().multi_size_mask_targets([torch.from_numpy(gd['boxes']).cuda()],
+                                     [torch.from_numpy(gd['inds']).cuda()], [pm])
+    for i, s in enumerate((14, 28, 56, 112)):
+        assert torch.equal(t[i].cpu(), torch.from_numpy(gd['target_%d' % s])), s
+    assert np.array_equal(pm.to_ndarray(), gd['full'].astype(bool))
+
+    class C:
+        mask_size = 28
+    one = dm().mask_target_single(torch.from_numpy(gd['boxes']).cuda(), torch.from_numpy(gd['inds']).cuda(), pm, C)
+    assert torch.equal(one.cpu(), torch.from_numpy(gd['target_28']))
+    # reference call chain: crop_and_resize(...).to_ndarray()
+    boxes = gd['boxes'].copy()
+    boxes[:, [0, 2]] = np.clip(boxes[:, [0, 2]], 0, W)
+    boxes[:, [1, 3]] = np.clip(boxes[:, [1, 3]], 0, H)
+    arr = pm.crop_and_resize(boxes, (28, 28), gd['inds'], device='cuda').to_ndarray()
+    assert np.array_equal(arr, gd['target_28'].astype(bool))
+
+
+def test_polygon_targets_bit_exact_batch():
+    rng = np.random.default_rng(95)
+    H, W = 200, 304
+    props, inds, pms, refs = [], [], [], [[] for _ in range(4)]
+    for b in range(3):
+        objs = synth.make_polygons(int(rng.integers(1, 9)), H, W, rng)
+        pb, pi = synth.jitter_boxes_from_polygons(objs, 0 if b == 1 else 24, rng)
+        if b == 2:
+            pb[0] = (-50, -50, 400, 300)       # clipped to the canvas
+            pb[1] = (100, 100, 100.2, 100.1)   # tiny box: huge scale, long off-window edges
+        props.append(torch.from_numpy(pb).cuda())
+        inds.append(torch.from_numpy(pi).cuda())
+        pms.append(dm().PolygonMasks(objs, H, W))
+        for i, s in enumerate((14, 28, 56, 112)):
+            refs[i].append(O.polygon_mask_target_single(pb, pi, objs, H, W, s))
+    t = dm().multi_size_mask_targets(props, inds, pms)
+    for i in range(4):
+        assert torch.equal(t[i].cpu(), torch.cat(refs[i])), i
+    frac = float(t[3].mean())
+    assert 0.1 < frac < 0.9, frac
+
+
+def test_polygon_and_bitmap_targets_agree_on_rectangles():
+    """Cross-check of the two ground-truth paths on shapes where both are exact."""
+    objs = [[np.array([32., 24, 96, 24, 96, 72, 32, 72])]]
+    bm = np.zeros((1, 96, 128), np.uint8)
+    bm[0, 24:72, 32:96] = 1
+    boxes = torch.tensor([[0., 0, 128, 96], [32, 24, 96, 72]]).cuda()
+    inds = torch.zeros(2, dtype=torch.long).cuda()
+    a = dm().multi_size_mask_targets([boxes], [inds], [dm().PolygonMasks(objs, 96, 128)], (16, 32))
+    b = dm().multi_size_mask_targets([boxes], [inds], [dm().BitmapMasks(bm, 96, 128)], (16, 32))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_polygon_masks_reference_known_answers_gpu():
+    """The reference's own PolygonMasks tests (tests/test_masks.py:329-355, :358-410, :447-470):
+    bitmaps the real pycocotools produced, reproduced by the device rasteriser."""
+    PM = dm().PolygonMasks
+    truth1 = np.array(
+        [[0, 0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+         [0, 0, 1, 1, 1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 1, 1, 1, 0, 0, 0],
+         [0, 0, 1, 1, 1, 1, 1, 0, 0, 0], [0, 0, 1, 1, 1, 1, 1, 1, 0, 0],
+         [0, 0, 0, 1, 1, 1, 1, 0, 0, 0], [0, 0, 0, 0, 1, 0, 0, 0, 0, 0],
+         [0, 0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 0, 0, 0]], np.uint8)
+    truth2 = np.array(
+        [[0, 1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 1, 1, 0, 0],
+         [0, 0, 1, 1, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0]], np.uint8)
+    # rescale / resize with 1 instance 1 part
+    raw_masks1 = [[np.array([1, 1, 3, 1, 4, 3, 2, 4, 1, 3], dtype=np.float64)]]
+    rescaled = PM(raw_masks1, 5, 5).rescale((12, 10))
+    assert (rescaled.height, rescaled.width) == (10, 10)
+    assert (rescaled.to_ndarray() == truth1).all()
+    resized1 = PM(raw_masks1, 5, 5).resize((10, 10))
+    assert resized1.to_ndarray().shape == (1, 10, 10)
+    assert (resized1.to_ndarray() == truth1).all()
+    # 1 instance 2 parts
+    raw_masks2 = [[np.array([0., 0., 1., 0., 1., 1.]), np.array([1., 1., 2., 1., 2., 2., 1., 2.])]]
+    resized2 = PM(raw_masks2, 3, 3).resize((6, 6))
+    assert (resized2.to_ndarray() == truth2).all()
+    # 2 instances
+    resized3 = PM([raw_masks1[0], raw_masks2[0]], 5, 5).resize((10, 10))
+    truth3 = np.stack([truth1, np.pad(truth2, ((0, 4), (0, 4)), 'constant')])
+    assert (resized3.to_ndarray() == truth3).all()
+    # empty
+    assert PM([], 28, 28).resize((56, 72)).to_ndarray().shape == (0, 56, 72)
+    # crop
+    cropped = PM([[np.array([1., 3., 5., 1., 5., 6., 1, 6])]], 7, 7).crop(np.array([0, 0, 3, 4]))
+    assert (cropped.height, cropped.width) == (4, 3)
+    assert (cropped.to_ndarray() == np.array([[0, 0, 0], [0, 0, 0], [0, 0, 1], [0, 1, 1]])).all()
+    # flip involution (test_masks.py:413-444)
+    rng = np.random.default_rng(4)
+    pm = PM(synth.make_polygons(3, 28, 28, rng), 28, 28)
+    for d in ('horizontal', 'vertical'):
+        assert (pm.to_ndarray() == pm.flip(d).flip(d).to_ndarray()).all()
+    # crop_and_resize: shape / len contract (test_masks.py:506-528)
+    out = pm.crop_and_resize(np.array([[2., 3, 20, 25], [0, 0, 28, 28]], np.float32), (56, 72), [0, 2])
+    assert len(out) == 2 and (out.height, out.width) == (56, 72)
+    assert out.to_ndarray().shape == (2, 56, 72)

@@ -266,3 +266,44 @@ def test_rle_ops_refuse_cpu_tensors():
         ops.rle_from_canvas(torch.zeros(1, 4, 4, dtype=torch.bool))
     with pytest.raises(NotImplementedError):
         ops.paste_rle(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4), None, 8, 8, [0, 0, 8, 8], True, 0.5)
+
+
+def test_polygon_masks_container_and_transforms():
+    """Host side of PolygonMasks (reference tests/test_masks.py:300-330, :413-470 minus the
+    rasterisation, which needs the device)."""
+    import dynamask_b200 as dm
+    PM = dm.PolygonMasks
+    with pytest.raises(AssertionError):
+        PM(np.zeros((3, 28, 28)), 28, 28)            # not a list
+    raw = [[np.array([1., 1, 3, 1, 4, 3, 2, 4, 1, 3])], [np.array([0., 0, 1, 0, 1, 1]), np.array([1., 1, 2, 1, 2, 2, 1, 2])]]
+    pm = PM(raw, 5, 5)
+    assert len(pm) == 2 and repr(pm) == 'PolygonMasks(num_masks=2, height=5, width=5)'
+    assert len(pm[0]) == 1 and len(pm[[1, 0]]) == 2 and len(pm[np.array([1])]) == 1
+    rs = pm.resize((10, 20))
+    assert (rs.height, rs.width) == (10, 20)
+    assert np.allclose(rs.masks[0][0][0::2], raw[0][0][0::2] * 4) and np.allclose(rs.masks[0][0][1::2], raw[0][0][1::2] * 2)
+    assert np.allclose(pm.flip('horizontal').masks[0][0][0::2], 5 - raw[0][0][0::2])
+    assert np.allclose(pm.flip('vertical').flip('vertical').masks[1][1], raw[1][1])
+    cr = pm.crop(np.array([1, 1, 4, 3]))
+    assert (cr.height, cr.width) == (2, 3) and np.allclose(cr.masks[0][0][:2], [0, 0])
+    assert pm.pad((8, 8)).height == 8
+    assert np.allclose(pm.areas, [6.5, 1.5])
+    car = pm.crop_and_resize(np.array([[1., 1, 3, 3]], np.float32), (4, 4), [0])
+    assert np.allclose(car.masks[0][0][:4], [0, 0, 4, 0])
+    assert len(PM([], 5, 5).crop_and_resize(np.zeros((0, 4), np.float32), (4, 4), [])) == 0
+    assert PM([], 5, 5).to_ndarray().shape == (0, 5, 5)
+    if not torch.cuda.is_available():
+        with pytest.raises(NotImplementedError):
+            pm.to_ndarray()
+        with pytest.raises(NotImplementedError):
+            pm.crop_and_resize_device(np.zeros((1, 4), np.float32), [(4, 4)], np.zeros(1, np.int64), 'cpu')
+
+
+def test_next_row_ops_refuse_cpu_tensors():
+    import dynamask_b200 as dm
+    with pytest.raises(NotImplementedError):
+        dm.SimpleRoIAlign(7, 0.25)(torch.zeros(1, 2, 8, 8), torch.zeros(1, 5))
+    with pytest.raises(NotImplementedError):
+        dm.refine_stage_instance_preds([torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 8, 8)])
+    layer = dm.SimpleRoIAlign(14, 1.0 / 4)
+    assert layer.output_size == (14, 14) and layer.spatial_scale == 0.25 and layer.aligned

@@ -150,3 +150,133 @@ def test_oracle_matches_live_reference():
         mask_size = 28
     ref = ns.mask_target([torch.from_numpy(pb)], [torch.from_numpy(pi)], [ns.BitmapMasks(masks, 80, 120)], C)
     assert torch.equal(ref, O.mask_target([pb], [pi], [masks], 28))
+
+
+def test_simple_roi_align_oracle_matches_closed_form():
+    """The mmcv restatement (affine_grid + grid_sample) against the closed form the header states:
+    one bilinear point per bin at (x1 + (pw+.5)/P*(x2-x1)) * scale - .5 with zero padding."""
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(2, 3, 19, 27, generator=g)
+    rois = torch.tensor([[0, 4., 6., 60., 50.], [1, -10., -5., 200., 100.], [0, 10., 10., 11., 11.],
+                         [1, 300., 300., 400., 400.]])
+    P, scale = 6, 0.25
+    out = O.simple_roi_align(feat, rois, P, scale).numpy()
+    H, W = feat.shape[2:]
+    f = feat.numpy().astype(np.float64)
+    for k in range(rois.size(0)):
+        b, x1, y1, x2, y2 = [float(v) for v in rois[k]]
+        for ph in range(P):
+            for pw in range(P):
+                x = (x1 + (pw + .5) / P * (x2 - x1)) * scale - .5
+                y = (y1 + (ph + .5) / P * (y2 - y1)) * scale - .5
+                x0, y0 = int(np.floor(x)), int(np.floor(y))
+                v = np.zeros(3)
+                for yy, wy in ((y0, 1 - (y - y0)), (y0 + 1, y - y0)):
+                    for xx, wx in ((x0, 1 - (x - x0)), (x0 + 1, x - x0)):
+                        if 0 <= yy < H and 0 <= xx < W:
+                            v += wy * wx * f[int(b), :, yy, xx]
+                assert np.allclose(out[k, :, ph, pw], v, rtol=1e-4, atol=1e-4)
+    assert np.all(out[3] == 0)
+    grad = O.simple_roi_align_backward(torch.ones(4, 3, P, P), feat.shape, rois, scale)
+    # every in-map point spreads total weight <= 1 per channel
+    assert float(grad.sum()) <= 4 * 3 * P * P + 1e-3
+
+
+def test_golden_refine_stages_bit_exact():
+    """Oracle restatement of the inference refinement loop against the reference's own source
+    lines (tests/golden/refine.npz, made by oracle/gen_golden_next.py)."""
+    gd = np.load(os.path.join(GOLD, 'refine.npz'))
+    ins = [torch.from_numpy(gd['in_%d' % i]) for i in range(4)]
+    out = O.refine_stage_preds(ins[1:])
+    assert np.array_equal(out[1].numpy(), gd['out_56'])
+    assert np.array_equal(out[2].numpy(), gd['out_112'])
+    m28 = ins[1].squeeze(1).sigmoid() >= 0.5
+    assert np.array_equal(O.generate_block_target(m28, 1).numpy(), gd['block_target_28'])
+    # the 3x3 closed form the kernel uses == the two Laplacian convolutions
+    assert np.array_equal(O.non_boundary_3x3(m28.numpy()), gd['block_target_28'] != 1)
+    rng = np.random.default_rng(3)
+    for shape in ((5, 1, 1), (4, 2, 3), (3, 9, 17), (2, 28, 28)):
+        m = rng.random(shape) < 0.6
+        assert np.array_equal(O.non_boundary_3x3(m), O.generate_block_target(torch.from_numpy(m), 1).numpy() != 1)
+
+
+def _golden_polygons():
+    gd = np.load(os.path.join(GOLD, 'polygon.npz'))
+    xy, voff, ooff = gd['xy'], gd['voff'], gd['ooff']
+    objs = [[xy[2 * voff[q]:2 * voff[q + 1]].copy() for q in range(ooff[g], ooff[g + 1])]
+            for g in range(len(ooff) - 1)]
+    return gd, objs
+
+
+def test_golden_polygon_targets_bit_exact():
+    """Oracle restatement of PolygonMasks.crop_and_resize + mask_target_single against the
+    reference's own Python (tests/golden/polygon.npz; the rasteriser underneath is the same C
+    restatement of pycocotools in both, so this pins the host arithmetic around it)."""
+    gd, objs = _golden_polygons()
+    H, W = [int(v) for v in gd['hw']]
+    for s in (14, 28, 56, 112):
+        t = O.polygon_mask_target_single(gd['boxes'], gd['inds'], objs, H, W, s)
+        assert np.array_equal(t.numpy(), gd['target_%d' % s]), s
+    full = np.stack([O.polygon_to_bitmap(o, H, W) for o in objs])
+    assert np.array_equal(full, gd['full'])
+
+
+def test_polygon_rasteriser_known_shapes():
+    """Properties of pycocotools' rleFrPoly rule that can be stated without the library: an
+    integer axis-aligned rectangle fills [x0,x1) x [y0,y1); a polygon covering the canvas fills
+    it; vertex order and starting vertex do not matter; an empty polygon list gives zeros."""
+    m = O.polygon_to_bitmap([np.array([2., 1, 6, 1, 6, 4, 2, 4])], 8, 10)
+    ref = np.zeros((8, 10), bool)
+    ref[1:4, 2:6] = True
+    assert np.array_equal(m, ref)
+    assert O.polygon_to_bitmap([np.array([-3., -2, 20, -2, 20, 30, -3, 30])], 8, 10).all()
+    assert not O.polygon_to_bitmap([], 8, 10).any()
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        p = synth.make_polygons(1, 40, 50, rng, max_parts=1)[0][0]
+        a = O.polygon_to_bitmap([p], 40, 50)
+        pts = p.reshape(-1, 2)
+        assert np.array_equal(a, O.polygon_to_bitmap([np.roll(pts, 3, axis=0).reshape(-1)], 40, 50))
+        assert np.array_equal(a, O.polygon_to_bitmap([pts[::-1].reshape(-1)], 40, 50))
+        # area close to the shoelace area (clipped polygons excluded)
+        if pts.min() > 1 and pts[:, 0].max() < 49 and pts[:, 1].max() < 39:
+            x, y = pts[:, 0], pts[:, 1]
+            area = 0.5 * abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+            per = np.hypot(np.diff(x, append=x[0]), np.diff(y, append=y[0])).sum()
+            assert abs(a.sum() - area) <= per + 2
+    # union of parts == OR of the parts
+    objs = synth.make_polygons(3, 40, 50, rng, max_parts=3)
+    for o in objs:
+        parts = np.stack([O.polygon_to_bitmap([p], 40, 50) for p in o])
+        assert np.array_equal(O.polygon_to_bitmap(o, 40, 50), parts.any(0))
+
+
+# Known-answer vectors held by the reference's own tests: bitmaps that the REAL pycocotools
+# produced for small polygons (reference tests/test_masks.py:339-355, :370-410, :460-470).
+# These pin the oracle's restatement of rleFrPoly / merge / decode against the library itself.
+_REF_TRUTH1 = np.array(
+    [[0, 0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+     [0, 0, 1, 1, 1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 1, 1, 1, 0, 0, 0],
+     [0, 0, 1, 1, 1, 1, 1, 0, 0, 0], [0, 0, 1, 1, 1, 1, 1, 1, 0, 0],
+     [0, 0, 0, 1, 1, 1, 1, 0, 0, 0], [0, 0, 0, 0, 1, 0, 0, 0, 0, 0],
+     [0, 0, 0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 0, 0, 0]], np.uint8)
+_REF_TRUTH2 = np.array(
+    [[0, 1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 1, 1, 0, 0],
+     [0, 0, 1, 1, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0]], np.uint8)
+_REF_CROP_TRUTH = np.array([[0, 0, 0], [0, 0, 0], [0, 0, 1], [0, 1, 1]], np.uint8)
+_REF_POLY1 = [np.array([1, 1, 3, 1, 4, 3, 2, 4, 1, 3], dtype=np.float64)]
+_REF_POLY2 = [np.array([0., 0., 1., 0., 1., 1.]), np.array([1., 1., 2., 1., 2., 2., 1., 2.])]
+_REF_POLY_CROP = [np.array([1., 3., 5., 1., 5., 6., 1, 6])]
+
+
+def test_polygon_rasteriser_matches_reference_known_answers():
+    # test_masks.py:370-383 -- 5x5 polygon resized x2 (polygon coordinates doubled), 1 part
+    doubled = [p * 2.0 for p in _REF_POLY1]
+    assert np.array_equal(O.polygon_to_bitmap(doubled, 10, 10), _REF_TRUTH1.astype(bool))
+    # test_masks.py:385-399 -- two parts, union
+    assert np.array_equal(O.polygon_to_bitmap([p * 2.0 for p in _REF_POLY2], 6, 6), _REF_TRUTH2.astype(bool))
+    # test_masks.py:401-410 -- the 3x3 object rasterised on the 10x10 canvas
+    assert np.array_equal(O.polygon_to_bitmap([p * 2.0 for p in _REF_POLY2], 10, 10),
+                          np.pad(_REF_TRUTH2, ((0, 4), (0, 4)), 'constant').astype(bool))
+    # test_masks.py:460-470 -- crop to [0,0,3,4]: pycocotools clips the boundary
+    assert np.array_equal(O.polygon_to_bitmap(_REF_POLY_CROP, 4, 3), _REF_CROP_TRUTH.astype(bool))
