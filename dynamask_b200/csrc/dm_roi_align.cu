@@ -85,6 +85,7 @@ struct RaParams {
     const int32_t* seg;
     int sampling_ratio, aligned;
     int mode;  // 0 RoIAlign, 1 SimpleRoIAlign (one zero-padded grid_sample point per bin)
+    int interleave;  // walk the buckets at the same fractional pace (1) or one after the other (0)
     int smem_floats;
 };
 
@@ -1204,9 +1205,45 @@ __global__ void __maxnreg__(BWD ? 128 : DM_FWD_REGS) ra_kernel(const __grid_cons
     __shared__ int s_stat[ST_N];
     if (threadIdx.x <= p.nb) s_seg[threadIdx.x] = p.seg ? p.seg[threadIdx.x] : (threadIdx.x == 0 ? 0 : p.K);
     __syncthreads();
-    const long long total = total_units(p, s_seg);
-    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-        const Unit un = decode_unit(p, s_seg, u);
+    // Ownership is a static round-robin over the units enumerated bucket by bucket (largest pooled
+    // size first).  The WALK is interleaved: a CTA visits its units of every bucket at the same
+    // fractional pace, so the latency-bound small-resolution units are spread over the whole launch
+    // and hide under the bandwidth-bound 112x112 stream instead of piling up in the tail.
+    long long first[DM_MAX_BUCKETS];   // this CTA's first unit inside bucket order[j]
+    int mine[DM_MAX_BUCKETS], done[DM_MAX_BUCKETS];
+    float inv_mine[DM_MAX_BUCKETS];
+    {
+        long long base = 0;
+        for (int j = 0; j < p.nb; ++j) {
+            const int b = p.order[j];
+            const long long n = (long long)(s_seg[b + 1] - s_seg[b]) * p.bk[b].nslab;
+            const long long G = gridDim.x;
+            const long long f = (((long long)blockIdx.x - base) % G + G) % G;
+            first[j] = f;
+            mine[j] = f < n ? (int)((n - f + G - 1) / G) : 0;
+            done[j] = 0;
+            inv_mine[j] = mine[j] > 0 ? 1.0f / (float)mine[j] : 0.0f;
+            base += n;
+        }
+    }
+    for (;;) {
+        int jsel = -1;
+        float best = 0.0f;
+        for (int j = 0; j < p.nb; ++j) {
+            if (done[j] >= mine[j]) continue;
+            const float key = p.interleave ? ((float)done[j] + 0.5f) * inv_mine[j] : (float)j;
+            if (jsel < 0 || key < best) { jsel = j; best = key; }
+        }
+        if (jsel < 0) break;
+        Unit un;
+        {
+            const long long u = first[jsel] + (long long)done[jsel] * gridDim.x;
+            ++done[jsel];
+            un.b = p.order[jsel];
+            // slab-major inside a RoI so consecutive CTAs share one RoI's patch in L2
+            un.i = (int)(u / p.bk[un.b].nslab);
+            un.slab = (int)(u - (long long)un.i * p.bk[un.b].nslab);
+        }
         const int vec = p.bk[un.b].vec;
         if (BWD) {
             if (vec == 4) bwd_unit<4>(p, un, s_seg, smem, s_stat);
@@ -1312,6 +1349,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
     p.sampling_ratio = sampling_ratio;
     p.aligned = aligned ? 1 : 0;
     p.mode = 0;
+    p.interleave = env_int("DM_RA_INTERLEAVE", 1);
     return DM_OK;
 }
 
