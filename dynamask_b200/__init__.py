@@ -9,7 +9,7 @@ There is no CPU fallback: ops raise if the shared library is missing or tensors 
 from . import ops
 from .bbox import bbox2roi
 from .mask_heads import (DynaMaskHeadMixin, _do_paste_mask, encode_mask_results, get_seg_masks,
-                         get_seg_masks_rle, paste_masks_in_image, refine_stage_instance_preds)
+                         get_seg_masks_rle, get_seg_masks_switched, paste_masks_in_image, refine_stage_instance_preds)
 from .mask_structures import BitmapMasks, PolygonMasks
 from .mask_target import mask_target, mask_target_single, multi_size_mask_targets
 from .roi_align import RoIAlign, SimpleRoIAlign, roi_align
@@ -24,6 +24,6 @@ __all__ = [
     'ops', 'bbox2roi', 'RoIAlign', 'SimpleRoIAlign', 'roi_align', 'BaseRoIExtractor', 'SingleRoIExtractor',
     'BucketedRoIExtractor', 'BucketedRoIFeats', 'BitmapMasks', 'PolygonMasks', 'mask_target',
     'mask_target_single', 'multi_size_mask_targets', '_do_paste_mask', 'get_seg_masks',
-    'paste_masks_in_image', 'get_seg_masks_rle', 'refine_stage_instance_preds', 'encode_mask_results', 'DynaMaskHeadMixin', 'get_mask_label', 'gumbel_softmax',
+    'paste_masks_in_image', 'get_seg_masks_rle', 'get_seg_masks_switched', 'refine_stage_instance_preds', 'encode_mask_results', 'DynaMaskHeadMixin', 'get_mask_label', 'gumbel_softmax',
     'image_shard', 'shard_rois', 'checksum64', 'gather_checksums'
 ]

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libdynamask_sm100.so')
+# DYNAMASK_LIB selects another build of the same library (kernel experiments); there is still no fallback
+LIB_PATH = os.environ.get('DYNAMASK_LIB') or os.path.join(_HERE, 'lib', 'libdynamask_sm100.so')
 
 _c_f32p = ctypes.c_void_p  # raw device / host addresses are passed as integers
 _vp = ctypes.c_void_p
@@ -28,6 +29,8 @@ SIGNATURES = {
                               _i, _i, _i, _vp]),
     'dm_paste_masks': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
                             _i, _vp, _vp]),
+    'dm_paste_masks_select': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
+                                   _i, _vp, _i, _i, _vp, _vp]),
     'dm_mask_target': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     'dm_paste_rle': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
                           _i, _vp, _vp, _vp, _vp, _vp]),

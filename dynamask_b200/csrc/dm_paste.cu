@@ -69,6 +69,7 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
     const int zero_i = p.sw + 1, nan_i = p.sw + 2;  // VD entries for "exactly zero" / "NaN" columns
     const long long T = (long long)p.rh * p.rw;
     for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
+        if (p.select && p.select[n] != p.select_value) continue;  // CTA-uniform
         const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
         int xa, xb, ya, yb;
         window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
@@ -200,11 +201,11 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
 
 }  // namespace dm
 
-extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
-                              const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
-                              const float* boxes, int img_h, int img_w, int x_lo, int y_lo,
-                              int x_hi, int y_hi, float thr, int out_mode, void* out,
-                              dm_stream_t stream) {
+static int paste_impl(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                      const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                      const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi, int y_hi,
+                      float thr, int out_mode, const int32_t* select, int select_value, int zero_fill,
+                      void* out, dm_stream_t stream) {
     if (N < 0 || S_h < 1 || S_w < 1 || img_h < 0 || img_w < 0) return DM_EINVAL;
     if (x_lo < 0 || y_lo < 0 || x_hi > img_w || y_hi > img_h || x_hi < x_lo || y_hi < y_lo)
         return DM_EINVAL;
@@ -234,10 +235,12 @@ extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t
     p.y_lo = y_lo;
     p.thr = thr;
     p.out = out;
+    p.select = select;
+    p.select_value = select_value;
     p.total = per_inst * N;
     const int ES = out_mode == DM_PASTE_F32 ? 4 : 1;
     cudaStream_t st = (cudaStream_t)stream;
-    {
+    if (zero_fill) {
         const long long nbytes = p.total * ES, n16 = nbytes / 16;
         const long long blocks = (n16 + 1 + 255) / 256;
         if (blocks >= (1ll << 31)) return DM_EUNSUPPORTED;
@@ -254,4 +257,23 @@ extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t
     }
     DM_LAUNCH_CHECK("dm_paste_masks");
     return DM_OK;
+}
+
+extern "C" int dm_paste_masks(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                              const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                              const float* boxes, int img_h, int img_w, int x_lo, int y_lo,
+                              int x_hi, int y_hi, float thr, int out_mode, void* out,
+                              dm_stream_t stream) {
+    return paste_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h,
+                      img_w, x_lo, y_lo, x_hi, y_hi, thr, out_mode, nullptr, 0, 1, out, stream);
+}
+
+extern "C" int dm_paste_masks_select(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                                     const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                                     const float* boxes, int img_h, int img_w, int x_lo, int y_lo,
+                                     int x_hi, int y_hi, float thr, int out_mode, const int32_t* select,
+                                     int select_value, int zero_fill, void* out, dm_stream_t stream) {
+    if (!select) return DM_EINVAL;
+    return paste_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h,
+                      img_w, x_lo, y_lo, x_hi, y_hi, thr, out_mode, select, select_value, zero_fill, out, stream);
 }

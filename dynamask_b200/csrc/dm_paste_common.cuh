@@ -24,6 +24,10 @@ struct PasteParams {
     long long total;         // N * rh * rw output elements
     float thr;
     void* out;
+    // optional per-instance selection (switch-driven inference): instance n is pasted only when
+    // select[n] == select_value; NULL pastes every instance
+    const int32_t* select = nullptr;
+    int select_value = 0;
 };
 
 __device__ __forceinline__ void window_1d(float lo_c, float hi_c, int S, int size, int& a, int& b) {

@@ -45,7 +45,13 @@
 namespace dm {
 
 // CTA size differs per direction (register budget): device code reads it from blockDim
-constexpr int kBwdThreads = 256;   // backward: 2 CTAs/SM x 8 warps at 128 registers
+#ifndef DM_BWD_THREADS
+#define DM_BWD_THREADS 256
+#endif
+#ifndef DM_BWD_REGS
+#define DM_BWD_REGS 128
+#endif
+constexpr int kBwdThreads = DM_BWD_THREADS;   // backward: 2 CTAs/SM x 8 warps at 128 registers
 #ifndef DM_FWD_THREADS
 #define DM_FWD_THREADS 224
 #endif
@@ -72,6 +78,8 @@ struct BucketDesc {
     int cg;     // channels per work unit
     int nslab;  // ceil(C / cg)
     int vec;    // vector width of the pooled-row accesses (4, 2 or 1)
+    int bvec;   // same for the backward walk, which moves grad_out with bulk copies when > 1:
+                // dense rows, 16-byte aligned planes
 };
 
 struct RaParams {
@@ -217,6 +225,33 @@ __device__ __forceinline__ void cp_async_sa(unsigned sa, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Bulk asynchronous copies (TMA, 1-D): one elected lane moves whole runs of pooled rows
+// global -> shared and the data's arrival is signalled on an mbarrier (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // Banded weight tables of one RoI, staged in shared memory.
@@ -830,7 +865,28 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // completes for the whole warp at once: it is dropped into the warp's row buffer, the
 // patch-gradient row is gathered from it (lane = feature column, its transposed X weights held in
 // registers) and reduced into the gradient map with one RED per element.
-constexpr int kRing = 8;   // ring depth of the grad_out prefetch, in pooled rows
+constexpr int kRing = 8;   // ring depth of the grad_out prefetch, in pooled rows (VEC == 1 path)
+// VEC > 1 (dense, 16-byte aligned grad_out): the warp's grad_out rows arrive as bulk copies of
+// kBulkRows pooled rows x cpw channels per chunk through a ring of kBulkSlots chunk slots
+#ifndef DM_BULK_ROWS
+#define DM_BULK_ROWS 4
+#endif
+#ifndef DM_BULK_SLOTS
+#define DM_BULK_SLOTS 4
+#endif
+#ifndef DM_BULK_ENABLE
+#define DM_BULK_ENABLE 0   // measured slower than the per-lane cp.async ring: 12.2 / 11.0 ms vs 9.9 ms
+#endif
+#ifndef DM_BWD_SMEM_KB
+#define DM_BWD_SMEM_KB (DM_BULK_ENABLE ? 96 : 72)
+#endif
+constexpr int kBulkRows = DM_BULK_ROWS;
+constexpr int kBulkSlots = DM_BULK_SLOTS;
+constexpr int kBulkSlotFloats = 128 * kBulkRows;  // >= cpw * kBulkRows * Pw  (cpw * Pw <= 32 * VEC = 128)
+// floats of a warp's grad_out ring: chunk slots + one 8-byte mbarrier per slot, or the cp.async ring
+__host__ __device__ constexpr int kBwdRingFloats(int vec) {
+    return (vec > 1 && DM_BULK_ENABLE) ? kBulkSlots * kBulkSlotFloats + ((2 * kBulkSlots + 3) & ~3) : kRing * 32 * vec;
+}
 constexpr int kBwdRowBuf = 128;  // floats of the warp's row buffer: cpw rows of Pw rounded up to 4
 constexpr int kBwdPad = 84;      // zeros after the row buffer: the aligned tap windows may overrun it
 
@@ -892,11 +948,13 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     __builtin_assume(__isShared(a.plo));
     __builtin_assume(__isShared(a.pcnt));
     __builtin_assume(__isShared(a.wxT));
-    // warp-private shared memory: [kRing][32 lanes][VEC] prefetch ring, then [cpw][Pws] row buffer
-    // followed by kBwdPad zeros
-    float* const ring = a.wsm + lane * VEC;
+    // warp-private shared memory: the grad_out ring ([kRing][32 lanes] floats for VEC == 1, bulk
+    // chunk slots + their mbarriers otherwise), then [cpw][Pws] row buffer followed by kBwdPad zeros
+    constexpr bool BULK = VEC > 1 && DM_BULK_ENABLE;
+    float* const ring = a.wsm + (BULK ? 0 : lane * VEC);
     const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
-    float* const rowbuf = a.wsm + kRing * 32 * VEC;
+    const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(a.wsm + kBulkSlots * kBulkSlotFloats);
+    float* const rowbuf = a.wsm + kBwdRingFloats(VEC);
     float* const myrow = rowbuf + (lane_on ? sub : 0) * Pws + pv * VEC;
     // zero weights meet whatever lies beyond a window's taps: it must be finite
     for (int q = lane; q < kBwdRowBuf + kBwdPad; q += 32) rowbuf[q] = 0.0f;
@@ -914,11 +972,48 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
         wq[q] = (t >= 0 && t < xn) ? a.wxT[xl * a.TW + t] : 0.0f;
     }
     const bool red_on = xon && part == 0;
+    const int step = RA_WARPS * cpw;
+    // ---- bulk ring state: the chunk stream runs over (channel batch, rows) without a break --------
+    const int nch = (Ph + kBulkRows - 1) / kBulkRows;   // chunks per channel batch
+    int p_cb = warp * cpw, p_ch = 0;                    // next chunk to request
+    unsigned p_slot = 0;
+    auto bulk_issue = [&]() {                           // warp-uniform bookkeeping, lane 0 issues
+        if (p_cb < nc) {
+            if (lane == 0) {
+                const int rows = min(kBulkRows, Ph - p_ch * kBulkRows);
+                const int np = min(cpw, nc - p_cb);
+                const unsigned bytes = (unsigned)(rows * Pw * 4);
+                const unsigned bar = bar_sa + 8 * p_slot;
+                mbar_expect_tx(bar, bytes * np);
+                const float* src = a.gbase + p_cb * a.gsC + p_ch * kBulkRows * Pw;
+                unsigned dst = ring_sa + p_slot * (kBulkSlotFloats * 4);
+                for (int s2 = 0; s2 < np; ++s2) {
+                    bulk_g2s(dst, src, bytes, bar);
+                    src += a.gsC;
+                    dst += kBulkRows * Pw * 4;
+                }
+            }
+            if (++p_ch == nch) { p_ch = 0; p_cb += step; }
+            p_slot = p_slot + 1 == kBulkSlots ? 0 : p_slot + 1;
+        }
+    };
+    unsigned c_slot = 0, c_par = 0;                     // chunk being consumed
+    int c_left = 0;                                     // its rows not yet consumed
+    const float* gp = ring;                             // this lane's next row in it
+    if (BULK) {
+        if (lane == 0) {
+            for (int q = 0; q < kBulkSlots; ++q) mbar_init(bar_sa + 8 * q, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kBulkSlots; ++q) bulk_issue();
+    }
     __syncwarp();
 
     const float* gwarp = a.gbase + pv * VEC;
     constexpr int YS = 2 * JW;
-    for (int cb = warp * cpw; cb < nc; cb += RA_WARPS * cpw) {
+    for (int cb = warp * cpw; cb < nc; cb += step) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
         const float* gnext = gwarp + (cb + (lane_on ? sub : 0)) * a.gsC;  // next pooled row to prefetch
@@ -931,33 +1026,55 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
         // ring slots by byte offset: the ring is a power of two in size
         constexpr unsigned kSlotB = 32 * VEC * 4, kRingMask = kRing * kSlotB - 1;
         int pre = on ? Ph : 0;  // pooled rows this lane still has to request
+        if (!BULK) {
 #pragma unroll
-        for (int d = 0; d < kRing - 1; ++d) {
-            if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + d * kSlotB, gnext);
-            --pre;
-            gnext += a.gsH;
-            cp_async_commit();
+            for (int d = 0; d < kRing - 1; ++d) {
+                if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + d * kSlotB, gnext);
+                --pre;
+                gnext += a.gsH;
+                cp_async_commit();
+            }
         }
         unsigned off_w = (kRing - 1) * kSlotB;  // ring slot the next prefetch lands in
         unsigned off_r = 0;                     // ring slot holding the next pooled row
+        int rows_left = Ph;                     // pooled rows of this channel batch not yet consumed
         const float* yrec = ytab;
         // band-row major: once the pooled rows whose band starts at `base` are in, band row `base`
         // is complete for every lane of the warp
         for (int base = 0; base < R; ++base) {
             const int n = rcnt[base];
             for (int k = 0; k < n; ++k) {
-                if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + off_w, gnext);
-                --pre;
-                gnext += a.gsH;
-                off_w = (off_w + kSlotB) & kRingMask;
-                cp_async_commit();
-                float2 w[JW];
-                load_yrec<JW>(yrec, w);
-                yrec += YS;
-                cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
                 float gv[VEC];
-                ld_vec<VEC>(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring) + off_r), gv);
-                off_r = (off_r + kSlotB) & kRingMask;
+                float2 w[JW];
+                if (BULK) {
+                    if (c_left == 0) {  // first row of a chunk: wait for its bytes
+                        mbar_wait(bar_sa + 8 * c_slot, c_par);
+                        c_left = min(kBulkRows, rows_left);
+                        gp = ring + c_slot * kBulkSlotFloats + (lane_on ? sub : 0) * (kBulkRows * Pw) + pv * VEC;
+                    }
+                    load_yrec<JW>(yrec, w);
+                    yrec += YS;
+                    ld_vec<VEC>(gp, gv);
+                    gp += Pw;
+                    --rows_left;
+                    if (--c_left == 0) {  // chunk consumed by every lane: its slot takes the next request
+                        __syncwarp();
+                        bulk_issue();
+                        c_slot = c_slot + 1 == kBulkSlots ? 0 : c_slot + 1;
+                        c_par ^= (c_slot == 0);
+                    }
+                } else {
+                    if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + off_w, gnext);
+                    --pre;
+                    gnext += a.gsH;
+                    off_w = (off_w + kSlotB) & kRingMask;
+                    cp_async_commit();
+                    load_yrec<JW>(yrec, w);
+                    yrec += YS;
+                    cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
+                    ld_vec<VEC>(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring) + off_r), gv);
+                    off_r = (off_r + kSlotB) & kRingMask;
+                }
 #pragma unroll
                 for (int j = 0; j < JW; ++j) vfma<VEC>(acc[j], w[j], gv);
             }
@@ -1009,8 +1126,14 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
             for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
             drow += a.dsH;
         }
-        cp_async_wait<0>();
+        if (!BULK) cp_async_wait<0>();
         __syncwarp();
+    }
+    if (BULK) {
+        // every requested chunk has been consumed; the barriers' storage is reused by the next unit
+        __syncwarp();
+        if (lane == 0)
+            for (int q = 0; q < kBulkSlots; ++q) mbar_inval(bar_sa + 8 * q);
     }
 }
 
@@ -1022,7 +1145,7 @@ __device__ __forceinline__ void bwd_warp(const BwdWarpArgs& a, int need) {
 }
 
 // shared-memory floats a warp needs on the fast path: ring + row buffer + zero pad
-__host__ __device__ constexpr int kBwdWarpFloats(int vec) { return kRing * 32 * vec + kBwdRowBuf + kBwdPad + 4; }
+__host__ __device__ constexpr int kBwdWarpFloats(int vec) { return kBwdRingFloats(vec) + kBwdRowBuf + kBwdPad + 4; }
 
 // Column pass, generic path for bands taller than 8 rows: shared-memory reductions into a zeroed U.
 template <int VEC>
@@ -1199,7 +1322,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD>
-__global__ void __maxnreg__(BWD ? 128 : DM_FWD_REGS) ra_kernel(const __grid_constant__ RaParams p) {
+__global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
@@ -1244,7 +1367,7 @@ __global__ void __maxnreg__(BWD ? 128 : DM_FWD_REGS) ra_kernel(const __grid_cons
             un.i = (int)(u / p.bk[un.b].nslab);
             un.slab = (int)(u - (long long)un.i * p.bk[un.b].nslab);
         }
-        const int vec = p.bk[un.b].vec;
+        const int vec = BWD ? p.bk[un.b].bvec : p.bk[un.b].vec;
         if (BWD) {
             if (vec == 4) bwd_unit<4>(p, un, s_seg, smem, s_stat);
             else if (vec == 2) bwd_unit<2>(p, un, s_seg, smem, s_stat);
@@ -1332,6 +1455,9 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
             else if (d.pw % 2 == 0 && d.sH % 2 == 0 && d.sC % 2 == 0 && d.sN % 2 == 0 && a % 8 == 0) vec = 2;
         }
         d.vec = vec;
+        const bool dense = d.sW == 1 && d.sH == d.pw && (d.ph * d.pw) % 4 == 0 && d.sC % 4 == 0 &&
+                           d.sN % 4 == 0 && a % 16 == 0;
+        d.bvec = dense ? vec : 1;
     }
     // largest outputs first
     for (int b = 0; b < nb; ++b) p.order[b] = b;
@@ -1355,7 +1481,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
 
 template <bool BWD>
 static int launch(RaParams& p, cudaStream_t st, const char* where) {
-    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? 72 : 72);
+    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? DM_BWD_SMEM_KB : 72);
     const int smem_bytes = smem_kb * 1024;
     const int threads = BWD ? kBwdThreads : kFwdThreads;
     p.smem_floats = smem_bytes / 4;

@@ -146,6 +146,42 @@ def encode_mask_results(mask_results):
     return out
 
 
+def get_seg_masks_switched(stage_instance_preds, mask_labels, det_bboxes, det_labels, rcnn_test_cfg,
+                           ori_shape, scale_factor, rescale):
+    """Switch-driven paste-back: detection j is pasted from the stage its
+    mask-switch label selects.
+
+    The reference only sketches this in comments (``dynamask_roi_head.py:176-203``): it pastes all
+    four stage predictions of every detection (``chunk_segm_result[idx] = get_seg_masks(stage idx)``,
+    four full passes) and then keeps ``chunk_segm_result[argmax(mask_labels[j])][j]``.  Here every
+    detection is pasted once.  ``stage_instance_preds``: list of ``[N, C, S_b, S_b]`` logits
+    (14/28/56/112); ``mask_labels``: ``[N, n_stages]`` one-hot (``get_mask_label``) or ``[N]``
+    integer stage indices.  Returns what ``get_seg_masks`` returns: a list of N numpy masks."""
+    from . import ops as _ops
+    bboxes = det_bboxes[:, :4]
+    if rescale:
+        img_h, img_w = ori_shape[:2]
+    else:
+        img_h = np.round(ori_shape[0] * scale_factor).astype(np.int32)
+        img_w = np.round(ori_shape[1] * scale_factor).astype(np.int32)
+        scale_factor = 1.0
+    if not isinstance(scale_factor, (float, torch.Tensor)):
+        scale_factor = bboxes.new_tensor(scale_factor)
+    bboxes = bboxes / scale_factor
+    if mask_labels.dim() == 2:
+        rois = torch.cat([bboxes.new_zeros((bboxes.size(0), 1)), bboxes.float()], 1)
+        bucket = _ops.assign(rois, mask_labels.float(), 1, 56.0, mask_labels.size(1))[1]
+    else:
+        bucket = mask_labels.to(torch.int32)
+    labels = det_labels if stage_instance_preds[0].shape[1] > 1 else None
+    thr = rcnn_test_cfg.mask_thr_binary
+    mode, t = (_ops.PASTE_BOOL, float(thr)) if thr >= 0 else (_ops.PASTE_U8, 0.0)
+    im_mask = _ops.paste_masks_switched([p.to(torch.float32) for p in stage_instance_preds], bucket, bboxes.float(),
+                                        labels, int(img_h), int(img_w), True, t, mode)
+    host = im_mask.cpu().numpy()
+    return [host[i] for i in range(host.shape[0])]
+
+
 def refine_stage_instance_preds(stage_instance_preds):
     """The coarse-to-fine refinement loop of ``DynaMaskRoIHead.simple_test_mask``
     (``mmdet/models/roi_heads/dynamask_roi_head.py:136-148``) as one launch.

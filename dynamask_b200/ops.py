@@ -14,7 +14,7 @@ from torch import Tensor
 from . import _lib
 
 __all__ = ['assign', 'roi_align_forward', 'roi_align_backward', 'paste_masks', 'mask_target',
-           'multilevel_roi_align', 'simple_roi_align_forward', 'simple_roi_align_backward', 'refine_stages_', 'polygon_target']
+           'multilevel_roi_align', 'simple_roi_align_forward', 'simple_roi_align_backward', 'refine_stages_', 'polygon_target', 'paste_masks_switched']
 
 PASTE_BOOL, PASTE_U8, PASTE_F32 = 0, 1, 2
 
@@ -554,3 +554,40 @@ def _(poly_xy, vert_offsets, obj_poly_offsets, img_meta, boxes, inds, roi_img, c
     K = boxes.size(0)
     return [torch.empty((K, sizes_hw[2 * s], sizes_hw[2 * s + 1]), dtype=torch.float32,
                         device=boxes.device) for s in range(len(sizes_hw) // 2)]
+
+
+# --------------------------------------------------------------------------------------------
+# dm_paste_masks_select  
+# --------------------------------------------------------------------------------------------
+def paste_masks_switched(stage_masks: Sequence[Tensor], bucket: Tensor, boxes: Tensor,
+                         labels: Optional[Tensor], img_h: int, img_w: int, apply_sigmoid: bool,
+                         thr: float, mode: int) -> Tensor:
+    """Paste instance n from ``stage_masks[bucket[n]]`` (each ``[N,C,S_b,S_b]``): one zero fill and
+    one window launch per stage, no gather / scatter and no host synchronisation."""
+    N = stage_masks[0].size(0)
+    dev = stage_masks[0].device
+    if not stage_masks[0].is_cuda:
+        raise NotImplementedError('dynamask::paste_masks_switched has no CPU implementation')
+    if bucket.dtype != torch.int32 or bucket.numel() != N:
+        raise TypeError('bucket must be int32 [N]')
+    boxes = _f32c(boxes, 'boxes')[:, :4].contiguous()
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    dt = {PASTE_BOOL: torch.bool, PASTE_U8: torch.uint8, PASTE_F32: torch.float32}[mode]
+    out = torch.empty((N, int(img_h), int(img_w)), dtype=dt, device=dev)
+    if out.numel() == 0:
+        return out
+    bucket = bucket.contiguous()
+    with torch.cuda.device(dev):
+        for b, m in enumerate(stage_masks):
+            m = _f32c(m, 'masks')
+            if m.dim() != 4 or m.size(0) != N:
+                raise ValueError('every stage must be [N,C,S,S]')
+            if m.stride(3) != 1 or m.stride(2) != m.size(3):
+                m = m.contiguous()
+            rc = _lib.load().dm_paste_masks_select(
+                _ptr(m), m.stride(0), m.stride(1), _ptr(labels), N, m.size(2), m.size(3),
+                int(bool(apply_sigmoid)), _ptr(boxes), int(img_h), int(img_w), 0, 0, int(img_w), int(img_h),
+                float(thr), int(mode), _ptr(bucket), b, 1 if b == 0 else 0, _ptr(out), _stream(dev))
+            _lib.check(rc, 'dm_paste_masks_select')
+    return out

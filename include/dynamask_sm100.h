@@ -230,6 +230,21 @@ int dm_polygon_target(const double* poly_xy, const int64_t* vert_offsets,
                       int clip, const int32_t* sizes_hw, int n_sizes, float* const* out_ptrs,
                       dm_stream_t stream);
 
+/*
+ * Next row: switch-driven inference.  The reference sketches it in comments
+ * (mmdet/models/roi_heads/dynamask_roi_head.py:176-203): paste ALL four stage predictions of every
+ * detection (four get_seg_masks passes), then keep chunk_segm_result[mask_labels[j]][j].  Here each
+ * detection is pasted once, from the stage its mask-switch label selects: call once per stage with
+ * that stage's [N,C,S,S] masks; instance n is written only when select[n] == select_value
+ * (select = the bucket array of dm_assign).  zero_fill != 0 clears the whole [N,h,w] output first
+ * (first call of a group).  Other arguments as dm_paste_masks.
+ */
+int dm_paste_masks_select(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                          const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                          const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                          int y_hi, float thr, int out_mode, const int32_t* select, int select_value,
+                          int zero_fill, void* out, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

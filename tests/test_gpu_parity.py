@@ -938,3 +938,33 @@ def test_polygon_masks_reference_known_answers_gpu():
     out = pm.crop_and_resize(np.array([[2., 3, 20, 25], [0, 0, 28, 28]], np.float32), (56, 72), [0, 2])
     assert len(out) == 2 and (out.height, out.width) == (56, 72)
     assert out.to_ndarray().shape == (2, 56, 72)
+
+
+# ------------------------------------------------------------------------------------------
+# next row: switch-driven paste-back -- dynamask_roi_head.py:176-203 (comments)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('as_onehot', [True, False])
+def test_get_seg_masks_switched_selects_stage_per_detection(as_onehot):
+    g = gen(101)
+    n = 24
+    stages = [synth.make_mask_logits(n, s, g) for s in (14, 28, 56, 112)]
+    boxes = synth.make_boxes(n, 240, 320, g, s_hi=200.0)
+    det = torch.cat([boxes, torch.ones(n, 1)], 1)
+    labels = torch.zeros(n, dtype=torch.long)
+    onehot = synth.make_onehot(n, g)
+    pick = onehot.argmax(1)
+
+    class Cfg:
+        mask_thr_binary = 0.5
+    # the reference's sketch: paste every stage, keep chunk_segm_result[mask_labels[j]][j]
+    per_stage = [O.get_seg_masks(s, det, labels, 0.5, (240, 320, 3), 1.0, False) for s in stages]
+    ref = [per_stage[int(pick[j])][j] for j in range(n)]
+    ml = onehot.cuda() if as_onehot else pick.cuda()
+    out = dm().get_seg_masks_switched([s.cuda() for s in stages], ml, det.cuda(), labels.cuda(), Cfg,
+                                      (240, 320, 3), 1.0, False)
+    agree = sum(int((a == b).sum()) for a, b in zip(out, ref)) / (n * 240 * 320)
+    assert agree >= 0.9999, agree
+    # every stage is actually used and a detection pasted from the wrong stage would be caught
+    assert len(set(pick.tolist())) == 4
+    wrong = [per_stage[(int(pick[j]) + 1) % 4][j] for j in range(n)]
+    assert sum(int((a == b).sum()) for a, b in zip(out, wrong)) / (n * 240 * 320) < 0.9999
