@@ -472,6 +472,74 @@ def run_extras(dm, ops, dev, rank, peak):
     ex['dm_mask_target'] = {'workload': 'C3: 2 images x 128 positives, G~U{1..20} 800x1344 bitmaps, sizes 14/28/56/112, '
                                         'includes the per-step upload of the bitmaps',
                             'ms': ms, 'rois_per_s': 256 / ms * 1e3}
+    del t, masks_l
+
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
+            r = fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, r
+
+    # ---- next rows ---------------------------------------------------------------
+    # polygon ground truth (the shipped COCO config): same C3 shape, polygons instead of bitmaps
+    polys_l, props, inds = [], [], []
+    for _ in range(2):
+        objs = synth.make_polygons(int(rng.integers(1, 21)), IMG_H, IMG_W, rng)
+        pb, pi = synth.jitter_boxes_from_polygons(objs, 128, rng)
+        polys_l.append(dm.PolygonMasks(objs, IMG_H, IMG_W))
+        props.append(torch.from_numpy(pb).to(dev))
+        inds.append(torch.from_numpy(pi).to(dev))
+    ms, _ = timed(lambda: dm.multi_size_mask_targets(props, inds, polys_l))
+    ex['dm_polygon_target'] = {'workload': 'C3 with polygon ground truth: 2 images x 128 positives, 1-3 polygons of 5-40 '
+                                           'vertices per object, sizes 14/28/56/112, includes the per-step upload',
+                               'ms': ms, 'rois_per_s': 256 / ms * 1e3}
+    # SimpleRoIAlign at the three SFMStage shapes (100 detections of one 800x1344 image, 256 channels)
+    g2 = torch.Generator().manual_seed(5 + rank)
+    rois100 = synth.make_rois(1, 100, IMG_H, IMG_W, g2).to(dev)
+    sra = {}
+    for P, s in ((14, 16), (28, 8), (56, 4)):
+        f = torch.randn(1, 256, IMG_H // s, IMG_W // s, device=dev, requires_grad=True)
+        layer = dm.SimpleRoIAlign(P, 1.0 / s)
+        ms_f, o = timed(lambda: layer(f, rois100))
+        go = torch.ones_like(o)
+        ms_b, _ = timed(lambda: ops.simple_roi_align_backward(go, rois100, list(f.shape), 1.0 / s, True))
+        by = o.numel() * 4
+        sra['P%d_stride%d' % (P, s)] = {'fwd_ms': ms_f, 'bwd_ms_incl_zero_init': ms_b, 'out_bytes': by,
+                                        'fwd_out_gbs': by / ms_f / 1e6}
+        del f, o, go
+    ex['dm_simple_roi_align'] = {'workload': 'SFMStage gathers: 100 RoIs x 256 ch at 14/28/56 from stride 16/8/4 maps', **sra}
+    # fused stage-to-stage refinement, one chunk of 100 detections (28 -> 56 -> 112)
+    st = [torch.randn(100, 1, sz, sz, device=dev) * 3 for sz in (28, 56, 112)]
+    ms, _ = timed(lambda: dm.refine_stage_instance_preds(st))
+    ex['dm_refine_stages'] = {'workload': '100 detections, stages 28/56/112, in place', 'ms': ms,
+                              'instances_per_s': 100 / ms * 1e3}
+    # ---- inference tail of one image, device resident, then to host as RLE (config C1/C4 per image):
+    # mask RoI extractor 14x14 -> [head convs: PyTorch, not timed] -> refine -> paste -> RLE strings
+    feats1 = [torch.randn(1, 256, h, w, device=dev) for (h, w) in synth.pyramid_shapes(IMG_H, IMG_W)]
+    ext = dm.SingleRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 256, STRIDES)
+    det100 = torch.cat([rois100[:, 1:], torch.ones(100, 1, device=dev)], 1)
+    lab100 = torch.zeros(100, dtype=torch.long, device=dev)
+
+    def tail():
+        ins = ext(feats1, rois100)
+        final = dm.refine_stage_instance_preds([t.clone() for t in st])
+        return ins, dm.get_seg_masks_rle(final, det100, lab100, _Cfg, (800, 1333, 3), 1.0, False)
+    tail()
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    for _ in range(5):
+        tail()
+    torch.cuda.synchronize()
+    dt = (_time.perf_counter() - t0) / 5
+    ex['inference_tail_per_image'] = {
+        'workload': 'one 800x1333 image, 100 detections: 14x14 mask RoIAlign (256 ch) + refinement 28/56/112 + '
+                    'fused paste->RLE, results on the host as RLE strings; head convolutions excluded (PyTorch)',
+        'ms': dt * 1e3, 'img_per_s': 1.0 / dt}
     return ex
 
 

@@ -36,6 +36,7 @@ SIGNATURES = {
                           _i, _vp, _vp, _vp, _vp, _vp]),
     'dm_rle_from_canvas': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'dm_rle_compress_host': (_i64, [_vp, _i64, _i64, _vp, _i64]),
+    'dm_rle_compress_batch_host': (_i64, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     'dm_polygon_target': (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     'dm_refine_stages': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'dm_simple_roi_align_fwd': (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),

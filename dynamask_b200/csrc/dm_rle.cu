@@ -361,3 +361,22 @@ extern "C" int64_t dm_rle_compress_host(const int32_t* transitions, int64_t n, i
     }
     return len;
 }
+
+// Host side, batch form: the transitions of N instances (instance n owns
+// transitions[offsets[n] .. offsets[n+1])) -> N compressed strings written back to back into
+// `out`; str_offsets[n] .. str_offsets[n+1] delimits string n.  Returns the total length or -1 when
+// `cap` is too small (6 bytes per transition + 8 per instance always suffice).
+extern "C" int64_t dm_rle_compress_batch_host(const int32_t* transitions, const int64_t* offsets, int64_t N,
+                                              int64_t total_pixels, char* out, int64_t cap,
+                                              int64_t* str_offsets) {
+    int64_t pos = 0;
+    for (int64_t n = 0; n < N; ++n) {
+        str_offsets[n] = pos;
+        const int64_t len = dm_rle_compress_host(transitions + offsets[n], offsets[n + 1] - offsets[n],
+                                                 total_pixels, out + pos, cap - pos);
+        if (len < 0) return -1;
+        pos += len;
+    }
+    str_offsets[N] = pos;
+    return pos;
+}

@@ -487,6 +487,47 @@ __device__ void direct_unit(const LevelDesc& Lv, const BucketDesc& B, const RoiG
     }
 }
 
+// SimpleRoIAlign on a patch too large for the streaming walk (a big RoI on a fine map: the points
+// are sparse in the patch, so staging whole patch rows would mostly move pixels nobody samples).
+// Every output is four taps; the two X taps / weights of a pooled column and the two Y taps of a
+// pooled row come from the banded tables (bands are at most 2 wide in point mode).  A warp owns
+// whole pooled rows of a channel, lanes run along the row: coalesced stores (forward) / loads
+// (backward), gathers served by L1 / L2, one RED per tap in the backward (the points are at least
+// a pixel apart here, so there is no contention to aggregate).
+template <bool BWD>
+__device__ __noinline__ void point_sparse_unit(const LevelDesc& Lv, const BucketDesc& B, const Tables& t, int batch,
+                                  int i, int c0, int c1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Pw = B.pw, Ph = B.ph;
+    const int rows = (c1 - c0) * Ph;
+    float* fbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC;
+    float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
+    for (int row = warp; row < rows; row += RA_WARPS) {
+        const int c = row / Ph, ph = row - c * Ph;
+        const int y0 = t.ys[ph], y1 = min(y0 + 1, Lv.H - 1);
+        const float wy0 = t.wy[ph], wy1 = t.JYa > 1 ? t.wy[Ph + ph] : 0.0f;
+        float* f0 = fbase + (long long)c * Lv.sC + (long long)y0 * Lv.sH;
+        float* f1 = fbase + (long long)c * Lv.sC + (long long)y1 * Lv.sH;
+        float* o = obase + (long long)c * B.sC + (long long)ph * B.sH;
+        for (int pw = lane; pw < Pw; pw += 32) {
+            const int x0 = t.xs[pw], x1 = min(x0 + 1, Lv.W - 1);
+            const float wx0 = t.wx[pw], wx1 = t.JXa > 1 ? t.wx[Pw + pw] : 0.0f;
+            if (BWD) {
+                const float g = __ldcs(o + (long long)pw * B.sW);
+                const float a = g * wy0, b = g * wy1;
+                if (a * wx0 != 0.0f) atomicAdd(f0 + (long long)x0 * Lv.sW, a * wx0);
+                if (a * wx1 != 0.0f) atomicAdd(f0 + (long long)x1 * Lv.sW, a * wx1);
+                if (b * wx0 != 0.0f) atomicAdd(f1 + (long long)x0 * Lv.sW, b * wx0);
+                if (b * wx1 != 0.0f) atomicAdd(f1 + (long long)x1 * Lv.sW, b * wx1);
+            } else {
+                const float v = wy0 * (wx0 * __ldg(f0 + (long long)x0 * Lv.sW) + wx1 * __ldg(f0 + (long long)x1 * Lv.sW)) +
+                                wy1 * (wx0 * __ldg(f1 + (long long)x0 * Lv.sW) + wx1 * __ldg(f1 + (long long)x1 * Lv.sW));
+                __stcs(o + (long long)pw * B.sW, v);
+            }
+        }
+    }
+}
+
 // Rows of the feature map needed by pooled rows [p0, p1): ys[p0] .. min(ys[p1-1]+JY-1, Y1)
 __device__ __forceinline__ int band_rows(const Tables& t, int p0, int p1) {
     return min(t.ys[p1 - 1] + t.JY - 1, t.Y1) - t.ys[p0] + 1;
@@ -832,6 +873,10 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
             else fwd_warp<VEC, 8>(a);
             return;
         }
+    }
+    if (p.mode && t.JX <= 2 && t.JY <= 2) {
+        point_sparse_unit<false>(Lv, B, t, batch, un.i, c0, c1);
+        return;
     }
     const int per_row = fw + B.pw;
     if ((long long)Rfull * per_row <= avail) {
@@ -1226,6 +1271,11 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) return;
     const int fw = fits ? t.X1 - t.X0 + 1 : 0;
     const int R = fits ? t.Y1 - t.Y0 + 1 : 0;
+    if (p.mode && fits && t.JX <= 2 && t.JY <= 2 && fw > 32) {
+        // SimpleRoIAlign, patch wider than a warp: points at least ~a pixel apart, nothing to aggregate
+        point_sparse_unit<true>(Lv, B, t, batch, un.i, c0, c1);
+        return;
+    }
     // transposed X tables: for feature column x the pooled columns [plo, plo+pcnt) whose band covers
     // it, and their weights wxT[x][q]
     int* plo = reinterpret_cast<int*>(smem + (fits ? t.floats : 0));
@@ -1444,6 +1494,14 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
         while (pw2 * 2 <= cg) pw2 *= 2;
         cg = cg < 1 ? 1 : pw2;
         cg = cg < 16 ? 16 : (cg > 256 ? 256 : cg);
+        if (nb == 1 && K > 0) {
+            // a single small bucket (inference: ~100 detections): split channels further so that the
+            // persistent grid still has a few units per CTA
+            const long long want = 6ll * sm_count();
+            int small = 256;
+            while (small > 16 && (long long)K * ((p.C + small - 1) / small) < want) small >>= 1;
+            if (small < cg) cg = small;
+        }
         cg = env_int("DM_RA_CG", 0) > 0 ? env_int("DM_RA_CG", 0) : cg;
         if (cg > p.C) cg = p.C;
         d.cg = cg;

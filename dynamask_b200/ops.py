@@ -329,21 +329,18 @@ def _rle_finish(N, rh, rw, totals, run_pass2):
     offsets = torch.from_numpy(offsets_h[:-1].copy()).to(dev)
     trans = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     run_pass2(offsets, trans)
-    trans_h = trans[:total].cpu().numpy()
+    trans_h = np.ascontiguousarray(trans[:max(total, 1)].cpu().numpy())
     lib = _lib.load()
-    out = []
-    buf = ctypes.create_string_buffer(64)
-    for n in range(N):
-        t = np.ascontiguousarray(trans_h[offsets_h[n]:offsets_h[n + 1]])
-        cap = 6 * (t.size + 1) + 8
-        if cap > len(buf):
-            buf = ctypes.create_string_buffer(cap)
-        ln = lib.dm_rle_compress_host(ctypes.c_void_p(t.ctypes.data), int(t.size), int(rh) * int(rw),
-                                      ctypes.cast(buf, ctypes.c_void_p), len(buf))
-        if ln < 0:
-            raise RuntimeError('dm_rle_compress_host: buffer too small')
-        out.append({'size': [int(rh), int(rw)], 'counts': buf.raw[:ln]})
-    return out
+    cap = 6 * total + 8 * N + 8
+    buf = np.empty(cap, np.uint8)
+    str_off = np.empty(N + 1, np.int64)
+    ln = lib.dm_rle_compress_batch_host(ctypes.c_void_p(trans_h.ctypes.data), ctypes.c_void_p(offsets_h.ctypes.data),
+                                        N, int(rh) * int(rw), ctypes.c_void_p(buf.ctypes.data), cap,
+                                        ctypes.c_void_p(str_off.ctypes.data))
+    if ln < 0:
+        raise RuntimeError('dm_rle_compress_batch_host: buffer too small')
+    raw = buf[:ln].tobytes()
+    return [{'size': [int(rh), int(rw)], 'counts': raw[str_off[n]:str_off[n + 1]]} for n in range(N)]
 
 
 def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,

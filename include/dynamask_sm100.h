@@ -168,6 +168,13 @@ int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int
  */
 int64_t dm_rle_compress_host(const int32_t* transitions, int64_t n, int64_t total_pixels, char* out,
                              int64_t cap);
+/*
+ * HOST function, batch form: instance n owns transitions[offsets[n] .. offsets[n+1]); the N strings
+ * are written back to back into `out`, string n at out[str_offsets[n] .. str_offsets[n+1]).
+ * Returns the total length or -1 if `cap` is too small (6 * transitions + 8 * N always suffices).
+ */
+int64_t dm_rle_compress_batch_host(const int32_t* transitions, const int64_t* offsets, int64_t N,
+                                   int64_t total_pixels, char* out, int64_t cap, int64_t* str_offsets);
 
 /*
  * Next row: SimpleRoIAlign, the per-RoI semantic-feature gather of SFMStage

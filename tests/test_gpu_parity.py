@@ -968,3 +968,22 @@ def test_get_seg_masks_switched_selects_stage_per_detection(as_onehot):
     assert len(set(pick.tolist())) == 4
     wrong = [per_stage[(int(pick[j]) + 1) % 4][j] for j in range(n)]
     assert sum(int((a == b).sum()) for a, b in zip(out, wrong)) / (n * 240 * 320) < 0.9999
+
+
+def test_simple_roi_align_large_rois_on_fine_map():
+    """Whole-image RoIs on the stride-4 map (patches far wider than a warp: the sparse path),
+    mixed with small ones, forward and backward."""
+    g = gen(75)
+    H, W = 200, 336
+    feat = torch.randn(1, 8, H, W, generator=g)
+    rois = torch.tensor([[0, 0., 0., 1344., 800.], [0, 100., 50., 1200., 700.], [0, 10., 10., 60., 50.],
+                         [0, 600., 5., 1340., 90.], [0, 30., 100., 80., 790.]])
+    for P in (14, 56):
+        fc = feat.cuda().requires_grad_()
+        out = dm().SimpleRoIAlign(P, 0.25)(fc, rois.cuda())
+        ref = O.simple_roi_align(feat, rois, P, 0.25)
+        assert_close(out, ref, FWD_RTOL, _sra_atol(feat), 'SimpleRoIAlign large P=%d' % P)
+        go = torch.randn(out.shape, generator=g)
+        out.backward(go.cuda())
+        assert_close(fc.grad, O.simple_roi_align_backward(go, feat.shape, rois, 0.25), BWD_RTOL, 2e-4,
+                     'SimpleRoIAlign large grad P=%d' % P)

@@ -307,3 +307,27 @@ def test_next_row_ops_refuse_cpu_tensors():
         dm.refine_stage_instance_preds([torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 8, 8)])
     layer = dm.SimpleRoIAlign(14, 1.0 / 4)
     assert layer.output_size == (14, 14) and layer.spatial_scale == 0.25 and layer.aligned
+
+
+def test_rle_compress_batch_host_equals_per_instance_strings():
+    rng = np.random.default_rng(6)
+    h, w = 23, 31
+    masks = [(rng.random((h, w)) < p).astype(np.uint8) for p in (0.0, 1.0, 0.5, 0.1, 0.9)]
+    trans = [_transitions(m) for m in masks]
+    offs = np.zeros(len(masks) + 1, np.int64)
+    np.cumsum([len(t) for t in trans], out=offs[1:])
+    flat = np.ascontiguousarray(np.concatenate(trans), np.int32)
+    lib = _lib.load()
+    cap = 6 * flat.size + 8 * len(masks) + 8
+    buf = np.empty(cap, np.uint8)
+    so = np.empty(len(masks) + 1, np.int64)
+    n = lib.dm_rle_compress_batch_host(ctypes.c_void_p(flat.ctypes.data), ctypes.c_void_p(offs.ctypes.data),
+                                       len(masks), h * w, ctypes.c_void_p(buf.ctypes.data), cap,
+                                       ctypes.c_void_p(so.ctypes.data))
+    assert n == so[-1] and n > 0
+    raw = buf[:n].tobytes()
+    for i, t in enumerate(trans):
+        assert raw[so[i]:so[i + 1]] == _compress(t, h * w)
+    assert lib.dm_rle_compress_batch_host(ctypes.c_void_p(flat.ctypes.data), ctypes.c_void_p(offs.ctypes.data),
+                                          len(masks), h * w, ctypes.c_void_p(buf.ctypes.data), 3,
+                                          ctypes.c_void_p(so.ctypes.data)) == -1
