@@ -375,6 +375,11 @@ def main():
     if not args.no_extras:
         line['extras'] = run_extras(dm, ops, dev, rank, peak)
 
+    if not args.no_extras and rank == 0 and world == 1:
+        line['gpu_competitor'] = run_competitor(dm, dev, rank, feats, rois, onehot)
+        if 'c2_torchvision_cuda_ms' in line['gpu_competitor']:
+            line['gpu_competitor']['c2_ours_ms'] = fwd_ms + bwd_ms + asg_ms
+
     # ---- e2e: plugin surface with host buffers -------------------------------------------------
     if not args.no_e2e:
         e2e = run_e2e(args, dm, dev, rank, world, feats, rois_h, onehot_h, counts)
@@ -541,6 +546,99 @@ def run_extras(dm, ops, dev, rank, peak):
                     'fused paste->RLE, results on the host as RLE strings; head convolutions excluded (PyTorch)',
         'ms': dt * 1e3, 'img_per_s': 1.0 / dt}
     return ex
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU competitor: the kernels a user of the reference gets on this box today --
+# torchvision's CUDA roi_align (the mmcv kernel's lineage, sm_100 SASS shipped in torchvision/_C.so)
+# under the reference's per-level select / align / scatter loop
+# (mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:53-81).  Library code timed
+# beside ours; it is not the oracle and nothing of it is on the product path.
+# ----------------------------------------------------------------------------------------------
+def tv_single_roi_extractor(feats, rois, out_size, strides, finest_scale=56):
+    import torchvision.ops as tvo
+    K, C = rois.size(0), feats[0].size(1)
+    out = feats[0].new_zeros(K, C, out_size, out_size)
+    if len(feats) == 1:
+        return tvo.roi_align(feats[0], rois, (out_size, out_size), 1.0 / strides[0], 0, True)
+    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    lvls = torch.floor(torch.log2(scale / finest_scale + 1e-6)).clamp(min=0, max=len(feats) - 1).long()
+    for i in range(len(feats)):
+        inds = lvls == i
+        if inds.any():
+            out[inds] = tvo.roi_align(feats[i], rois[inds], (out_size, out_size), 1.0 / strides[i], 0, True)
+    return out
+
+
+def run_competitor(dm, dev, rank, feats, rois, onehot):
+    """Ours vs torchvision-CUDA on (a) the C2 step and (b) the extractor calls of one C3 training step
+    (2 images: 7x7 bbox features of 1024 RoIs fwd+bwd, 14x14 mask features of 256 positives fwd+bwd,
+    56x56 single-level switch input of the same 256 fwd only).  Device-resident, CUDA events."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    res = {}
+    bucket = onehot.argmax(1)
+    fr = [f.detach().requires_grad_() for f in feats]
+
+    def tv_c2():
+        for f in fr:
+            f.grad = None
+        outs = []
+        for bi, P in enumerate(BUCKET_SIZES):
+            outs.append(tv_single_roi_extractor(fr, rois[bucket == bi], P, STRIDES))
+        torch.autograd.backward(outs, [o.detach() for o in outs])
+    try:
+        res['c2_torchvision_cuda_ms'] = timed(tv_c2, reps=2)
+    except Exception as e:  # noqa: BLE001  (e.g. out of memory on a shared box)
+        res['c2_torchvision_cuda_error'] = str(e)[:120]
+    for f in fr:
+        f.grad = None
+    torch.cuda.empty_cache()
+
+    # C3: two images of the batch
+    f2 = [f[:2].detach().clone().requires_grad_() for f in feats]
+    r_bbox = rois[:1024]
+    r_mask = torch.cat([rois[:128], rois[512:640]])
+    ours7 = dm.SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=0), 256, STRIDES)
+    ours14 = dm.SingleRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 256, STRIDES)
+    ours56 = dm.SingleRoIExtractor(dict(type='RoIAlign', output_size=56, sampling_ratio=0), 256, [4])
+
+    def ours_c3():
+        for f in f2:
+            f.grad = None
+        o7 = ours7(f2, r_bbox)
+        o14 = ours14(f2, r_mask)
+        o56 = ours56([f2[0].detach()], r_mask)
+        torch.autograd.backward([o7, o14], [o7.detach(), o14.detach()])
+        return o56
+
+    def tv_c3():
+        for f in f2:
+            f.grad = None
+        o7 = tv_single_roi_extractor(f2, r_bbox, 7, STRIDES)
+        o14 = tv_single_roi_extractor(f2, r_mask, 14, STRIDES)
+        o56 = tv_single_roi_extractor([f2[0].detach()], r_mask, 56, [4])
+        torch.autograd.backward([o7, o14], [o7.detach(), o14.detach()])
+        return o56
+    res['c3_extractors_ours_ms'] = timed(ours_c3, reps=10, warm=3)
+    try:
+        res['c3_extractors_torchvision_cuda_ms'] = timed(tv_c3, reps=10, warm=3)
+    except Exception as e:  # noqa: BLE001
+        res['c3_torchvision_cuda_error'] = str(e)[:120]
+    res['workload'] = ('c2: the bench step (8192 RoIs, mixed sizes, fwd+bwd); c3: extractor calls of one training step, '
+                       '2 images -- 7x7 x 1024 RoIs fwd+bwd, 14x14 x 256 fwd+bwd, 56x56 single-level x 256 fwd')
+    return res
 
 
 def run_e2e(args, dm, dev, rank, world, feats_dev, rois_h, onehot_h, counts):

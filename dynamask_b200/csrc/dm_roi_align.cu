@@ -618,6 +618,7 @@ struct FwdWarpArgs {
     int sC, sH;          // feature strides in floats
     int osC, osH;        // pooled strides in floats
     int Pw, Ph, R, X0a, fws, cpr, cw, cpw, nc;
+    int nring;           // ring slots actually used (<= kFwdRing): wide patch rows get a shallower ring
 };
 
 template <int VEC, int JW>
@@ -642,14 +643,18 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     // shared memory and are re-read once per patch row: registers are the scarcer resource here
     const int* const xsp = a.xs + (lane_on ? pv * VEC : 0);
     const float* const wxp = a.wx + (lane_on ? pv * VEC : 0);
+    const int nring = a.nring, pf = nring - 2;
     // the pad columns are never written by the copies: they must hold finite values
-    for (int q = lane * 4; q < kFwdRing * rowf; q += 128) *reinterpret_cast<float4*>(ring + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = lane * 4; q < nring * rowf; q += 128) *reinterpret_cast<float4*>(ring + q) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
-    // ---- producer side: this lane's copy of every patch row ---------------------------------------
+    // ---- producer side: this lane's copies of every patch row --------------------------------------
+    // copy q of a ring row is channel q / cpr, floats (q % cpr) * cw ..; a lane owns q = lane (and
+    // lane + 32, ... when the rows are wider than a warp's worth of copies)
     const int step = RA_WARPS * cpw;
-    const int cc_c = lane / a.cpr;                     // channel of this lane's copy inside the batch
-    const int cc_x = (lane - cc_c * a.cpr) * a.cw;     // first float of the copy inside the row
+    const int ncopy = cpw * a.cpr;
+    const int cc_c = lane / a.cpr;                     // channel of this lane's first copy inside the batch
+    const int cc_x = (lane - cc_c * a.cpr) * a.cw;     // first float of that copy inside the row
     const float* i_src = a.src0 + (warp * cpw + cc_c) * a.sC + cc_x;  // this lane's source, next row to issue
     float* const i_dst = ring + cc_c * a.fws + cc_x;
     int i_cb = warp * cpw, i_r = 0, i_slot = 0;
@@ -657,6 +662,13 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
         if (i_cb < nc) {
 #if !defined(DM_DIAG_NO_READS)
             if (cc_c < min(cpw, nc - i_cb)) cp_async_w(a.cw, i_dst + i_slot * rowf, i_src);
+            if (ncopy > 32) {
+                for (int q = lane + 32; q < ncopy; q += 32) {
+                    const int c = q / a.cpr, x = (q - c * a.cpr) * a.cw;
+                    if (c < min(cpw, nc - i_cb))
+                        cp_async_w(a.cw, ring + i_slot * rowf + c * a.fws + x, i_src + (c - cc_c) * a.sC + (x - cc_x));
+                }
+            }
 #endif
             i_src += a.sH;
             if (++i_r == R) {
@@ -664,7 +676,7 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
                 i_cb += step;
                 i_src += step * a.sC - R * a.sH;
             }
-            i_slot = i_slot + 1 == kFwdRing ? 0 : i_slot + 1;
+            i_slot = i_slot + 1 == nring ? 0 : i_slot + 1;
         }
         cp_async_commit();
     };
@@ -673,7 +685,9 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     int r_slot = 0;
     auto consume = [&](float (&v)[VEC]) {
         issue();
-        cp_async_wait<kFwdPF>();
+        if (pf == kFwdPF) cp_async_wait<kFwdPF>();
+        else if (pf >= 6) cp_async_wait<6>();
+        else cp_async_wait<3>();
         __syncwarp();
         int xo[VEC];
         ld_vec_i<VEC>(xsp, xo);
@@ -695,10 +709,9 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
                 }
             }
         }
-        if (++r_slot == kFwdRing) { r_slot = 0; pr -= (kFwdRing - 1) * rowf; } else { pr += rowf; }
+        if (++r_slot == nring) { r_slot = 0; pr -= (nring - 1) * rowf; } else { pr += rowf; }
     };
-#pragma unroll
-    for (int d = 0; d < kFwdPF; ++d) issue();
+    for (int d = 0; d < pf; ++d) issue();
 
     constexpr int YS = 2 * JW;
     float* o_cb = a.obase + (warp * cpw + subc) * a.osC + pv * VEC;
@@ -867,8 +880,21 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
         a.cw = Lv.cw;
         a.fws = fwd_row_stride(t.X0, t.X1, a.cw, wc, a.X0a, fwp);
         a.cpr = fwp / a.cw;
+        // channels per warp pass and ring depth: the full ring (12 rows in flight) when it fits;
+        // patch rows wider than that get a shallower ring (6 or 3 rows in flight -- the bytes in
+        // flight stay about the same) and, beyond 32 copies per row, several copies per lane
         a.cpw = min(min(32 / PwV, slice / (kFwdRing * a.fws)), 32 / a.cpr);
-        if (a.cpw >= 1) {
+        a.nring = kFwdRing;
+        if (a.cpw < 32 / PwV) {
+            // keep the lanes busy first (as many channels per pass as the strips allow), then give
+            // the ring what is left: 8 slots (6 rows in flight) or 5 (3 in flight)
+            a.nring = 0;
+            for (int c = 32 / PwV; c >= 1 && a.nring == 0; --c) {
+                const int nr = slice / (c * a.fws);
+                if (nr >= 5) { a.cpw = c; a.nring = nr >= kFwdRing ? kFwdRing : (nr >= 8 ? 8 : 5); }
+            }
+        }
+        if (a.cpw >= 1 && a.nring > 0) {
             a.src0 = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + a.X0a;
             a.obase = B.ptr + (long long)un.i * B.sN + (long long)c0 * B.sC;
             a.ytab = t.ytab; a.rcnt = t.rcnt; a.xs = t.xs; a.wx = t.wx;

@@ -987,3 +987,18 @@ def test_simple_roi_align_large_rois_on_fine_map():
         out.backward(go.cuda())
         assert_close(fc.grad, O.simple_roi_align_backward(go, feat.shape, rois, 0.25), BWD_RTOL, 2e-4,
                      'SimpleRoIAlign large grad P=%d' % P)
+
+
+def test_single_level_56_on_large_rois_streams_wide_patch_rows():
+    """The switch input (base_roi_head.py:53-58: 56x56, single level, stride 4) on RoIs up to the
+    whole image: patch rows far wider than 128 floats take the shallow-ring / multi-copy walk."""
+    g = gen(76)
+    feat = torch.randn(2, 6, 200, 336, generator=g)
+    rois = torch.tensor([[0, 0., 0., 1344., 800.], [1, 100., 50., 1200., 700.], [0, 10., 10., 60., 50.],
+                         [1, 600., 5., 1340., 90.], [0, 30., 100., 80., 790.], [1, 3., 3., 900., 500.]])
+    ext = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=56, sampling_ratio=0), 6, [4])
+    out = ext([feat.cuda()], rois.cuda())
+    ref = O.single_roi_extractor([feat], rois, 56, [4])
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL, 'single-level 56 large RoIs')
+    out14 = dm().roi_align(feat.cuda(), rois.cuda(), 14, 0.25, 2, 'avg', True)
+    assert_close(out14, O.roi_align(feat, rois, (14, 14), 0.25, 2, True), FWD_RTOL, FWD_ATOL, '14 sr2 large RoIs')
