@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--no-competitor', action='store_true', help='skip the torchvision-CUDA leg (e.g. under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--e2e-chunk-images', type=int, default=2)
     ap.add_argument('--cpu-sample-rois', type=int, default=8, help='RoIs per image in the CPU sample')
@@ -375,7 +376,7 @@ def main():
     if not args.no_extras:
         line['extras'] = run_extras(dm, ops, dev, rank, peak)
 
-    if not args.no_extras and rank == 0 and world == 1:
+    if not args.no_extras and not args.no_competitor and rank == 0 and world == 1:
         line['gpu_competitor'] = run_competitor(dm, dev, rank, feats, rois, onehot)
         if 'c2_torchvision_cuda_ms' in line['gpu_competitor']:
             line['gpu_competitor']['c2_ours_ms'] = fwd_ms + bwd_ms + asg_ms

@@ -65,10 +65,9 @@ constexpr int kBwdThreads = DM_BWD_THREADS;   // backward: 2 CTAs/SM x 8 warps a
 #ifndef DM_FWD_REGS
 #define DM_FWD_REGS 96
 #endif
-constexpr int kFwdThreads = DM_FWD_THREADS;   // forward: 3 CTAs/SM x 7 warps at 96 registers
+constexpr int kFwdThreads = DM_FWD_THREADS;   // forward: 2 CTAs/SM x 7 warps at 96 registers (7 warps are allocated as 8)
 #define RA_THREADS ((int)blockDim.x)
 #define RA_WARPS ((int)(blockDim.x >> 5))
-constexpr int kFwdCtasPerSm = 3;
 
 struct LevelDesc {
     float* ptr;  // const for forward, accumulated into for backward
@@ -603,7 +602,7 @@ __device__ __forceinline__ int fwd_row_stride(int X0, int X1, int cw, int jw, in
     return (fwp + jw - 1 + 3) & ~3;     // + zero pad for the padded taps
 }
 
-// Register budget matters here (three CTAs per SM = 80 registers): offsets are 32-bit (one
+// Register budget matters here (96 registers without spills in the row loop): offsets are 32-bit (one
 // level's map and one RoI's pooled block are far below 2^31 floats), every lane owns at most one
 // copy per patch row (the caller keeps cpw * copies-per-row <= 32), and only scalars cross the
 // call boundary.
@@ -1572,7 +1571,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
 
 template <bool BWD>
 static int launch(RaParams& p, cudaStream_t st, const char* where) {
-    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? DM_BWD_SMEM_KB : 72);
+    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? DM_BWD_SMEM_KB : 100);
     const int smem_bytes = smem_kb * 1024;
     const int threads = BWD ? kBwdThreads : kFwdThreads;
     p.smem_floats = smem_bytes / 4;
