@@ -143,6 +143,13 @@ __device__ __forceinline__ bool geom_tap(const RoiGeom& g, int axis, int P, int 
     return point_tap(point_coord(start, bin, g.scale, g.mode, P, size, p), size, lo, hi, l, h);
 }
 
+// Fire-and-forget reduction into GLOBAL memory (SASS: RED.E.ADD.F32).  `atomicAdd` on a pointer whose
+// address space the compiler cannot prove (anything that crossed a __noinline__ call) compiles to a
+// generic ATOM that returns a predicate plus shared / local fall-back code the warp has to wait for.
+__device__ __forceinline__ void red_add(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float2* p, const float2& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float* p, const float& v) { __stcs(p, v); }

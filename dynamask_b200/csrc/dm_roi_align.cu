@@ -228,6 +228,23 @@ __device__ __forceinline__ void cp_async_sa(unsigned sa, const void* gsrc) {
     else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+// Unpredicated form: `live` false copies nothing and zero-fills the destination (src-size 0), so the
+// instruction, its address arithmetic and its memory descriptor stay outside any per-lane branch.
+// The source is `base + 4 * off` with a 32-bit float offset: the address is formed by one wide
+// multiply-add inside the asm block, so no 64-bit pointer is carried (and shuffled) around the loop.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill_sa(unsigned sa, const float* base, int off, bool live) {
+    const int n = live ? BYTES : 0;
+    if (BYTES == 16)
+        asm volatile("{\n.reg .u64 a;\nmad.wide.s32 a, %3, 4, %1;\ncp.async.cg.shared.global [%0], [a], 16, %2;\n}"
+                     ::"r"(sa), "l"(base), "r"(n), "r"(off) : "memory");
+    else if (BYTES == 8)
+        asm volatile("{\n.reg .u64 a;\nmad.wide.s32 a, %3, 4, %1;\ncp.async.ca.shared.global [%0], [a], 8, %2;\n}"
+                     ::"r"(sa), "l"(base), "r"(n), "r"(off) : "memory");
+    else
+        asm volatile("{\n.reg .u64 a;\nmad.wide.s32 a, %3, 4, %1;\ncp.async.ca.shared.global [%0], [a], 4, %2;\n}"
+                     ::"r"(sa), "l"(base), "r"(n), "r"(off) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -480,10 +497,10 @@ __device__ DM_COLD void direct_unit(const LevelDesc& Lv, const BucketDesc& B, co
                 float* p3 = f + (long long)yh * Lv.sH + (long long)xl * Lv.sW;
                 float* p4 = f + (long long)yh * Lv.sH + (long long)xh * Lv.sW;
                 if (BWD) {
-                    atomicAdd(p1, gv * hy * hx);
-                    atomicAdd(p2, gv * hy * lx);
-                    atomicAdd(p3, gv * ly * hx);
-                    atomicAdd(p4, gv * ly * lx);
+                    red_add(p1, gv * hy * hx);
+                    red_add(p2, gv * hy * lx);
+                    red_add(p3, gv * ly * hx);
+                    red_add(p4, gv * ly * lx);
                 } else {
                     acc += hy * hx * __ldg(p1) + hy * lx * __ldg(p2) + ly * hx * __ldg(p3) + ly * lx * __ldg(p4);
                 }
@@ -521,10 +538,10 @@ __device__ __noinline__ void point_sparse_unit(const LevelDesc& Lv, const Bucket
             if (BWD) {
                 const float g = __ldcs(o + (long long)pw * B.sW);
                 const float a = g * wy0, b = g * wy1;
-                if (a * wx0 != 0.0f) atomicAdd(f0 + (long long)x0 * Lv.sW, a * wx0);
-                if (a * wx1 != 0.0f) atomicAdd(f0 + (long long)x1 * Lv.sW, a * wx1);
-                if (b * wx0 != 0.0f) atomicAdd(f1 + (long long)x0 * Lv.sW, b * wx0);
-                if (b * wx1 != 0.0f) atomicAdd(f1 + (long long)x1 * Lv.sW, b * wx1);
+                if (a * wx0 != 0.0f) red_add(f0 + (long long)x0 * Lv.sW, a * wx0);
+                if (a * wx1 != 0.0f) red_add(f0 + (long long)x1 * Lv.sW, a * wx1);
+                if (b * wx0 != 0.0f) red_add(f1 + (long long)x0 * Lv.sW, b * wx0);
+                if (b * wx1 != 0.0f) red_add(f1 + (long long)x1 * Lv.sW, b * wx1);
             } else {
                 const float v = wy0 * (wx0 * __ldg(f0 + (long long)x0 * Lv.sW) + wx1 * __ldg(f0 + (long long)x1 * Lv.sW)) +
                                 wy1 * (wx0 * __ldg(f1 + (long long)x0 * Lv.sW) + wx1 * __ldg(f1 + (long long)x1 * Lv.sW));
@@ -942,7 +959,10 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // completes for the whole warp at once: it is dropped into the warp's row buffer, the
 // patch-gradient row is gathered from it (lane = feature column, its transposed X weights held in
 // registers) and reduced into the gradient map with one RED per element.
-constexpr int kRing = 8;   // ring depth of the grad_out prefetch, in pooled rows (VEC == 1 path)
+#ifndef DM_BWD_RING
+#define DM_BWD_RING 8
+#endif
+constexpr int kRing = DM_BWD_RING;   // ring depth of the grad_out prefetch, in pooled rows (VEC == 1 path)
 // VEC > 1 (dense, 16-byte aligned grad_out): the warp's grad_out rows arrive as bulk copies of
 // kBulkRows pooled rows x cpw channels per chunk through a ring of kBulkSlots chunk slots
 #ifndef DM_BULK_ROWS
@@ -982,7 +1002,7 @@ __device__ __noinline__ void bwd_retire_wide(const float* rowbuf, int Pws, int n
             const float* wp = wxT + x * TW;
             float a = 0.0f;
             for (int q = (x < cols ? min(n, (lo & ~3) + cover - lo) : 0); q < n; ++q) a += wp[q] * up[q];
-            if (a != 0.0f) atomicAdd(drow + x, a);
+            if (a != 0.0f) red_add(drow + x, a);
         }
     }
 }
@@ -1093,7 +1113,10 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     for (int cb = warp * cpw; cb < nc; cb += step) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
-        const float* gnext = gwarp + (cb + (lane_on ? sub : 0)) * a.gsC;  // next pooled row to prefetch
+        // next pooled row to prefetch = gcb + goff (a 32-bit offset: one IMAD.WIDE per address
+        // instead of a 64-bit pointer carried around the loop)
+        const float* const gcb = gwarp + (cb + (lane_on ? sub : 0)) * a.gsC;
+        int goff = 0;
         float* drow = a.dbase + cb * a.dsC + xl;                           // gradient-map row being retired
         float acc[JW][VEC];
 #pragma unroll
@@ -1106,9 +1129,9 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
         if (!BULK) {
 #pragma unroll
             for (int d = 0; d < kRing - 1; ++d) {
-                if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + d * kSlotB, gnext);
+                cp_async_zfill_sa<VEC * 4>(ring_sa + d * kSlotB, gcb, goff, pre > 0);
                 --pre;
-                gnext += a.gsH;
+                goff += a.gsH;
                 cp_async_commit();
             }
         }
@@ -1141,15 +1164,16 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                         c_par ^= (c_slot == 0);
                     }
                 } else {
-                    if (pre > 0) cp_async_sa<VEC * 4>(ring_sa + off_w, gnext);
+                    // the prefetch lands in the slot the previous pooled row was read from
+                    cp_async_zfill_sa<VEC * 4>(ring_sa + off_w, gcb, goff, pre > 0);
                     --pre;
-                    gnext += a.gsH;
-                    off_w = (off_w + kSlotB) & kRingMask;
+                    goff += a.gsH;
                     cp_async_commit();
                     load_yrec<JW>(yrec, w);
                     yrec += YS;
                     cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
                     ld_vec<VEC>(reinterpret_cast<const float*>(reinterpret_cast<const char*>(ring) + off_r), gv);
+                    off_w = off_r;
                     off_r = (off_r + kSlotB) & kRingMask;
                 }
 #pragma unroll
@@ -1178,7 +1202,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                 if (a.split == 1) {
                     for (int s2 = 0; s2 < nact; ++s2) {
                         const float r = taps(up);
-                        if (xon && r != 0.0f) atomicAdd(dp, r);
+                        if (xon && r != 0.0f) red_add(dp, r);
                         up += Pws;
                         dp += a.dsC;
                     }
@@ -1187,7 +1211,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                         float r = taps(up);
                         if (a.split >= 4) r += __shfl_down_sync(0xffffffffu, r, 16);
                         r += __shfl_down_sync(0xffffffffu, r, a.split >= 4 ? 8 : 16);
-                        if (red_on && r != 0.0f) atomicAdd(dp, r);
+                        if (red_on && r != 0.0f) red_add(dp, r);
                         up += Pws;
                         dp += a.dsC;
                     }
@@ -1276,7 +1300,7 @@ __device__ DM_COLD void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, c
         for (int q = 0; q < n; ++q) acc += wp[q] * up[q];
         if (acc != 0.0f) {
             const int c = fdR.div(row), r = row - c * R;
-            atomicAdd(dst + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW, acc);
+            red_add(dst + (long long)c * Lv.sC + (long long)r * Lv.sH + (long long)x * Lv.sW, acc);
         }
     }
 }
