@@ -523,6 +523,11 @@ __device__ __noinline__ void point_sparse_unit(const LevelDesc& Lv, const Bucket
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Pw = B.pw, Ph = B.ph;
     const int rows = (c1 - c0) * Ph;
+    // not inlined: the tables live in shared memory (LDS, not generic LD)
+    __builtin_assume(__isShared(t.xs));
+    __builtin_assume(__isShared(t.ys));
+    __builtin_assume(__isShared(t.wx));
+    __builtin_assume(__isShared(t.wy));
     float* fbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC;
     float* obase = B.ptr + (long long)i * B.sN + (long long)c0 * B.sC;
     for (int row = warp; row < rows; row += RA_WARPS) {
@@ -993,6 +998,10 @@ constexpr int kBwdPad = 84;      // zeros after the row buffer: the aligned tap 
 __device__ __noinline__ void bwd_retire_wide(const float* rowbuf, int Pws, int nact, int fw, int cols, int cover,
                                              const int* plo, const int* pcnt, const float* wxT, int TW,
                                              float* drow0, int dsC, int lane) {
+    __builtin_assume(__isShared(rowbuf));
+    __builtin_assume(__isShared(plo));
+    __builtin_assume(__isShared(pcnt));
+    __builtin_assume(__isShared(wxT));
     for (int s2 = 0; s2 < nact; ++s2) {
         const float* ur = rowbuf + s2 * Pws;
         float* drow = drow0 + s2 * dsC;   // points at column 0 of the patch row
@@ -1110,33 +1119,42 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
 
     const float* gwarp = a.gbase + pv * VEC;
     constexpr int YS = 2 * JW;
+    // ring slots by byte offset: the ring is a power of two in size
+    constexpr unsigned kSlotB = 32 * VEC * 4, kRingMask = kRing * kSlotB - 1;
+    // ---- cp.async ring state: this lane's grad_out rows form ONE stream over (channel batch, pooled
+    // row), so the first rows of the next batch are already in flight while the current one retires
+    // and no batch starts on a cold load.  The next row to request is p_base + 4 * p_off (a 32-bit
+    // offset: one wide multiply-add per address instead of a 64-bit pointer carried around the loop).
+    const float* p_base = gwarp + (warp * cpw + (lane_on ? sub : 0)) * a.gsC;
+    int p_off = 0, p_rows = Ph, p_left = nc - warp * cpw;   // rows of the batch not yet requested, channels from it on
+    bool p_live = lane_on && sub < p_left;
+    auto request = [&](unsigned slot_sa) {
+        cp_async_zfill_sa<VEC * 4>(slot_sa, p_base, p_off, p_live);
+        p_off += a.gsH;
+        if (--p_rows == 0) {
+            p_base += step * a.gsC;
+            p_off = 0;
+            p_rows = Ph;
+            p_left -= step;
+            p_live = lane_on && sub < p_left;
+        }
+        cp_async_commit();
+    };
+    if (!BULK && warp * cpw < nc) {
+#pragma unroll
+        for (int d = 0; d < kRing - 1; ++d) request(ring_sa + d * kSlotB);
+    }
+    unsigned off_w = (kRing - 1) * kSlotB;  // ring slot the next prefetch lands in
+    unsigned off_r = 0;                     // ring slot holding the next pooled row
     for (int cb = warp * cpw; cb < nc; cb += step) {
         const int nact = min(cpw, nc - cb);
         const bool on = lane_on && sub < nact;
-        // next pooled row to prefetch = gcb + goff (a 32-bit offset: one IMAD.WIDE per address
-        // instead of a 64-bit pointer carried around the loop)
-        const float* const gcb = gwarp + (cb + (lane_on ? sub : 0)) * a.gsC;
-        int goff = 0;
         float* drow = a.dbase + cb * a.dsC + xl;                           // gradient-map row being retired
         float acc[JW][VEC];
 #pragma unroll
         for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
-        // ring slots by byte offset: the ring is a power of two in size
-        constexpr unsigned kSlotB = 32 * VEC * 4, kRingMask = kRing * kSlotB - 1;
-        int pre = on ? Ph : 0;  // pooled rows this lane still has to request
-        if (!BULK) {
-#pragma unroll
-            for (int d = 0; d < kRing - 1; ++d) {
-                cp_async_zfill_sa<VEC * 4>(ring_sa + d * kSlotB, gcb, goff, pre > 0);
-                --pre;
-                goff += a.gsH;
-                cp_async_commit();
-            }
-        }
-        unsigned off_w = (kRing - 1) * kSlotB;  // ring slot the next prefetch lands in
-        unsigned off_r = 0;                     // ring slot holding the next pooled row
         int rows_left = Ph;                     // pooled rows of this channel batch not yet consumed
         const float* yrec = ytab;
         // band-row major: once the pooled rows whose band starts at `base` are in, band row `base`
@@ -1165,10 +1183,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                     }
                 } else {
                     // the prefetch lands in the slot the previous pooled row was read from
-                    cp_async_zfill_sa<VEC * 4>(ring_sa + off_w, gcb, goff, pre > 0);
-                    --pre;
-                    goff += a.gsH;
-                    cp_async_commit();
+                    request(ring_sa + off_w);
                     load_yrec<JW>(yrec, w);
                     yrec += YS;
                     cp_async_wait<kRing - 1>();  // this lane's copy of the pooled row has landed
@@ -1227,9 +1242,9 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
             for (int e = 0; e < VEC; ++e) acc[JW - 1][e] = 0.0f;
             drow += a.dsH;
         }
-        if (!BULK) cp_async_wait<0>();
         __syncwarp();
     }
+    if (!BULK) cp_async_wait<0>();   // the trailing zero-fill requests have landed before the ring is reused
     if (BULK) {
         // every requested chunk has been consumed; the barriers' storage is reused by the next unit
         __syncwarp();
