@@ -150,6 +150,12 @@ __device__ __forceinline__ void red_add(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
 }
 
+// Same, predicated inside the asm block: no branch (BSSY / BRA / BSYNC) around the reduction.
+__device__ __forceinline__ void red_add_if(float* p, float v, bool on) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\n@q red.global.add.f32 [%0], %1;\n}"
+                 ::"l"(__cvta_generic_to_global(p)), "f"(v), "r"((int)on) : "memory");
+}
+
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float2* p, const float2& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float* p, const float& v) { __stcs(p, v); }

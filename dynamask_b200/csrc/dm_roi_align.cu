@@ -1125,18 +1125,18 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     // row), so the first rows of the next batch are already in flight while the current one retires
     // and no batch starts on a cold load.  The next row to request is p_base + 4 * p_off (a 32-bit
     // offset: one wide multiply-add per address instead of a 64-bit pointer carried around the loop).
-    const float* p_base = gwarp + (warp * cpw + (lane_on ? sub : 0)) * a.gsC;
-    int p_off = 0, p_rows = Ph, p_left = nc - warp * cpw;   // rows of the batch not yet requested, channels from it on
-    bool p_live = lane_on && sub < p_left;
+    const float* const p_base = gwarp + (warp * cpw + (lane_on ? sub : 0)) * a.gsC;
+    int p_off = 0, p_rows = Ph;   // float offset of the next row, rows of its batch not yet requested
+    // a lane is live for its first batches only (the last batch of a slab may be partial): count rows
+    int p_cnt = lane_on && nc - warp * cpw > sub ? Ph * ((nc - warp * cpw - sub + step - 1) / step) : 0;
+    const int p_jump = step * a.gsC - Ph * a.gsH;   // from the end of a batch to the start of the next
     auto request = [&](unsigned slot_sa) {
-        cp_async_zfill_sa<VEC * 4>(slot_sa, p_base, p_off, p_live);
+        cp_async_zfill_sa<VEC * 4>(slot_sa, p_base, p_off, p_cnt > 0);
+        --p_cnt;
         p_off += a.gsH;
         if (--p_rows == 0) {
-            p_base += step * a.gsC;
-            p_off = 0;
             p_rows = Ph;
-            p_left -= step;
-            p_live = lane_on && sub < p_left;
+            p_off += p_jump;
         }
         cp_async_commit();
     };
@@ -1217,7 +1217,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                 if (a.split == 1) {
                     for (int s2 = 0; s2 < nact; ++s2) {
                         const float r = taps(up);
-                        if (xon && r != 0.0f) red_add(dp, r);
+                        red_add_if(dp, r, xon);   // every column of the patch is touched: a zero test would only cost
                         up += Pws;
                         dp += a.dsC;
                     }
@@ -1226,7 +1226,7 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
                         float r = taps(up);
                         if (a.split >= 4) r += __shfl_down_sync(0xffffffffu, r, 16);
                         r += __shfl_down_sync(0xffffffffu, r, a.split >= 4 ? 8 : 16);
-                        if (red_on && r != 0.0f) red_add(dp, r);
+                        red_add_if(dp, r, red_on);
                         up += Pws;
                         dp += a.dsC;
                     }
@@ -1398,7 +1398,7 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     {
         const int PwV = B.pw / VEC;
         if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
-            B.sC < (1 << 24) && B.sH < (1 << 24)) {
+            B.sC < (1 << 24) && B.sH < (1 << 24) && (long long)(c1 - c0 + RA_WARPS * 32) * B.sC < (1ll << 31)) {
             // fast path: warp-private ring + row buffer, no CTA-wide barrier after this point
             __syncthreads();
             BwdWarpArgs a;
