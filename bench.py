@@ -663,31 +663,52 @@ def run_e2e(args, dm, dev, rank, world, feats_dev, rois_h, onehot_h, counts):
         cnt = torch.bincount(bucket_h[sel], minlength=len(BUCKET_SIZES)).tolist()
         chunks.append((i0, i1, r.pin_memory(), onehot_h[sel].clone().pin_memory(), cnt))
     max_cnt = [max(c[4][b] for c in chunks) for b in range(len(BUCKET_SIZES))]
+    NBUF = 2   # result staging is double buffered: chunk i's D2H overlaps chunk i+1's H2D and kernels
     try:
         feats_pin = [torch.empty(f.shape, dtype=f.dtype, pin_memory=True) for f in feats_dev]
         for p, f in zip(feats_pin, feats_dev):
             p.copy_(f)
-        outs_pin = [torch.empty((max_cnt[b], C, s, s), dtype=torch.float32, pin_memory=True)
-                    for b, s in enumerate(BUCKET_SIZES)]
-        grads_pin = [torch.empty((ci, ) + tuple(f.shape[1:]), dtype=f.dtype, pin_memory=True) for f in feats_dev]
+        outs_pin = [[torch.empty((max_cnt[b], C, s, s), dtype=torch.float32, pin_memory=True)
+                     for b, s in enumerate(BUCKET_SIZES)] for _ in range(NBUF)]
+        grads_pin = [[torch.empty((ci, ) + tuple(f.shape[1:]), dtype=f.dtype, pin_memory=True) for f in feats_dev]
+                     for _ in range(NBUF)]
     except RuntimeError as e:
         return {'value': None, 'unit': UNIT, 'error': 'pinned allocation failed: %s' % str(e)[:80]}
     h2d = sum(p.numel() * 4 for p in feats_pin) + rois_h.numel() * 4 + onehot_h.numel() * 4
     d2h = sum(counts[b] * C * s * s * 4 for b, s in enumerate(BUCKET_SIZES)) + sum(p.numel() * 4 for p in feats_pin)
+    main = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)    # device -> host results; PCIe is full duplex, so it runs beside the H2D
     torch.cuda.synchronize()
 
     def one():
-        for (i0, i1, r_pin, o_pin, cnt) in chunks:
+        done = [None] * NBUF          # event: the host may read / reuse staging set k
+        for j, (i0, i1, r_pin, o_pin, cnt) in enumerate(chunks):
+            k = j % NBUF
+            if done[k] is not None:
+                done[k].synchronize()     # the host consumes that set's results before it is refilled
             fd = [p[i0:i1].to(dev, non_blocking=True).requires_grad_() for p in feats_pin]
             rd = r_pin.to(dev, non_blocking=True)
             od = o_pin.to(dev, non_blocking=True)
             res = ext.forward_bucketed(fd, rd, od)
-            for p, o in zip(outs_pin, res.feats):
-                p[:o.size(0)].copy_(o.detach(), non_blocking=True)
-            torch.autograd.backward(res.feats, [o.detach() for o in res.feats])
-            for p, f in zip(grads_pin, fd):
-                p[:i1 - i0].copy_(f.grad, non_blocking=True)
-            torch.cuda.synchronize()   # the host consumes this chunk's results before the buffers are reused
+            outs = [o.detach() for o in res.feats]
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(fwd_done)
+                for p, o in zip(outs_pin[k], outs):
+                    p[:o.size(0)].copy_(o, non_blocking=True)
+                    o.record_stream(copy)
+            torch.autograd.backward(res.feats, outs)
+            bwd_done = torch.cuda.Event()
+            bwd_done.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(bwd_done)
+                for p, f in zip(grads_pin[k], fd):
+                    p[:i1 - i0].copy_(f.grad, non_blocking=True)
+                    f.grad.record_stream(copy)
+                done[k] = torch.cuda.Event()
+                done[k].record(copy)
+        torch.cuda.synchronize()
 
     one()  # warm-up
     if world > 1:
@@ -705,7 +726,8 @@ def run_e2e(args, dm, dev, rank, world, feats_dev, rois_h, onehot_h, counts):
     return {'value': world * rois_h.size(0) / dt, 'unit': UNIT, 'ms_per_step': dt * 1e3,
             'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': args.e2e_steps,
             'chunk_images': ci,
-            'api': 'BucketedRoIExtractor.forward_bucketed + autograd backward per chunk, pinned host in / out'}
+            'api': 'BucketedRoIExtractor.forward_bucketed + autograd backward per chunk, pinned host in / out, '
+                   'results double buffered on a copy stream'}
 
 
 if __name__ == '__main__':
