@@ -60,12 +60,15 @@ namespace dm {
 #endif
 constexpr int kBwdThreads = DM_BWD_THREADS;   // backward: 2 CTAs/SM x 8 warps at 128 registers
 #ifndef DM_FWD_THREADS
-#define DM_FWD_THREADS 224
+#define DM_FWD_THREADS 256
+#endif
+#ifndef DM_FWD_HOIST
+#define DM_FWD_HOIST 1   // X strip constants (first column, weights) of a lane in registers instead of re-read per patch row
 #endif
 #ifndef DM_FWD_REGS
-#define DM_FWD_REGS 96
+#define DM_FWD_REGS (DM_FWD_HOIST ? 128 : 96)
 #endif
-constexpr int kFwdThreads = DM_FWD_THREADS;   // forward: 2 CTAs/SM x 7 warps at 96 registers (7 warps are allocated as 8)
+constexpr int kFwdThreads = DM_FWD_THREADS;   // forward: 2 CTAs/SM x 8 warps at 128 registers
 #define RA_THREADS ((int)blockDim.x)
 #define RA_WARPS ((int)(blockDim.x >> 5))
 
@@ -704,6 +707,16 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     // ---- consumer side: next patch row of the stream -> this lane's X-interpolated strip values ----
     const float* pr = ring + subc * a.fws - a.X0a;  // this lane's channel in the slot being read next
     int r_slot = 0;
+#if DM_FWD_HOIST
+    // strip constants in registers (the kernel is built for 128 registers: 2 CTAs x 7 warps still fit)
+    int xo_r[VEC];
+    float wx_r[JW <= 4 ? JW : 1][VEC];
+    if (JW <= 4) {
+        ld_vec_i<VEC>(xsp, xo_r);
+#pragma unroll
+        for (int j = 0; j < (JW <= 4 ? JW : 1); ++j) ld_vec<VEC>(wxp + j * a.Pw, wx_r[j]);
+    }
+#endif
     auto consume = [&](float (&v)[VEC]) {
         issue();
         if (pf == kFwdPF) cp_async_wait<kFwdPF>();
@@ -711,10 +724,22 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
         else cp_async_wait<3>();
         __syncwarp();
         int xo[VEC];
+#if DM_FWD_HOIST
+        if (JW <= 4) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) xo[e] = xo_r[e];
+        } else
+#endif
         ld_vec_i<VEC>(xsp, xo);
 #pragma unroll
         for (int j = 0; j < JW; ++j) {
             float wj[VEC], pj[VEC];
+#if DM_FWD_HOIST
+            if (JW <= 4) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) wj[e] = wx_r[JW <= 4 ? j : 0][e];
+            } else
+#endif
             ld_vec<VEC>(wxp + j * a.Pw, wj);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) pj[e] = pr[xo[e] + j];
