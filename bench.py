@@ -112,6 +112,9 @@ def algorithmic_bytes(rois, lvl, bucket, shapes, batch, channels):
 # clocks sampler
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING the timed region: NVML polled every few ms
+    from a thread (the timed region of the default run is ~160 ms -- `nvidia-smi -lms` does not even
+    deliver its first line in that time); nvidia-smi is the fall-back when pynvml is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -120,8 +123,27 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []       # (sm_mhz, power_w, reasons bitmask)
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(',')) and self.index < len(vis.split(',')):
+                phys = int(vis.split(',')[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
@@ -132,11 +154,45 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    watts = 0.0
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, watts, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            if not self.samples:
+                return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+            bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+            seen = 0
+            for _, _, m in self.samples:
+                seen |= m
+            return {'sm_mhz': float(np.median([x[0] for x in self.samples])), 'sm_max_mhz': self.max_mhz,
+                    'power_w_max': float(max(x[1] for x in self.samples)), 'samples': len(self.samples),
+                    'source': 'nvml', 'reasons': sorted(k for k, b in bits.items() if seen & b)}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -162,7 +218,8 @@ class ClockSampler:
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)),
-                'power_w_max': float(max(power)), 'samples': len(sm), 'reasons': sorted(reasons)}
+                'power_w_max': float(max(power)), 'samples': len(sm), 'source': 'nvidia-smi',
+                'reasons': sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------------
