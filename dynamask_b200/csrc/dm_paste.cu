@@ -13,14 +13,18 @@
 // Pixels whose sample falls outside (-1, S) are exactly zero; a conservative per-instance window
 // bounds the pixels that have to be evaluated at all (~2-3 % of a COCO-shaped canvas).
 //
-// Two launches on the caller's stream:
-//   1. paste_fill_kernel: the whole [N, rh, rw] output leaves as zeros, 16 bytes per thread, one
-//      shot -- the flavour of write-only stream that runs fastest on this part
-//      (profiles/r01_membench.md: 7.4 TB/s).
-//   2. paste_window_kernel: grid = (16-row bands of a window, instances).  A CTA stages
-//      sigmoid(mask) for the mask rows its canvas rows can reach and the x terms of the window's
-//      columns (both depend on one axis only), then a warp per canvas row interpolates along y into
-//      a private row buffer and along x straight into global memory, one pixel per lane.
+// Window kernel (paste_window_body): grid = (32-row bands of a window, instances).  A CTA stages
+// sigmoid(mask) for the mask rows its canvas rows can reach and the x terms of the window's columns
+// (both depend on one axis only), then a warp per canvas row interpolates along y into a private row
+// buffer and along x straight into global memory, one pixel per lane.
+// The zero background comes in one of two ways:
+//   * fused (default for canvases of >= 64 KB per instance): ONE launch, paste_fused_kernel.  The window
+//     CTAs own every element of their instances' window ROWS (zeros included), the rest of the output
+//     is zeroed in 64 KB tiles dealt to the same CTAs, which issue their tiles first -- fire-and-forget
+//     stores that drain to HBM while the CTA goes on to its window bands.  183 us for the C4 shape.
+//   * two launches (small canvases, and DM_PASTE_FUSED=0): paste_fill_kernel zeroes the whole output, 16
+//     bytes per thread, one shot (7.4 TB/s, profiles/r01_membench.md), then paste_window_kernel writes
+//     the non-zero pixels only.  227 us for the C4 shape (115 us + 83 us + launch gap).
 // An earlier single-launch form (every 16 KB tile decides "zero or evaluate") spent more time in
 // the latency chains of its sparse live tiles than in the fill itself.
 //
@@ -57,30 +61,55 @@ __global__ void __launch_bounds__(256) paste_fill_kernel(uint4* __restrict__ out
 // is then V[lo] + wh * (V[lo+1] - V[lo]) -- one 8-byte table read, one 8-byte VD read, one FMA.
 // Columns whose sample misses (-1, S) point at a (0, 0) entry, NaN columns at a (NaN, NaN) entry,
 // so the pixel loop has no branches.
-template <int MODE>
-__global__ void __launch_bounds__(kPasteThreads, 5)
-paste_window_kernel(const __grid_constant__ PasteParams p) {
+// The rows an instance's window kernel CTAs own in FULL mode (they write every element of these rows,
+// the fill role none of them): region rows [wya, wyb), empty when the instance is not pasted at all.
+// Both roles of paste_fused_kernel call this, so they agree by construction.
+__device__ __forceinline__ bool window_rows(const PasteParams& p, int n, int& wya, int& wyb, int& wxa, int& wxb,
+                                            float4& bx) {
+    if (p.select && p.select[n] != p.select_value) return false;
+    bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
+    int xa, xb, ya, yb;
+    window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
+    window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
+    // window in region coordinates, clipped to the region
+    wya = max(ya - p.y_lo, 0); wyb = min(yb - p.y_lo, p.rh);
+    wxa = max(xa - p.x_lo, 0); wxb = min(xb - p.x_lo, p.rw);
+    return wya < wyb && wxa < wxb;
+}
+
+// zero `nbytes` bytes at `q` (any alignment) with one warp: 16-byte stores for the aligned middle
+__device__ __forceinline__ void warp_zero(unsigned char* q, int nbytes, int lane) {
+    if (nbytes <= 0) return;
+    const int head = min(nbytes, (int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(q) & 15u)) & 15u));
+    if (lane < head) q[lane] = 0;
+    q += head;
+    nbytes -= head;
+    const int nv = nbytes >> 4;
+    for (int i = lane; i < nv; i += 32) __stcs(reinterpret_cast<uint4*>(q) + i, make_uint4(0u, 0u, 0u, 0u));
+    if (lane < (nbytes & 15)) q[(nv << 4) + lane] = 0;
+}
+
+// FULL = false: only non-zero pixels of the window are written (the canvas was zeroed before).
+// FULL = true: every element of the window's ROWS is written -- zeros outside the window's columns and
+// where the sample misses the mask -- so the rows need no zero fill and the fill can run beside it.
+template <int MODE, bool FULL>
+__device__ __forceinline__ void paste_window_body(const PasteParams& p, int bxi, int nbx, int byi, int nby) {
     __shared__ __align__(16) float s_mask[kMaskStage];          // sigmoid(mask) rows, one-pixel zero border
     __shared__ __align__(8) float2 s_col[kColTab];              // per window column {VD index, wh}
     __shared__ __align__(8) float2 s_vd[kPasteThreads / 32][kVPairs];
     __shared__ __align__(16) float4 s_row[kBandRows];           // per band row {lo, wl, wh, state}
+    constexpr int ES = MODE == DM_PASTE_F32 ? 4 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int st_w = p.sw + 2;
     const int zero_i = p.sw + 1, nan_i = p.sw + 2;  // VD entries for "exactly zero" / "NaN" columns
     const long long T = (long long)p.rh * p.rw;
-    for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
-        if (p.select && p.select[n] != p.select_value) continue;  // CTA-uniform
-        const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
-        int xa, xb, ya, yb;
-        window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
-        // window in region coordinates, clipped to the region
-        const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
-        if (wya + (int)blockIdx.x * kBandRows >= wyb) continue;  // CTA-uniform: no band for this CTA
-        window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
-        const int wxa = max(xa - p.x_lo, 0), wxb = min(xb - p.x_lo, p.rw);
-        if (wxa >= wxb) continue;
-        // this CTA takes bands blockIdx.x, blockIdx.x + gridDim.x, ... of the window's rows
-      for (int r0 = wya + blockIdx.x * kBandRows; r0 < wyb; r0 += gridDim.x * kBandRows) {
+    for (int n = byi; n < p.N; n += nby) {
+        float4 bx;
+        int wya, wyb, wxa, wxb;
+        if (!window_rows(p, n, wya, wyb, wxa, wxb, bx)) continue;  // CTA-uniform
+        if (wya + bxi * kBandRows >= wyb) continue;                // CTA-uniform: no band for this CTA
+        // this CTA takes bands bxi, bxi + nbx, ... of the window's rows
+      for (int r0 = wya + bxi * kBandRows; r0 < wyb; r0 += nbx * kBandRows) {
         const int r1 = min(r0 + kBandRows, wyb);      // exclusive
         const long long cls = p.labels ? p.labels[n] : 0;
         const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
@@ -103,11 +132,18 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
             // geometry): taps from global memory
             Instance in;
             in.load(p, n);
-            for (int r = r0 + warp; r < r1; r += kPasteThreads / 32)
+            for (int r = r0 + warp; r < r1; r += kPasteThreads / 32) {
+                if (FULL) {
+                    unsigned char* row8 = reinterpret_cast<unsigned char*>(p.out) + (obase + (long long)r * p.rw) * ES;
+                    warp_zero(row8, wxa * ES, lane);
+                    warp_zero(row8 + (long long)wxb * ES, (p.rw - wxb) * ES, lane);
+                }
                 for (int c = wxa + lane; c < wxb; c += 32) {
                     const float v = in.eval(p.x_lo + c, p.y_lo + r);
-                    if (v != 0.0f) put<MODE>(p, obase + (long long)r * p.rw + c, v);
+                    if (FULL) put<MODE>(p, obase + (long long)r * p.rw + c, v != 0.0f ? v : 0.0f);
+                    else if (v != 0.0f) put<MODE>(p, obase + (long long)r * p.rw + c, v);
                 }
+            }
             continue;
         }
         __syncthreads();  // the scratch of the previous instance is no longer read
@@ -156,6 +192,15 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
         for (int r = r0 + warp; r < r1; r += kPasteThreads / 32) {
             const float4 rt = s_row[r - r0];
             const int rstate = __float_as_int(rt.w);
+            if (FULL) {
+                unsigned char* row8 = reinterpret_cast<unsigned char*>(p.out) + (obase + (long long)r * p.rw) * ES;
+                if (rstate == 0) {  // the row's samples miss the mask: all zeros
+                    warp_zero(row8, p.rw * ES, lane);
+                    continue;
+                }
+                warp_zero(row8, wxa * ES, lane);
+                warp_zero(row8 + (long long)wxb * ES, (p.rw - wxb) * ES, lane);
+            }
             if (rstate == 0) continue;  // warp-uniform
             __syncwarp();
             if (rstate == 1) {
@@ -177,10 +222,11 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
                 const float2 pr = vd[__float_as_int(e.x)];
                 const float v = fmaf(e.y, pr.y, pr.x);
                 if (MODE == DM_PASTE_F32) {
-                    if (v != 0.0f) reinterpret_cast<float*>(orow8)[c] = v;
+                    if (FULL) reinterpret_cast<float*>(orow8)[c] = v != 0.0f ? v : 0.0f;
+                    else if (v != 0.0f) reinterpret_cast<float*>(orow8)[c] = v;
                 } else {
                     const uint32_t b = encode<MODE>(v, p.thr);
-                    if (b) orow8[c] = (unsigned char)b;
+                    if (FULL || b) orow8[c] = (unsigned char)b;
                 }
             };
             if (use_tab) {
@@ -197,6 +243,75 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
         }
       }  // bands
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPasteThreads, 5)
+paste_window_kernel(const __grid_constant__ PasteParams p) {
+    paste_window_body<MODE, false>(p, (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, (int)gridDim.y);
+}
+
+// Zero fill and windows in ONE launch over disjoint rows.  Window CTAs (8 per instance slot, as in the
+// two-launch form) own every element of their instances' window rows; the zero fill of everything
+// else is dealt to the same CTAs in 64 KB tiles, which each CTA issues FIRST: the stores are
+// fire-and-forget, so they drain to HBM while the CTA goes on to its instruction-bound window work.
+// (A split into fill CTAs and window CTAs shares the 5 CTA slots of an SM between the two roles and
+// slows the window role down by what the fill role occupies: 183 us vs 227 us for two launches.)
+constexpr int kFillVecs = 16;                              // 16-byte stores per fill thread
+constexpr int kFillTile = kPasteThreads * kFillVecs * 16;   // bytes per fill tile (64 KB)
+
+template <int ES>
+__device__ __forceinline__ void fill_tile(const PasteParams& p, long long tile, long long nbytes) {
+    const long long t0 = tile * kFillTile;
+    const long long TB = (long long)p.rh * p.rw * ES;   // bytes per instance (>= kFillTile on this path)
+    // the tile touches at most two instances: their skipped byte ranges (window rows), absolute.
+    // Every thread derives them itself (two box loads, broadcast): no barrier here.
+    long long a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
+    {
+        const long long n = t0 / TB;
+        float4 bx;
+        int wya, wyb, wxa, wxb;
+        if (n < p.N && window_rows(p, (int)n, wya, wyb, wxa, wxb, bx)) {
+            a_lo = n * TB + (long long)wya * p.rw * ES;
+            a_hi = n * TB + (long long)wyb * p.rw * ES;
+        }
+        if (n + 1 < p.N && (n + 1) * TB < t0 + kFillTile && window_rows(p, (int)n + 1, wya, wyb, wxa, wxb, bx)) {
+            b_lo = (n + 1) * TB + (long long)wya * p.rw * ES;
+            b_hi = (n + 1) * TB + (long long)wyb * p.rw * ES;
+        }
+    }
+    unsigned char* const out8 = reinterpret_cast<unsigned char*>(p.out);
+    // CTA-uniform fast paths: a tile wholly inside window rows has nothing to do, a whole tile clear
+    // of them is 16 plain streaming stores per thread; only tiles on a boundary test every vector
+    const long long t1 = min(t0 + kFillTile, nbytes);
+    if ((t0 >= a_lo && t1 <= a_hi) || (t0 >= b_lo && t1 <= b_hi)) return;
+    if (t1 - t0 == kFillTile && (t1 <= a_lo || t0 >= a_hi) && (t1 <= b_lo || t0 >= b_hi)) {
+        uint4* q = reinterpret_cast<uint4*>(out8 + t0) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < kFillVecs; ++k) __stcs(q + k * kPasteThreads, make_uint4(0u, 0u, 0u, 0u));
+        return;
+    }
+#pragma unroll 4
+    for (int k = 0; k < kFillVecs; ++k) {
+        const long long o = t0 + ((long long)k * kPasteThreads + threadIdx.x) * 16;
+        if (o >= nbytes) break;
+        const long long e = min(o + 16, nbytes);
+        if ((o >= a_lo && e <= a_hi) || (o >= b_lo && e <= b_hi)) continue;          // inside window rows
+        if (e - o == 16 && (e <= a_lo || o >= a_hi) && (e <= b_lo || o >= b_hi)) {   // clear of them
+            __stcs(reinterpret_cast<uint4*>(out8 + o), make_uint4(0u, 0u, 0u, 0u));
+            continue;
+        }
+        for (long long q = o; q < e; ++q)
+            if (!(q >= a_lo && q < a_hi) && !(q >= b_lo && q < b_hi)) out8[q] = 0;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPasteThreads, 5)
+paste_fused_kernel(const __grid_constant__ PasteParams p, int win_y, long long n_fill, long long nbytes) {
+    constexpr int ES = MODE == DM_PASTE_F32 ? 4 : 1;
+    for (long long tile = blockIdx.x; tile < n_fill; tile += gridDim.x) fill_tile<ES>(p, tile, nbytes);
+    paste_window_body<MODE, true>(p, (int)(blockIdx.x % kBandCtas), kBandCtas, (int)(blockIdx.x / kBandCtas), win_y);
 }
 
 }  // namespace dm
@@ -240,6 +355,22 @@ static int paste_impl(const float* masks, int64_t mask_stride_n, int64_t mask_st
     p.total = per_inst * N;
     const int ES = out_mode == DM_PASTE_F32 ? 4 : 1;
     cudaStream_t st = (cudaStream_t)stream;
+    const long long nbytes_all = p.total * ES;
+    const char* fenv = getenv("DM_PASTE_FUSED");
+    const bool fused = zero_fill && per_inst * ES >= dm::kFillTile && !(fenv && *fenv == '0');
+    if (fused) {
+        // one launch: every CTA issues its share of the zero fill, then pastes its window bands
+        const int win_y = N < 65535 ? N : 65535;
+        const unsigned n_win = (unsigned)(dm::kBandCtas * win_y);
+        const long long n_fill = (nbytes_all + dm::kFillTile - 1) / dm::kFillTile;
+        switch (out_mode) {
+            case DM_PASTE_BOOL: dm::paste_fused_kernel<DM_PASTE_BOOL><<<n_win, dm::kPasteThreads, 0, st>>>(p, win_y, n_fill, nbytes_all); break;
+            case DM_PASTE_U8: dm::paste_fused_kernel<DM_PASTE_U8><<<n_win, dm::kPasteThreads, 0, st>>>(p, win_y, n_fill, nbytes_all); break;
+            default: dm::paste_fused_kernel<DM_PASTE_F32><<<n_win, dm::kPasteThreads, 0, st>>>(p, win_y, n_fill, nbytes_all); break;
+        }
+        DM_LAUNCH_CHECK("dm_paste_masks/fused");
+        return DM_OK;
+    }
     if (zero_fill) {
         const long long nbytes = p.total * ES, n16 = nbytes / 16;
         const long long blocks = (n16 + 1 + 255) / 256;
