@@ -89,8 +89,24 @@ def get_seg_masks(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape, s
     """
     im_mask = paste_masks_in_image(mask_pred, det_bboxes, det_labels,
                                    rcnn_test_cfg.mask_thr_binary, ori_shape, scale_factor, rescale)
-    host = im_mask.cpu().numpy()
+    host = _to_host(im_mask)
     return [host[i] for i in range(host.shape[0])]
+
+
+def _to_host(t):
+    """One device->host copy into PINNED memory (torch's caching host allocator hands the block back
+    on the next call once the previous results are dropped): ~50 GB/s instead of the ~2 GB/s of a
+    pageable ``.cpu()`` for the 107 MB of canvases of one 100-detection image.  The returned array is
+    a view of the pinned tensor and keeps it alive."""
+    if t.numel() == 0:
+        return t.cpu().numpy()
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:      # pinned memory exhausted: pageable copy, as the reference does
+        return t.cpu().numpy()
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 def get_seg_masks_rle(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape, scale_factor,
@@ -178,7 +194,7 @@ def get_seg_masks_switched(stage_instance_preds, mask_labels, det_bboxes, det_la
     mode, t = (_ops.PASTE_BOOL, float(thr)) if thr >= 0 else (_ops.PASTE_U8, 0.0)
     im_mask = _ops.paste_masks_switched([p.to(torch.float32) for p in stage_instance_preds], bucket, bboxes.float(),
                                         labels, int(img_h), int(img_w), True, t, mode)
-    host = im_mask.cpu().numpy()
+    host = _to_host(im_mask)
     return [host[i] for i in range(host.shape[0])]
 
 
