@@ -1591,11 +1591,18 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
         cg = cg < 1 ? 1 : pw2;
         cg = cg < 16 ? 16 : (cg > 256 ? 256 : cg);
         if (nb == 1 && K > 0) {
-            // a single small bucket (inference: ~100 detections): split channels further so that the
-            // persistent grid still has a few units per CTA
-            const long long want = 6ll * sm_count();
+            // a single small bucket (one extractor call of a training step, ~100 detections at
+            // inference): the RoIs' patches differ by orders of magnitude in area, so the biggest
+            // units set the launch time -- split channels until the persistent grid has ~24 units per
+            // SM, but never below what one pass of a CTA's warps covers (8 warps x channels per warp).
+            // Measured on the C3 extractor calls (tools/c3_breakdown.py): 7x7 x 1024 RoIs bwd 0.89 ->
+            // 0.54 ms, 56x56 single-level x 256 RoIs fwd 1.33 -> 0.78 ms.
+            const int pwv_guess = (d.pw % 4 == 0) ? d.pw / 4 : ((d.pw % 2 == 0) ? d.pw / 2 : d.pw);
+            const int cpw_guess = pwv_guess >= 32 ? 1 : 32 / pwv_guess;
+            const int cg_min = 8 * (cpw_guess > 4 ? 4 : cpw_guess);
+            const long long want = (long long)env_int("DM_RA_WANT", 24) * sm_count();
             int small = 256;
-            while (small > 16 && (long long)K * ((p.C + small - 1) / small) < want) small >>= 1;
+            while (small > cg_min && (long long)K * ((p.C + small - 1) / small) < want) small >>= 1;
             if (small < cg) cg = small;
         }
         cg = env_int("DM_RA_CG", 0) > 0 ? env_int("DM_RA_CG", 0) : cg;
