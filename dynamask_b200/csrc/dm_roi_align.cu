@@ -108,6 +108,7 @@ struct RaParams {
     // dynamic scheduling: one ticket counter per bucket (zeroed before the launch), NULL = static
     // round-robin ownership
     unsigned* tickets;
+    float bias;      // how much later (per bucket rank) the smaller buckets are paced
 };
 
 // Ticket counters of the launches in flight: a ring of slots in device memory, one slot per launch
@@ -1489,26 +1490,41 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
         // patch is 0.1 ... 1 MB whatever it is pooled to), and with static ownership the SMs were
         // active for only 88 % (forward) / 92 % (backward) of the launch (ncu sm__cycles_active
         // avg / elapsed).  A CTA takes its next unit from the bucket that is globally least advanced
-        // (same fractional pace for every bucket, as in the static interleaved walk; the smaller
-        // buckets are held back by a few percent so that the launch ends on small units).
+        // (same fractional pace for every bucket, as in the static interleaved walk; holding the smaller
+        // buckets back so that the launch ends on small units was measured and does not pay).
         __shared__ int s_next[2];
+        // thread 0's view: units this CTA has taken per bucket, buckets found exhausted.  Pacing by the
+        // CTA's own counts (every CTA ends up with ~1/grid of each bucket) costs one L2 round trip per
+        // unit -- the ticket -- instead of two (reading the global counters first).
+        int taken[DM_MAX_BUCKETS];
+        unsigned gone = 0u;
+        for (int j = 0; j < DM_MAX_BUCKETS; ++j) taken[j] = 0;
         auto fetch = [&]() {   // thread 0
             for (;;) {
                 int jsel = -1;
                 float best = 0.0f;
-                for (int j = 0; j < p.nb; ++j) {
+#pragma unroll
+                for (int j = 0; j < DM_MAX_BUCKETS; ++j) {
+                    if (j >= p.nb || ((gone >> j) & 1u)) continue;
                     const int b = p.order[j];
                     const unsigned n = (unsigned)(s_seg[b + 1] - s_seg[b]) * (unsigned)p.bk[b].nslab;
-                    const unsigned c = *reinterpret_cast<volatile unsigned*>(p.tickets + j);
-                    if (c >= n) continue;
-                    const float key = p.interleave ? ((float)c + 0.5f) / (float)n * (1.0f + 0.04f * (float)j) : (float)j;
+                    if (n == 0u) { gone |= 1u << j; continue; }
+                    const float key = p.interleave ? ((float)taken[j] + 0.5f) / (float)n * (1.0f + p.bias * (float)j) : (float)j;
                     if (jsel < 0 || key < best) { jsel = j; best = key; }
                 }
                 if (jsel < 0) { s_next[0] = -1; return; }
                 const int b = p.order[jsel];
                 const unsigned n = (unsigned)(s_seg[b + 1] - s_seg[b]) * (unsigned)p.bk[b].nslab;
                 const unsigned t = atomicAdd(p.tickets + jsel, 1u);
-                if (t < n) { s_next[0] = jsel; s_next[1] = (int)t; return; }
+                if (t < n) {
+#pragma unroll
+                    for (int j = 0; j < DM_MAX_BUCKETS; ++j)
+                        if (j == jsel) ++taken[j];
+                    s_next[0] = jsel;
+                    s_next[1] = (int)t;
+                    return;
+                }
+                gone |= 1u << jsel;
             }
         };
         if (threadIdx.x == 0) fetch();
@@ -1716,6 +1732,7 @@ static int launch(RaParams& p, cudaStream_t st, const char* where) {
     if (occ < 1) return DM_EUNSUPPORTED;
     const int grid = sm_count() * occ;
     p.tickets = nullptr;
+    p.bias = 0.001f * (float)env_int("DM_RA_BIAS", 0);
     if (env_int("DM_RA_DYNAMIC", 1)) {
         static std::atomic<unsigned> seq{0};
         void* base = nullptr;
