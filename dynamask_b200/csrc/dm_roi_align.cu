@@ -59,6 +59,11 @@ namespace dm {
 #ifndef DM_BWD_REGS
 #define DM_BWD_REGS 128
 #endif
+#ifndef DM_BWD_DYNAMIC
+#define DM_BWD_DYNAMIC 0   // dynamic unit scheduling in the backward: measured 8.32 ms vs 8.25 ms static on the same box
+                           // (it evens out the SMs -- 96 % active instead of 92 % -- but the launch time does not follow); the
+                           // forward defaults to dynamic (6.61 vs 7.58 ms)
+#endif
 constexpr int kBwdThreads = DM_BWD_THREADS;   // backward: 2 CTAs/SM x 8 warps at 128 registers
 #ifndef DM_FWD_THREADS
 #define DM_FWD_THREADS 256
@@ -1478,14 +1483,14 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // ---------------------------------------------------------------------------------------------
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
-template <bool BWD>
+template <bool BWD, bool DYN>
 __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __grid_constant__ RaParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
     if (threadIdx.x <= p.nb) s_seg[threadIdx.x] = p.seg ? p.seg[threadIdx.x] : (threadIdx.x == 0 ? 0 : p.K);
     __syncthreads();
-    if (p.tickets) {
+    if (DYN) {
         // Dynamic scheduling.  The per-unit work differs by more than an order of magnitude (a RoI's
         // patch is 0.1 ... 1 MB whatever it is pooled to), and with static ownership the SMs were
         // active for only 88 % (forward) / 92 % (backward) of the launch (ncu sm__cycles_active
@@ -1496,16 +1501,18 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
         // thread 0's view: units this CTA has taken per bucket, buckets found exhausted.  Pacing by the
         // CTA's own counts (every CTA ends up with ~1/grid of each bucket) costs one L2 round trip per
         // unit -- the ticket -- instead of two (reading the global counters first).
-        int taken[DM_MAX_BUCKETS];
-        unsigned gone = 0u;
-        for (int j = 0; j < DM_MAX_BUCKETS; ++j) taken[j] = 0;
+        __shared__ int taken[DM_MAX_BUCKETS];   // touched by thread 0 only (kept out of its registers)
+        __shared__ unsigned gone;
+        if (threadIdx.x == 0) {
+            gone = 0u;
+            for (int j = 0; j < DM_MAX_BUCKETS; ++j) taken[j] = 0;
+        }
         auto fetch = [&]() {   // thread 0
             for (;;) {
                 int jsel = -1;
                 float best = 0.0f;
-#pragma unroll
-                for (int j = 0; j < DM_MAX_BUCKETS; ++j) {
-                    if (j >= p.nb || ((gone >> j) & 1u)) continue;
+                for (int j = 0; j < p.nb; ++j) {
+                    if ((gone >> j) & 1u) continue;
                     const int b = p.order[j];
                     const unsigned n = (unsigned)(s_seg[b + 1] - s_seg[b]) * (unsigned)p.bk[b].nslab;
                     if (n == 0u) { gone |= 1u << j; continue; }
@@ -1517,9 +1524,7 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
                 const unsigned n = (unsigned)(s_seg[b + 1] - s_seg[b]) * (unsigned)p.bk[b].nslab;
                 const unsigned t = atomicAdd(p.tickets + jsel, 1u);
                 if (t < n) {
-#pragma unroll
-                    for (int j = 0; j < DM_MAX_BUCKETS; ++j)
-                        if (j == jsel) ++taken[j];
+                    ++taken[jsel];
                     s_next[0] = jsel;
                     s_next[1] = (int)t;
                     return;
@@ -1726,21 +1731,24 @@ static int launch(RaParams& p, cudaStream_t st, const char* where) {
     const int smem_bytes = smem_kb * 1024;
     const int threads = BWD ? kBwdThreads : kFwdThreads;
     p.smem_floats = smem_bytes / 4;
-    DM_CUDA_CHECK(cudaFuncSetAttribute(ra_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
+    // static and dynamic scheduling are separate instantiations (each with its own register allocation)
+    const bool dyn = env_int(BWD ? "DM_RA_BWD_DYNAMIC" : "DM_RA_FWD_DYNAMIC", BWD ? DM_BWD_DYNAMIC : 1) != 0;
+    auto kern = dyn ? ra_kernel<BWD, true> : ra_kernel<BWD, false>;
+    DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
     int occ = 0;
-    DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_kernel<BWD>, threads, smem_bytes), where);
+    DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem_bytes), where);
     if (occ < 1) return DM_EUNSUPPORTED;
     const int grid = sm_count() * occ;
     p.tickets = nullptr;
     p.bias = 0.001f * (float)env_int("DM_RA_BIAS", 0);
-    if (env_int("DM_RA_DYNAMIC", 1)) {
+    if (dyn) {
         static std::atomic<unsigned> seq{0};
         void* base = nullptr;
         DM_CUDA_CHECK(cudaGetSymbolAddress(&base, g_ra_tickets), where);
         p.tickets = reinterpret_cast<unsigned*>(base) + (size_t)(seq.fetch_add(1u, std::memory_order_relaxed) % kTicketSlots) * DM_MAX_BUCKETS;
         DM_CUDA_CHECK(cudaMemsetAsync(p.tickets, 0, sizeof(unsigned) * DM_MAX_BUCKETS, st), where);
     }
-    ra_kernel<BWD><<<grid, threads, smem_bytes, st>>>(p);
+    kern<<<grid, threads, smem_bytes, st>>>(p);
     DM_LAUNCH_CHECK(where);
     return DM_OK;
 }
