@@ -3,9 +3,12 @@
  * DynaMask per-instance mask hot path.
  *
  * This is the drop-in boundary.  Every entry point takes plain device
- * pointers, sizes and a CUDA stream; no torch / ATen types cross it.  The library owns no
- * memory and holds no mutable global state: every buffer (inputs, outputs, scratch) belongs to
- * the caller, every call is asynchronous on `stream` and re-entrant across streams.
+ * pointers, sizes and a CUDA stream; no torch / ATen types cross it.  The library allocates no
+ * memory: every buffer (inputs, outputs, scratch) belongs to the caller, every call is
+ * asynchronous on `stream` and re-entrant across streams.  Its only state is the thread-local
+ * error text, a launch counter, and a static ring of 512 work-ticket slots in device memory of
+ * which each dm_roi_align_fwd launch takes the next one (zeroed on `stream` before the kernel), so
+ * at most 512 such launches may be in flight at once per process and device.
  *
  * Reference interfaces replaced (paths relative to the reference tree, lslrh/DynaMask):
  *   dm_assign          <- SingleRoIExtractor.map_roi_levels
