@@ -109,6 +109,34 @@ def algorithmic_bytes(rois, lvl, bucket, shapes, batch, channels):
 
 
 # ----------------------------------------------------------------------------------------------
+# host placement for the e2e leg
+# ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs NVML lists as local to its GPU, so that the pinned staging buffers
+    of the e2e leg are allocated on (first touched from) the GPU's own NUMA node: with several ranks
+    on one host the device<->host copies otherwise cross the socket interconnect.  Returns the
+    number of CPUs bound to, or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        phys = index
+        if vis and all(v.strip().isdigit() for v in vis.split(',')) and index < len(vis.split(',')):
+            phys = int(vis.split(',')[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------
 # clocks sampler
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -440,8 +468,15 @@ def main():
 
     # ---- e2e: plugin surface with host buffers -------------------------------------------------
     if not args.no_e2e:
+        # the e2e leg runs on the CPUs local to this rank's GPU (pinned staging buffers on the GPU's NUMA
+        # node); the affinity is restored afterwards so that the CPU baseline leg sees every core
+        aff0 = os.sched_getaffinity(0)
+        numa = bind_to_gpu_numa_node(local)
         e2e = run_e2e(args, dm, dev, rank, world, feats, rois_h, onehot_h, counts)
+        os.sched_setaffinity(0, aff0)
         line['e2e'] = e2e
+        if numa:
+            line['e2e']['cpus_bound_per_rank'] = numa
     del feats
     torch.cuda.empty_cache()
 
