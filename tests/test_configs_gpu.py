@@ -148,3 +148,37 @@ def test_c5_dense_small_instances_1024x2048():
     agree = sum(int((a == b).sum()) for a, b in zip(out, ref))
     assert agree / (n * img_h * img_w) >= 0.9999, agree / (n * img_h * img_w)
     assert sum(int(a.sum()) for a in out) > 0
+
+
+# ------------------------------------------------------------------------------------------
+# scheduling state of the library: the forward deals its work units through a ring of 512 ticket
+# slots in device memory (one per launch) -- wrap-around and concurrent streams must not interfere
+# ------------------------------------------------------------------------------------------
+def test_forward_ticket_slots_wrap_and_streams_do_not_interfere():
+    g = gen(601)
+    feats = synth.make_features(1, 8, 800, 1344, g)
+    fc = [f.cuda() for f in feats]
+    rois_a = synth.make_rois(1, 96, 800, 1344, g).cuda()
+    rois_b = synth.make_rois(1, 64, 800, 1344, g).cuda()
+    onehot_a = synth.make_onehot(96, g).cuda()
+    onehot_b = synth.make_onehot(64, g).cuda()
+    ext = dm().BucketedRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), 8, STRIDES)
+    ref_a = [t.clone() for t in ext.forward_bucketed(fc, rois_a, onehot_a).feats]
+    ref_b = [t.clone() for t in ext.forward_bucketed(fc, rois_b, onehot_b).feats]
+    # more launches than the ring has slots, alternating two streams that overlap on the device
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for it in range(300):
+        with torch.cuda.stream(s1):
+            ra = ext.forward_bucketed(fc, rois_a, onehot_a).feats
+        with torch.cuda.stream(s2):
+            rb = ext.forward_bucketed(fc, rois_b, onehot_b).feats
+        if it % 50 == 49 or it == 299:
+            outs.append((ra, rb))
+    torch.cuda.synchronize()
+    for ra, rb in outs:
+        for x, y in zip(ra, ref_a):
+            assert torch.equal(x, y)
+        for x, y in zip(rb, ref_b):
+            assert torch.equal(x, y)
