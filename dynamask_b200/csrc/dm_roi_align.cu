@@ -644,7 +644,7 @@ __device__ __forceinline__ int fwd_row_stride(int X0, int X1, int cw, int jw, in
     return (fwp + jw - 1 + 3) & ~3;     // + zero pad for the padded taps
 }
 
-// Register budget matters here (96 registers without spills in the row loop): offsets are 32-bit (one
+// Register budget matters here (no spills in the row loop): offsets are 32-bit (one
 // level's map and one RoI's pooled block are far below 2^31 floats), every lane owns at most one
 // copy per patch row (the caller keeps cpw * copies-per-row <= 32), and only scalars cross the
 // call boundary.
@@ -725,7 +725,7 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     const float* pr = ring + subc * a.fws - a.X0a;  // this lane's channel in the slot being read next
     int r_slot = 0;
 #if DM_FWD_HOIST
-    // strip constants in registers (the kernel is built for 128 registers: 2 CTAs x 7 warps still fit)
+    // strip constants in registers (the kernel is built for 128 registers: 2 CTAs x 8 warps fill the file)
     int xo_r[VEC];
     float wx_r[JW <= 4 ? JW : 1][VEC];
     if (JW <= 4) {
