@@ -331,3 +331,21 @@ def test_rle_compress_batch_host_equals_per_instance_strings():
     assert lib.dm_rle_compress_batch_host(ctypes.c_void_p(flat.ctypes.data), ctypes.c_void_p(offs.ctypes.data),
                                           len(masks), h * w, ctypes.c_void_p(buf.ctypes.data), 3,
                                           ctypes.c_void_p(so.ctypes.data)) == -1
+
+
+def test_bench_helpers_degrade_without_a_gpu():
+    """bench.py's host helpers must not fail (or change the process) where there is no NVML / GPU:
+    the NUMA binding returns None and leaves the affinity alone, the clock sampler reports why it has
+    no samples."""
+    import bench
+    aff = os.sched_getaffinity(0)
+    got = bench.bind_to_gpu_numa_node(0)
+    if got is None:
+        assert os.sched_getaffinity(0) == aff
+    else:                                   # a GPU box: bound to a non-empty subset
+        assert 0 < got <= len(aff)
+        os.sched_setaffinity(0, aff)
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
