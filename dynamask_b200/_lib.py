@@ -24,9 +24,9 @@ SIGNATURES = {
     'dm_launch_count': (_i64, []),
     'dm_assign': (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     'dm_roi_align_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp,
-                              _i, _i, _vp]),
+                              _i, _i, _vp, _vp]),
     'dm_roi_align_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp,
-                              _i, _i, _i, _vp]),
+                              _i, _i, _i, _vp, _vp]),
     'dm_paste_masks': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
                             _i, _vp, _vp]),
     'dm_paste_masks_select': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
@@ -39,8 +39,8 @@ SIGNATURES = {
     'dm_rle_compress_batch_host': (_i64, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     'dm_polygon_target': (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     'dm_refine_stages': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
-    'dm_simple_roi_align_fwd': (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
-    'dm_simple_roi_align_bwd': (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    'dm_simple_roi_align_fwd': (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    'dm_simple_roi_align_bwd': (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -40,6 +40,11 @@
 #include <atomic>
 #include <climits>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is
+                    // resolved through cudaGetDriverEntryPoint, the library does not link libcuda
 
 #include "dm_common.cuh"
 
@@ -97,6 +102,23 @@ struct BucketDesc {
                 // dense rows, 16-byte aligned planes
 };
 
+// Patch loads by TMA (cp.async.bulk.tensor.3d): one tensor map per (pyramid level, box-width class).
+// A box is kTmaCh channels x BH patch rows x BW columns of one image, BW the smallest class that
+// covers the patch from its first column rounded down to a 16-byte boundary, BH = 8 rows for
+// BW <= 32 and 4 above, so a box is at most 4 KB.
+constexpr int kTmaCh = 4;           // channels per box = channels per warp pass on this path
+constexpr int kNumBW = 10;
+__host__ __device__ constexpr int tma_bw(int cls) {
+    return cls == 0 ? 8 : cls == 1 ? 12 : cls == 2 ? 16 : cls == 3 ? 20 : cls == 4 ? 24 : cls == 5 ? 28
+         : cls == 6 ? 32 : cls == 7 ? 40 : cls == 8 ? 48 : 64;
+}
+__host__ __device__ constexpr int tma_bh(int cls) { return cls <= 6 ? 8 : 4; }
+constexpr int kTmaMaxBW = 64;
+constexpr int kTmaMaxSlots = 4;     // chunk slots per warp (ring depth)
+struct alignas(64) TmaMaps {
+    CUtensorMap m[DM_MAX_LEVELS][kNumBW];
+};
+
 struct RaParams {
     LevelDesc lv[DM_MAX_LEVELS];
     BucketDesc bk[DM_MAX_BUCKETS];
@@ -114,13 +136,12 @@ struct RaParams {
     // round-robin ownership
     unsigned* tickets;
     float bias;      // how much later (per bucket rank) the smaller buckets are paced
+    // TMA patch loads: bit c of tma_mask[l] = level l has a tensor map for width class c;
+    // tma_rowmajor = 1: boxes land as [row][channel][BW] (tensor dims W, C*N, H), 0: [channel][row][BW]
+    unsigned tma_mask[DM_MAX_LEVELS];
+    int tma_rowmajor;
+    int tma_slots;   // ring depth wanted (2 .. kTmaMaxSlots)
 };
-
-// Ticket counters of the launches in flight: a ring of slots in device memory, one slot per launch
-// (zeroed by a memset node in front of the kernel).  The library allocates nothing at run time; the
-// ring only bounds how many RoIAlign launches may be in flight at once before a slot is reused.
-constexpr int kTicketSlots = 512;
-__device__ unsigned g_ra_tickets[kTicketSlots][DM_MAX_BUCKETS];
 
 // exact n / d whenever n * d < 2^32 (indices here are far below that)
 struct FastDiv {
@@ -283,6 +304,16 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// Tiled TMA load of one 3-D box global -> shared (SASS: UTMALDG.3D), completion counted in bytes
+// on an mbarrier.  `map` points at a CUtensorMap in kernel-parameter space (__grid_constant__).
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void* map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
@@ -837,6 +868,202 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Forward, TMA path: the same warp-autonomous strip walk, but the warp's patches arrive as TMA box
+// loads -- one cp.async.bulk.tensor.3d per chunk of BH patch rows x 4 channels x BW columns,
+// issued by lane 0 into a ring of chunk slots and signalled on one mbarrier per slot -- instead of
+// one 16-byte cp.async per lane and patch row.  The steady state has no copy bookkeeping in the
+// row loop: per chunk one parity wait, one warp barrier and (lane 0) one expect_tx + one TMA.
+// The last chunk of a channel batch is shifted up so that it ends on the patch's last row (the rows
+// it repeats come from L2 and are skipped), so nothing below the patch is fetched.
+// Requires Pw / VEC <= 8 (four channels per warp pass), fw <= 64, JX, JY <= JW.
+// ---------------------------------------------------------------------------------------------
+struct FwdTmaArgs {
+    const void* map;     // tensor map of (level, width class), kernel-parameter space
+    float* obase;        // pooled element (i, c0, 0, 0)
+    const float* ytab;   // packed Y records (shared)
+    const int* rcnt;     // pooled rows per patch row (shared)
+    const int* xs;       // first feature column of every pooled column (shared)
+    const float* wx;     // folded X weights [JW][Pw] (shared)
+    float* ring;         // this warp's chunk slots (shared, 128-byte aligned) followed by a zeroed pad
+    unsigned bar_sa;     // shared address of this warp's first mbarrier (one per slot)
+    unsigned* phase;     // this warp's parity bits, carried from unit to unit (shared)
+    int osC, osH;        // pooled strides in floats
+    int Pw, Ph, R, X0, Y0, BW, BH, nslot, nc;   // X0: first column of the boxes (multiple of 4)
+    int cidx0;           // tensor coordinate of channel c0 of this RoI's image: batch * C + c0
+    int chs, rws;        // floats between channels / between rows inside a slot
+};
+
+template <int VEC, int JW>
+__device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PwV = a.Pw / VEC;
+    const int R = a.R, BH = a.BH, nc = a.nc, nslot = a.nslot;
+    const int sub = lane / PwV, pv = lane - sub * PwV;
+    const bool lane_on = sub < kTmaCh;
+    const int subc = lane_on ? sub : 0;
+    const float* __restrict__ ytab = a.ytab;
+    const int* __restrict__ rcnt = a.rcnt;
+    float* const ring = a.ring;
+    __builtin_assume(__isShared(ytab));
+    __builtin_assume(__isShared(rcnt));
+    __builtin_assume(__isShared(ring));
+    __builtin_assume(__isShared(a.xs));
+    __builtin_assume(__isShared(a.wx));
+    __builtin_assume(__isShared(a.phase));
+    const int step = RA_WARPS * kTmaCh;
+    const int rws = a.rws;
+    const int slotf = kTmaCh * a.BW * BH;                  // floats per slot
+    const unsigned slot_bytes = (unsigned)slotf * 4u;
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+    // the padded taps of the last channel's last row run past the ring: that pad must be finite
+    if (lane < 8) ring[nslot * slotf + lane] = 0.0f;
+    const int nchunk = (R + BH - 1) / BH;                  // chunks per channel batch
+    const int last_shift = R >= BH ? nchunk * BH - R : 0;  // rows the last chunk repeats
+    const int nbatch = warp * kTmaCh < nc ? (nc - warp * kTmaCh + step - 1) / step : 0;
+    const int q_total = nbatch * nchunk;
+    unsigned par = *a.phase;
+    __syncwarp();
+
+    // ---- producer side (warp-uniform bookkeeping, lane 0 issues) -------------------------------
+    int q_issue = 0, i_k = 0, i_slot = 0;
+    int i_c = a.cidx0 + warp * kTmaCh;                     // channel coordinate of the next chunk
+    auto issue = [&]() {
+        if (q_issue < q_total) {
+            if (lane == 0) {
+                const unsigned bar = a.bar_sa + 8u * (unsigned)i_slot;
+                const int y = a.Y0 + i_k * BH - (i_k == nchunk - 1 ? last_shift : 0);
+                mbar_expect_tx(bar, slot_bytes);
+                const bool rowmajor = a.rws > a.chs;   // tensor dims (x, channel, y) or (x, y, channel)
+                tma_load_3d(ring_sa + (unsigned)i_slot * slot_bytes, a.map, a.X0, rowmajor ? i_c : y, rowmajor ? y : i_c, bar);
+            }
+            ++q_issue;
+            if (++i_k == nchunk) { i_k = 0; i_c += step; }
+            i_slot = i_slot + 1 == nslot ? 0 : i_slot + 1;
+        }
+    };
+    // ---- consumer side ------------------------------------------------------------------------
+    int q_cons = 0, c_k = 0, c_slot = 0, rows_left = 0;
+    const float* pr = ring;   // first float of the current patch row's channel 0 (warp-uniform)
+    auto acquire = [&]() {    // the next chunk of the stream becomes current
+        if (q_cons > 0) {     // the slot just drained takes the next request
+            __syncwarp();
+            issue();
+        }
+        mbar_wait(a.bar_sa + 8u * (unsigned)c_slot, (par >> c_slot) & 1u);
+        par ^= 1u << c_slot;
+        const int skip = c_k == nchunk - 1 ? last_shift : 0;
+        rows_left = min(BH, R) - skip;
+        pr = ring + c_slot * slotf + skip * rws;
+        c_slot = c_slot + 1 == nslot ? 0 : c_slot + 1;
+        ++q_cons;
+        if (++c_k == nchunk) c_k = 0;
+    };
+    // strip constants: first patch column (as an offset inside a slot row) and X weights of this
+    // lane's VEC pooled columns
+    int xo_r[VEC];
+    {
+        int xs_l[VEC];
+        ld_vec_i<VEC>(a.xs + (lane_on ? pv * VEC : 0), xs_l);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) xo_r[e] = xs_l[e] - a.X0 + subc * a.chs;
+    }
+    const float* const wxp = a.wx + (lane_on ? pv * VEC : 0);
+    float wx_r[JW <= 4 ? JW : 1][VEC];
+    if (JW <= 4) {
+#pragma unroll
+        for (int j = 0; j < (JW <= 4 ? JW : 1); ++j) ld_vec<VEC>(wxp + j * a.Pw, wx_r[j]);
+    }
+    auto consume = [&](float (&v)[VEC]) {
+        if (rows_left == 0) acquire();
+        --rows_left;
+#pragma unroll
+        for (int j = 0; j < JW; ++j) {
+            float wj[VEC], pj[VEC];
+            if (JW <= 4) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) wj[e] = wx_r[JW <= 4 ? j : 0][e];
+            } else {
+                ld_vec<VEC>(wxp + j * a.Pw, wj);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) pj[e] = pr[xo_r[e] + j];
+            if (VEC == 1) {
+                v[0] = j == 0 ? wj[0] * pj[0] : v[0] + wj[0] * pj[0];
+            } else {
+#pragma unroll
+                for (int e = 0; e + 1 < VEC; e += 2) {
+                    const float2 r = j == 0 ? fmul2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]))
+                                            : ffma2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]), make_float2(v[e], v[e + 1]));
+                    v[e] = r.x;
+                    v[e + 1] = r.y;
+                }
+            }
+        }
+        pr += rws;
+    };
+    auto skip_rows = [&](int n) {   // rows of this batch the walk does not need
+        while (n > 0) {
+            if (rows_left == 0) acquire();
+            const int m = min(n, rows_left);
+            rows_left -= m;
+            pr += m * rws;
+            n -= m;
+        }
+    };
+    for (int d = 0; d < nslot; ++d) issue();
+
+    constexpr int YS = 2 * JW;
+    float* o_cb = a.obase + (warp * kTmaCh + subc) * a.osC + pv * VEC;
+    for (int cb = warp * kTmaCh; cb < nc; cb += step, o_cb += step * a.osC) {
+        const bool on = lane_on && sub < nc - cb;
+        float win[JW][VEC];
+#pragma unroll
+        for (int j = 0; j < JW; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) win[j][e] = 0.0f;
+        int used = 0;   // patch rows of this batch consumed so far
+        float* o = o_cb;
+        const float* yrec = ytab;
+        int left = a.Ph;
+        // patch-row major: the window slides one patch row per step (the first JW - 1 steps only
+        // fill it); all pooled rows whose band starts at `base` share one window
+        for (int base = 1 - JW;; ++base) {
+#pragma unroll
+            for (int j = 0; j + 1 < JW; ++j)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
+            if (base + JW - 1 < R) {
+                consume(win[JW - 1]);
+                ++used;
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) win[JW - 1][e] = 0.0f;
+            }
+            if (base < 0) continue;
+            const int n = rcnt[base];
+#pragma unroll 2
+            for (int k = 0; k < n; ++k) {
+                float2 w[JW];
+                load_yrec<JW>(yrec, w);
+                yrec += YS;
+                float acc[VEC];
+                vmul<VEC>(acc, w[0], win[0]);
+#pragma unroll
+                for (int j = 1; j < JW; ++j) vfma<VEC>(acc, w[j], win[j]);
+                if (on) st_stream_vec<VEC>(o, acc);
+                o += a.osH;
+            }
+            left -= n;
+            if (left <= 0) break;
+        }
+        skip_rows(R - used);   // keep the stream aligned: every batch spans exactly R rows
+    }
+    // every requested chunk has been waited for: nothing is in flight when the slots are reused
+    __syncwarp();
+    if (lane == 0) *a.phase = par;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Forward, generic path (bands wider than 8, or bands too tall for one tile): two passes through
 // shared memory, pooled rows processed in tiles [p0, p1).
 // ---------------------------------------------------------------------------------------------
@@ -896,8 +1123,15 @@ __device__ DM_COLD void fwd_tile(const LevelDesc& Lv, const BucketDesc& B, const
     }
 }
 
+// per-CTA state of the TMA path: one mbarrier per (warp, slot) and the warps' parity bits
+struct TmaShared {
+    unsigned long long* bars;   // [warps][kTmaMaxSlots]
+    unsigned* phase;            // [warps]
+};
+
 template <int VEC>
-__device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, float* smem, int* stat) {
+__device__ void fwd_unit(const RaParams& p, const TmaMaps& tm, const TmaShared ts, const Unit& un,
+                         const int* s_seg, float* smem, int* stat) {
     const BucketDesc& B = p.bk[un.b];
     const int pos = s_seg[un.b] + un.i;
     const int k = p.perm ? p.perm[pos] : pos;
@@ -934,6 +1168,44 @@ __device__ void fwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
     const int Rfull = t.Y1 - t.Y0 + 1;
     const int wc = window_class(max(t.JX, t.JY));
     const int PwV = B.pw / VEC;
+    if (wc && PwV <= 32 / kTmaCh && fw <= kTmaMaxBW - 3 && p.tma_mask[lv] && B.sW == 1 &&
+        B.sC < (1 << 24) && B.sH < (1 << 24)) {
+        // TMA path: the warps' patches arrive as box loads of 4 channels x BH rows x BW columns
+        // a box must start on a 16-byte boundary of global memory (an unaligned first column is an
+        // illegal instruction: tools/tma_probe.cu), so it starts at X0 rounded down to 4 columns
+        const int X0a = t.X0 & ~3;
+        const int fwa = t.X1 - X0a + 1;
+        int cls = 0;
+        while (cls < kNumBW - 1 && tma_bw(cls) < fwa) ++cls;
+        const int BW = tma_bw(cls), BH = tma_bh(cls);
+        const int slot_bytes = kTmaCh * BW * BH * 4;
+        // the slots must be 128-byte aligned; every warp's ring ends in a 128-byte pad
+        const unsigned tile_sa = (unsigned)__cvta_generic_to_shared(tile);
+        const int lead = (int)((128u - (tile_sa & 127u)) & 127u);
+        const int per_warp = ((avail * 4 - lead) / RA_WARPS) & ~127;
+        int nslot = (per_warp - 128) / slot_bytes;
+        nslot = nslot > p.tma_slots ? p.tma_slots : nslot;
+        if (((p.tma_mask[lv] >> cls) & 1u) && nslot >= 2 && fwa <= BW) {
+            const int warp = threadIdx.x >> 5;
+            FwdTmaArgs a;
+            a.map = &tm.m[lv][cls];
+            a.obase = B.ptr + (long long)un.i * B.sN + (long long)c0 * B.sC;
+            a.ytab = t.ytab; a.rcnt = t.rcnt; a.xs = t.xs; a.wx = t.wx;
+            a.ring = reinterpret_cast<float*>(reinterpret_cast<char*>(tile) + lead + (size_t)warp * per_warp);
+            a.bar_sa = (unsigned)__cvta_generic_to_shared(ts.bars + warp * kTmaMaxSlots);
+            a.phase = ts.phase + warp;
+            a.osC = (int)B.sC; a.osH = (int)B.sH;
+            a.Pw = B.pw; a.Ph = B.ph; a.R = Rfull; a.X0 = X0a; a.Y0 = t.Y0; a.BW = BW; a.BH = BH;
+            a.nslot = nslot; a.nc = c1 - c0;
+            a.cidx0 = batch * p.C + c0;
+            a.chs = p.tma_rowmajor ? BW : BH * BW;
+            a.rws = p.tma_rowmajor ? kTmaCh * BW : BW;
+            if (wc == 2) fwd_warp_tma<VEC, 2>(a);
+            else if (wc == 4) fwd_warp_tma<VEC, 4>(a);
+            else fwd_warp_tma<VEC, 8>(a);
+            return;
+        }
+    }
     if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
         B.sC < (1 << 24) && B.sH < (1 << 24)) {
         // fast path: every warp streams its channels' patch rows through a private ring of row slots
@@ -1485,11 +1757,24 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
 // Persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <bool BWD, bool DYN>
-__global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __grid_constant__ RaParams p) {
-    extern __shared__ __align__(16) float smem[];
+__global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __grid_constant__ RaParams p,
+                                                                          const __grid_constant__ TmaMaps tm) {
+    extern __shared__ __align__(128) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
+    __shared__ __align__(8) unsigned long long s_bars[(BWD ? 1 : 32) * kTmaMaxSlots];
+    __shared__ unsigned s_phase[32];
+    TmaShared ts;
+    ts.bars = s_bars;
+    ts.phase = s_phase;
     if (threadIdx.x <= p.nb) s_seg[threadIdx.x] = p.seg ? p.seg[threadIdx.x] : (threadIdx.x == 0 ? 0 : p.K);
+    if (!BWD) {
+        // one mbarrier per (warp, chunk slot), initialised once per CTA; parities carry over from unit to unit
+        if (threadIdx.x < RA_WARPS * kTmaMaxSlots)
+            mbar_init((unsigned)__cvta_generic_to_shared(s_bars + threadIdx.x), 1);
+        if (threadIdx.x < 32) s_phase[threadIdx.x] = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     if (DYN) {
         // Dynamic scheduling.  The per-unit work differs by more than an order of magnitude (a RoI's
@@ -1552,9 +1837,9 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
                 else if (vec == 2) bwd_unit<2>(p, un, s_seg, smem, s_stat);
                 else bwd_unit<1>(p, un, s_seg, smem, s_stat);
             } else {
-                if (vec == 4) fwd_unit<4>(p, un, s_seg, smem, s_stat);
-                else if (vec == 2) fwd_unit<2>(p, un, s_seg, smem, s_stat);
-                else fwd_unit<1>(p, un, s_seg, smem, s_stat);
+                if (vec == 4) fwd_unit<4>(p, tm, ts, un, s_seg, smem, s_stat);
+                else if (vec == 2) fwd_unit<2>(p, tm, ts, un, s_seg, smem, s_stat);
+                else fwd_unit<1>(p, tm, ts, un, s_seg, smem, s_stat);
             }
             __syncthreads();
         }
@@ -1605,9 +1890,9 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
             else if (vec == 2) bwd_unit<2>(p, un, s_seg, smem, s_stat);
             else bwd_unit<1>(p, un, s_seg, smem, s_stat);
         } else {
-            if (vec == 4) fwd_unit<4>(p, un, s_seg, smem, s_stat);
-            else if (vec == 2) fwd_unit<2>(p, un, s_seg, smem, s_stat);
-            else fwd_unit<1>(p, un, s_seg, smem, s_stat);
+            if (vec == 4) fwd_unit<4>(p, tm, ts, un, s_seg, smem, s_stat);
+            else if (vec == 2) fwd_unit<2>(p, tm, ts, un, s_seg, smem, s_stat);
+            else fwd_unit<1>(p, tm, ts, un, s_seg, smem, s_stat);
         }
         __syncthreads();
     }
@@ -1619,6 +1904,91 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+// Experiment knobs, read from the environment ONCE per process (they select between measured
+// variants; the defaults are the shipped configuration).
+struct RaConfig {
+    int want, cg, interleave, fwd_smem_kb, bwd_smem_kb, fwd_dynamic, bwd_dynamic, bias;
+    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2;
+};
+static const RaConfig& config() {
+    static const RaConfig c = [] {
+        RaConfig r;
+        r.want = env_int("DM_RA_WANT", 24);
+        r.cg = env_int("DM_RA_CG", 0);
+        r.interleave = env_int("DM_RA_INTERLEAVE", 1);
+        r.fwd_smem_kb = env_int("DM_RA_FWD_SMEM_KB", 100);
+        r.bwd_smem_kb = env_int("DM_RA_BWD_SMEM_KB", DM_BWD_SMEM_KB);
+        r.fwd_dynamic = env_int("DM_RA_FWD_DYNAMIC", 1);
+        r.bwd_dynamic = env_int("DM_RA_BWD_DYNAMIC", DM_BWD_DYNAMIC);
+        r.bias = env_int("DM_RA_BIAS", 0);
+        r.fwd_threads = env_int("DM_RA_FWD_THREADS", kFwdThreads);
+        r.tma = env_int("DM_RA_TMA", 1);
+        r.tma_rowmajor = env_int("DM_RA_TMA_ROWMAJOR", 1);
+        r.tma_slots = env_int("DM_RA_TMA_SLOTS", 3);
+        r.tma_l2 = env_int("DM_RA_TMA_L2", 0);
+        return r;
+    }();
+    return c;
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// The maps of one level: pure host arithmetic, ~0.05 us per map (tools/tma_probe.cu), so they are
+// simply encoded per launch -- no cache, no state.  Returns the bit mask of the usable width classes.
+static unsigned level_maps(const LevelDesc& d, int rowmajor, int l2, CUtensorMap* out) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return 0u;
+    // TMA needs unit inner stride, a 16-byte aligned base, strides that are multiples of 16 bytes,
+    // and (here) images stacked at C * sC so that (image, channel) is one tensor dimension
+    if (d.sW != 1 || (reinterpret_cast<uintptr_t>(d.ptr) & 15u) || (d.sH & 3) || (d.sC & 3) ||
+        d.sN != (long long)d.C * d.sC || d.sH < d.W || d.sC < 1)
+        return 0u;
+    unsigned mask = 0u;
+    const cuuint64_t nc = (cuuint64_t)d.N * (cuuint64_t)d.C;
+    for (int c = 0; c < kNumBW; ++c) {
+        cuuint64_t dims[3];
+        cuuint64_t strides[2];
+        cuuint32_t box[3];
+        const cuuint32_t ones[3] = {1, 1, 1};
+        dims[0] = (cuuint64_t)d.W;
+        box[0] = (cuuint32_t)tma_bw(c);
+        if (rowmajor) {   // (x, channel, y): a box lands as [row][channel][BW]
+            dims[1] = nc; dims[2] = (cuuint64_t)d.H;
+            strides[0] = (cuuint64_t)d.sC * 4; strides[1] = (cuuint64_t)d.sH * 4;
+            box[1] = kTmaCh; box[2] = (cuuint32_t)tma_bh(c);
+        } else {          // (x, y, channel): [channel][row][BW]
+            dims[1] = (cuuint64_t)d.H; dims[2] = nc;
+            strides[0] = (cuuint64_t)d.sH * 4; strides[1] = (cuuint64_t)d.sC * 4;
+            box[1] = (cuuint32_t)tma_bh(c); box[2] = kTmaCh;
+        }
+        const CUtensorMapL2promotion prom = l2 == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                          : l2 == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                          : l2 == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        const CUresult r = enc(&out[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d.ptr), dims, strides,
+                               box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, prom,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) mask |= 1u << c;
+        else memset(&out[c], 0, sizeof(CUtensorMap));
+    }
+    return mask;
 }
 
 static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat_shapes,
@@ -1686,12 +2056,12 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
             const int pwv_guess = (d.pw % 4 == 0) ? d.pw / 4 : ((d.pw % 2 == 0) ? d.pw / 2 : d.pw);
             const int cpw_guess = pwv_guess >= 32 ? 1 : 32 / pwv_guess;
             const int cg_min = 8 * (cpw_guess > 4 ? 4 : cpw_guess);
-            const long long want = (long long)env_int("DM_RA_WANT", 24) * sm_count();
+            const long long want = (long long)config().want * sm_count();
             int small = 256;
             while (small > cg_min && (long long)K * ((p.C + small - 1) / small) < want) small >>= 1;
             if (small < cg) cg = small;
         }
-        cg = env_int("DM_RA_CG", 0) > 0 ? env_int("DM_RA_CG", 0) : cg;
+        cg = config().cg > 0 ? config().cg : cg;
         if (cg > p.C) cg = p.C;
         d.cg = cg;
         d.nslab = (p.C + cg - 1) / cg;
@@ -1722,34 +2092,64 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
     p.sampling_ratio = sampling_ratio;
     p.aligned = aligned ? 1 : 0;
     p.mode = 0;
-    p.interleave = env_int("DM_RA_INTERLEAVE", 1);
+    p.interleave = config().interleave;
     return DM_OK;
 }
 
+// occupancy and the dynamic shared-memory opt-in of one kernel variant, resolved once per device
+struct KernelSetup {
+    std::atomic<int> grid{0};
+};
 template <bool BWD>
-static int launch(RaParams& p, cudaStream_t st, const char* where) {
-    const int smem_kb = env_int(BWD ? "DM_RA_BWD_SMEM_KB" : "DM_RA_FWD_SMEM_KB", BWD ? DM_BWD_SMEM_KB : 100);
-    const int smem_bytes = smem_kb * 1024;
-    const int threads = BWD ? kBwdThreads : kFwdThreads;
-    p.smem_floats = smem_bytes / 4;
-    // static and dynamic scheduling are separate instantiations (each with its own register allocation)
-    const bool dyn = env_int(BWD ? "DM_RA_BWD_DYNAMIC" : "DM_RA_FWD_DYNAMIC", BWD ? DM_BWD_DYNAMIC : 1) != 0;
+static int kernel_grid(bool dyn, int threads, int smem_bytes, const char* where, int& grid) {
+    static KernelSetup setup[64][2];
+    static std::mutex mu;
+    int dev = 0;
+    DM_CUDA_CHECK(cudaGetDevice(&dev), where);
+    if (dev < 0 || dev >= 64) return DM_EUNSUPPORTED;
+    grid = setup[dev][dyn].grid.load(std::memory_order_acquire);
+    if (grid > 0) return DM_OK;
+    std::lock_guard<std::mutex> lock(mu);
     auto kern = dyn ? ra_kernel<BWD, true> : ra_kernel<BWD, false>;
     DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), where);
     int occ = 0;
     DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem_bytes), where);
     if (occ < 1) return DM_EUNSUPPORTED;
-    const int grid = sm_count() * occ;
+    grid = sm_count() * occ;
+    setup[dev][dyn].grid.store(grid, std::memory_order_release);
+    return DM_OK;
+}
+
+// `sched` = caller-owned device scratch of DM_SCHED_SCRATCH_BYTES (work-ticket counters, zeroed here
+// on the caller's stream) or NULL: static round-robin ownership of the work units.
+template <bool BWD>
+static int launch(RaParams& p, cudaStream_t st, unsigned* sched, const char* where) {
+    const RaConfig& cf = config();
+    const int smem_bytes = (BWD ? cf.bwd_smem_kb : cf.fwd_smem_kb) * 1024;
+    const int threads = BWD ? kBwdThreads : cf.fwd_threads;
+    p.smem_floats = smem_bytes / 4;
+    // static and dynamic scheduling are separate instantiations (each with its own register allocation)
+    const bool dyn = sched != nullptr && (BWD ? cf.bwd_dynamic : cf.fwd_dynamic) != 0;
+    int grid = 0;
+    const int rc = kernel_grid<BWD>(dyn, threads, smem_bytes, where, grid);
+    if (rc != DM_OK) return rc;
     p.tickets = nullptr;
-    p.bias = 0.001f * (float)env_int("DM_RA_BIAS", 0);
+    p.bias = 0.001f * (float)cf.bias;
     if (dyn) {
-        static std::atomic<unsigned> seq{0};
-        void* base = nullptr;
-        DM_CUDA_CHECK(cudaGetSymbolAddress(&base, g_ra_tickets), where);
-        p.tickets = reinterpret_cast<unsigned*>(base) + (size_t)(seq.fetch_add(1u, std::memory_order_relaxed) % kTicketSlots) * DM_MAX_BUCKETS;
+        p.tickets = sched;
         DM_CUDA_CHECK(cudaMemsetAsync(p.tickets, 0, sizeof(unsigned) * DM_MAX_BUCKETS, st), where);
     }
-    kern<<<grid, threads, smem_bytes, st>>>(p);
+    // tensor maps of the levels (forward patch loads)
+    static_assert(sizeof(TmaMaps) <= 16384, "kernel parameter space");
+    TmaMaps tm;
+    p.tma_rowmajor = cf.tma_rowmajor ? 1 : 0;
+    p.tma_slots = cf.tma_slots < 2 ? 2 : (cf.tma_slots > kTmaMaxSlots ? kTmaMaxSlots : cf.tma_slots);
+    for (int l = 0; l < DM_MAX_LEVELS; ++l) p.tma_mask[l] = 0u;
+    if (!BWD && cf.tma && p.mode == 0) {
+        for (int l = 0; l < p.L; ++l) p.tma_mask[l] = level_maps(p.lv[l], p.tma_rowmajor, cf.tma_l2, tm.m[l]);
+    }
+    auto kern = dyn ? ra_kernel<BWD, true> : ra_kernel<BWD, false>;
+    kern<<<grid, threads, smem_bytes, st>>>(p, tm);
     DM_LAUNCH_CHECK(where);
     return DM_OK;
 }
@@ -1762,7 +2162,7 @@ extern "C" int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* fe
                                 const int32_t* perm, const int32_t* seg_offsets, int num_buckets,
                                 const int32_t* out_hw, float* const* out_ptrs,
                                 const int64_t* out_strides, int sampling_ratio, int aligned,
-                                dm_stream_t stream) {
+                                void* sched_scratch, dm_stream_t stream) {
     dm::RaParams p;
     const int rc = dm::fill_params(p, const_cast<float* const*>(feat_ptrs), feat_shapes, feat_strides,
                                    spatial_scales, num_levels, rois, K, lvl, perm, seg_offsets,
@@ -1771,7 +2171,7 @@ extern "C" int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* fe
     if (K == 0) return DM_OK;
     for (int b = 0; b < num_buckets; ++b)
         if (!out_ptrs[b] && !seg_offsets) return DM_EINVAL;
-    return dm::launch<false>(p, (cudaStream_t)stream, "dm_roi_align_fwd");
+    return dm::launch<false>(p, (cudaStream_t)stream, static_cast<unsigned*>(sched_scratch), "dm_roi_align_fwd");
 }
 
 extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* feat_shapes,
@@ -1780,7 +2180,7 @@ extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* fea
                                 const int32_t* perm, const int32_t* seg_offsets, int num_buckets,
                                 const int32_t* out_hw, const float* const* grad_out_ptrs,
                                 const int64_t* grad_out_strides, int sampling_ratio, int aligned,
-                                int zero_init, dm_stream_t stream) {
+                                int zero_init, void* sched_scratch, dm_stream_t stream) {
     dm::RaParams p;
     const int rc = dm::fill_params(p, grad_feat_ptrs, feat_shapes, feat_strides, spatial_scales,
                                    num_levels, rois, K, lvl, perm, seg_offsets, num_buckets, out_hw,
@@ -1799,7 +2199,7 @@ extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* fea
         }
     }
     if (K == 0) return DM_OK;
-    return dm::launch<true>(p, st, "dm_roi_align_bwd");
+    return dm::launch<true>(p, st, static_cast<unsigned*>(sched_scratch), "dm_roi_align_bwd");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1810,7 +2210,8 @@ extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* fea
 extern "C" int dm_simple_roi_align_fwd(const float* feat, const int32_t* feat_shape,
                                        const int64_t* feat_strides, float spatial_scale,
                                        const float* rois, int K, int out_h, int out_w, float* out,
-                                       const int64_t* out_strides, int aligned, dm_stream_t stream) {
+                                       const int64_t* out_strides, int aligned, void* sched_scratch,
+                                       dm_stream_t stream) {
     if (!feat || !feat_shape || !feat_strides || !out_strides || (K > 0 && !out)) return DM_EINVAL;
     dm::RaParams p;
     float* fp = const_cast<float*>(feat);
@@ -1820,14 +2221,14 @@ extern "C" int dm_simple_roi_align_fwd(const float* feat, const int32_t* feat_sh
     if (rc != DM_OK) return rc;
     if (K == 0) return DM_OK;
     p.mode = 1;
-    return dm::launch<false>(p, (cudaStream_t)stream, "dm_simple_roi_align_fwd");
+    return dm::launch<false>(p, (cudaStream_t)stream, static_cast<unsigned*>(sched_scratch), "dm_simple_roi_align_fwd");
 }
 
 extern "C" int dm_simple_roi_align_bwd(float* grad_feat, const int32_t* feat_shape,
                                        const int64_t* feat_strides, float spatial_scale,
                                        const float* rois, int K, int out_h, int out_w,
                                        const float* grad_out, const int64_t* grad_out_strides,
-                                       int aligned, int zero_init, dm_stream_t stream) {
+                                       int aligned, int zero_init, void* sched_scratch, dm_stream_t stream) {
     if (!grad_feat || !feat_shape || !feat_strides || !grad_out_strides || (K > 0 && !grad_out)) return DM_EINVAL;
     dm::RaParams p;
     float* go = const_cast<float*>(grad_out);
@@ -1845,5 +2246,5 @@ extern "C" int dm_simple_roi_align_bwd(float* grad_feat, const int32_t* feat_sha
     }
     if (K == 0) return DM_OK;
     p.mode = 1;
-    return dm::launch<true>(p, st, "dm_simple_roi_align_bwd");
+    return dm::launch<true>(p, st, static_cast<unsigned*>(sched_scratch), "dm_simple_roi_align_bwd");
 }

@@ -31,6 +31,14 @@ def _arr(ctype, vals):
     return (ctype * max(len(vals), 1))(*vals)
 
 
+def _sched_scratch(dev):
+    """Caller-owned scratch of one RoIAlign launch (DM_SCHED_SCRATCH_BYTES): the work-ticket counters
+    of the dynamic unit scheduler.  A fresh block of the caching allocator per launch, so launches on
+    different streams -- or replays of a captured graph -- never share counters; the allocator only
+    hands the block out again in stream order."""
+    return torch.empty(16, dtype=torch.int32, device=dev)
+
+
 def _f32c(t, name):
     if t.dtype != torch.float32:
         raise TypeError('%s must be float32, got %s' % (name, t.dtype))
@@ -125,10 +133,11 @@ def roi_align_forward(feats: Sequence[Tensor], rois: Tensor, lvl: Optional[Tenso
     optrs, ohw, ostrides = _bucket_arrays(outs, out_hw)
     scales = _arr(ctypes.c_float, [float(s) for s in spatial_scales])
     with torch.cuda.device(dev):
+        sched = _sched_scratch(dev)
         rc = _lib.load().dm_roi_align_fwd(fptrs, fshapes, fstrides, scales, L, _ptr(rois), K,
                                           _ptr(lvl), _ptr(perm), _ptr(seg), nb, ohw, optrs,
                                           ostrides, int(sampling_ratio), int(bool(aligned)),
-                                          _stream(dev))
+                                          _ptr(sched), _stream(dev))
     _lib.check(rc, 'dm_roi_align_fwd')
     return outs
 
@@ -163,10 +172,11 @@ def roi_align_backward(grad_outs: Sequence[Tensor], rois: Tensor, lvl: Optional[
     optrs, ohw, ostrides = _bucket_arrays(gos, out_hw)
     scales = _arr(ctypes.c_float, [float(s) for s in spatial_scales])
     with torch.cuda.device(dev):
+        sched = _sched_scratch(dev)
         rc = _lib.load().dm_roi_align_bwd(gptrs, gshapes, gstrides, scales, L, _ptr(rois), K,
                                           _ptr(lvl), _ptr(perm), _ptr(seg), nb, ohw, optrs,
                                           ostrides, int(sampling_ratio), int(bool(aligned)), 1,
-                                          _stream(dev))
+                                          _ptr(sched), _stream(dev))
     _lib.check(rc, 'dm_roi_align_bwd')
     return grads
 
@@ -427,10 +437,11 @@ def simple_roi_align_forward(feat: Tensor, rois: Tensor, out_h: int, out_w: int,
     if K == 0:
         return out
     with torch.cuda.device(dev):
+        sched = _sched_scratch(dev)
         rc = _lib.load().dm_simple_roi_align_fwd(
             _ptr(feat), _arr(ctypes.c_int32, list(feat.shape)), _arr(ctypes.c_int64, list(feat.stride())),
             float(spatial_scale), _ptr(rois), K, int(out_h), int(out_w), _ptr(out),
-            _arr(ctypes.c_int64, list(out.stride())), int(bool(aligned)), _stream(dev))
+            _arr(ctypes.c_int64, list(out.stride())), int(bool(aligned)), _ptr(sched), _stream(dev))
     _lib.check(rc, 'dm_simple_roi_align_fwd')
     return out
 
@@ -450,11 +461,12 @@ def simple_roi_align_backward(grad_out: Tensor, rois: Tensor, feat_shape: Sequen
     grad = torch.empty([int(v) for v in feat_shape], dtype=torch.float32, device=dev)
     K = rois.size(0)
     with torch.cuda.device(dev):
+        sched = _sched_scratch(dev)
         rc = _lib.load().dm_simple_roi_align_bwd(
             _ptr(grad), _arr(ctypes.c_int32, list(grad.shape)), _arr(ctypes.c_int64, list(grad.stride())),
             float(spatial_scale), _ptr(rois), K, int(grad_out.size(2)), int(grad_out.size(3)),
             _ptr(grad_out), _arr(ctypes.c_int64, list(grad_out.stride())), int(bool(aligned)), 1,
-            _stream(dev))
+            _ptr(sched), _stream(dev))
     _lib.check(rc, 'dm_simple_roi_align_bwd')
     return grad
 

@@ -5,10 +5,10 @@
  * This is the drop-in boundary.  Every entry point takes plain device
  * pointers, sizes and a CUDA stream; no torch / ATen types cross it.  The library allocates no
  * memory: every buffer (inputs, outputs, scratch) belongs to the caller, every call is
- * asynchronous on `stream` and re-entrant across streams.  Its only state is the thread-local
- * error text, a launch counter, and a static ring of 512 work-ticket slots in device memory of
- * which each dm_roi_align_fwd launch takes the next one (zeroed on `stream` before the kernel), so
- * at most 512 such launches may be in flight at once per process and device.
+ * asynchronous on `stream` and re-entrant across streams (and across CUDA-graph replays: a launch
+ * keeps its scheduling counters in the caller's `sched_scratch`, not in the library).  The library
+ * holds no mutable device state; on the host it keeps the thread-local error text, a launch
+ * counter and per-device constants resolved once (SM count, kernel occupancy).
  *
  * Reference interfaces replaced (paths relative to the reference tree, lslrh/DynaMask):
  *   dm_assign          <- SingleRoIExtractor.map_roi_levels
@@ -40,6 +40,8 @@ extern "C" {
 
 #define DM_MAX_LEVELS 8
 #define DM_MAX_BUCKETS 8
+/* bytes of caller-owned device scratch one RoIAlign launch may be given (see sched_scratch) */
+#define DM_SCHED_SCRATCH_BYTES 64
 
 #define DM_OK 0
 #define DM_EINVAL (-1)       /* bad argument (null pointer, size, stride) */
@@ -89,6 +91,10 @@ int dm_assign(const float* rois, int K, const float* onehot, int num_buckets, in
  *   out_ptrs       host [num_buckets] device pointers, bucket b is [seg[b+1]-seg[b], C, h, w]
  *   out_strides    host [num_buckets*4] element strides (n, c, h, w) of each bucket's output
  *   sampling_ratio 0 = adaptive ceil(roi_size / out_size);  aligned 1 = half-pixel shift
+ *   sched_scratch  device scratch of DM_SCHED_SCRATCH_BYTES owned by the caller and not touched by
+ *                  anyone else until the launch has finished (the work-ticket counters of the
+ *                  dynamic unit scheduler; cleared by the library on `stream`), or NULL: the work
+ *                  units are then dealt statically (slower on mixed-resolution launches)
  * Every output element of every listed RoI is written (zeros where the reference yields zeros).
  */
 int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* feat_shapes,
@@ -96,7 +102,7 @@ int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* feat_shapes,
                      const float* rois, int K, const int32_t* lvl, const int32_t* perm,
                      const int32_t* seg_offsets, int num_buckets, const int32_t* out_hw,
                      float* const* out_ptrs, const int64_t* out_strides, int sampling_ratio,
-                     int aligned, dm_stream_t stream);
+                     int aligned, void* sched_scratch, dm_stream_t stream);
 
 /*
  * Stage 2 backward: scatters grad_out of every bucket into the per-level gradient maps.
@@ -108,7 +114,8 @@ int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* feat_shapes,
                      const float* rois, int K, const int32_t* lvl, const int32_t* perm,
                      const int32_t* seg_offsets, int num_buckets, const int32_t* out_hw,
                      const float* const* grad_out_ptrs, const int64_t* grad_out_strides,
-                     int sampling_ratio, int aligned, int zero_init, dm_stream_t stream);
+                     int sampling_ratio, int aligned, int zero_init, void* sched_scratch,
+                     dm_stream_t stream);
 
 /*
  * Stage 3: paste N instance masks into image canvases, fused sigmoid + bilinear + threshold.
@@ -190,17 +197,18 @@ int64_t dm_rle_compress_batch_host(const int32_t* transitions, const int64_t* of
  *   feat        device [N,C,H,W] fp32, feat_shape host [4], feat_strides host [4] (elements)
  *   rois        device [K,5] (batch_idx, x1, y1, x2, y2) in input-image pixels
  *   out         device [K,C,out_h,out_w], out_strides host [4]; row k belongs to RoI k
- * The backward adds into grad_feat (cleared first when zero_init != 0).
+ * The backward adds into grad_feat (cleared first when zero_init != 0).  sched_scratch as in
+ * dm_roi_align_fwd.
  */
 int dm_simple_roi_align_fwd(const float* feat, const int32_t* feat_shape,
                             const int64_t* feat_strides, float spatial_scale, const float* rois,
                             int K, int out_h, int out_w, float* out, const int64_t* out_strides,
-                            int aligned, dm_stream_t stream);
+                            int aligned, void* sched_scratch, dm_stream_t stream);
 int dm_simple_roi_align_bwd(float* grad_feat, const int32_t* feat_shape,
                             const int64_t* feat_strides, float spatial_scale, const float* rois,
                             int K, int out_h, int out_w, const float* grad_out,
                             const int64_t* grad_out_strides, int aligned, int zero_init,
-                            dm_stream_t stream);
+                            void* sched_scratch, dm_stream_t stream);
 
 /*
  * Next row: inference-time stage-to-stage refinement, fused.  Replaces the
