@@ -102,21 +102,23 @@ struct BucketDesc {
                 // dense rows, 16-byte aligned planes
 };
 
-// Patch loads by TMA (cp.async.bulk.tensor.3d): one tensor map per (pyramid level, box-width class).
-// A box is kTmaCh channels x BH patch rows x BW columns of one image, BW the smallest class that
-// covers the patch from its first column rounded down to a 16-byte boundary, BH = 8 rows for
-// BW <= 32 and 4 above, so a box is at most 4 KB.
-constexpr int kTmaCh = 4;           // channels per box = channels per warp pass on this path
+// Patch loads by TMA (cp.async.bulk.tensor.3d): one tensor map per (pyramid level, channels per
+// box, box-width class).  A box is 4 << set channels x BH patch rows x BW columns of one image: BW the
+// smallest class that covers the patch from its first column rounded down to a 16-byte boundary,
+// the channel count what one warp pass consumes (a lane always produces four pooled values per
+// patch row: VEC columns of 4 / VEC channels), BH such that a box is at most 4 KB.
+constexpr int kTmaSets = 3;         // boxes of 4, 8, 16 channels
+constexpr int kTmaLevels = 5;       // pyramid levels that can have maps (kernel-parameter space)
 constexpr int kNumBW = 10;
 __host__ __device__ constexpr int tma_bw(int cls) {
     return cls == 0 ? 8 : cls == 1 ? 12 : cls == 2 ? 16 : cls == 3 ? 20 : cls == 4 ? 24 : cls == 5 ? 28
          : cls == 6 ? 32 : cls == 7 ? 40 : cls == 8 ? 48 : 64;
 }
-__host__ __device__ constexpr int tma_bh(int cls) { return cls <= 6 ? 8 : 4; }
+__host__ __device__ constexpr int tma_bh(int set, int cls) { return (cls <= 6 ? 8 : 4) >> set; }
 constexpr int kTmaMaxBW = 64;
 constexpr int kTmaMaxSlots = 4;     // chunk slots per warp (ring depth)
 struct alignas(64) TmaMaps {
-    CUtensorMap m[DM_MAX_LEVELS][kNumBW];
+    CUtensorMap m[kTmaLevels][kTmaSets][kNumBW];
 };
 
 struct RaParams {
@@ -136,11 +138,12 @@ struct RaParams {
     // round-robin ownership
     unsigned* tickets;
     float bias;      // how much later (per bucket rank) the smaller buckets are paced
-    // TMA patch loads: bit c of tma_mask[l] = level l has a tensor map for width class c;
+    // TMA patch loads: bit c of tma_mask[l][s] = level l has a tensor map for channel set s, width class c;
     // tma_rowmajor = 1: boxes land as [row][channel][BW] (tensor dims W, C*N, H), 0: [channel][row][BW]
-    unsigned tma_mask[DM_MAX_LEVELS];
+    unsigned tma_mask[kTmaLevels][kTmaSets];
     int tma_rowmajor;
     int tma_slots;   // ring depth wanted (2 .. kTmaMaxSlots)
+    int diag;        // measurement only (DM_RA_DIAG)
 };
 
 // exact n / d whenever n * d < 2^32 (indices here are far below that)
@@ -349,9 +352,14 @@ struct Tables {
 // register-window class for a band width: 2, 4, 8, or 0 when wider than 8
 __device__ __forceinline__ int window_class(int j) { return j <= 2 ? 2 : (j <= 4 ? 4 : (j <= 8 ? 8 : 0)); }
 
-__device__ __forceinline__ void axis_scan(const RoiGeom& g, int axis, int P, int size, int grid,
-                                          int* s_start, int* stat) {
-    for (int p = threadIdx.x; p < P; p += RA_THREADS) {
+// One warp scans one axis: lane p owns bin p (and p + 32, ...).  Writes the first pixel of every
+// bin's band to s_start (INT_MAX when the bin has no valid sample) and the axis statistics
+// {widest band, first pixel, last pixel, first valid bin, last valid bin} to stat[0..5).
+__device__ __forceinline__ void axis_scan_warp(const RoiGeom& g, int axis, int P, int size, int grid,
+                                               int* s_start, int* stat) {
+    const int lane = threadIdx.x & 31;
+    int jmax = 0, pmin = INT_MAX, pmax = -1, bmin = INT_MAX, bmax = -1;
+    for (int p = lane; p < P; p += 32) {
         int first = INT_MAX, last = -1;
         for (int i = 0; i < grid; ++i) {
             int lo, hi;
@@ -363,20 +371,41 @@ __device__ __forceinline__ void axis_scan(const RoiGeom& g, int axis, int P, int
         }
         s_start[p] = first;
         if (last >= 0) {
-            atomicMax(&stat[0], last - first + 1);
-            atomicMin(&stat[1], first);
-            atomicMax(&stat[2], last);
-            atomicMin(&stat[3], p);
-            atomicMax(&stat[4], p);
+            jmax = max(jmax, last - first + 1);
+            pmin = min(pmin, first);
+            pmax = max(pmax, last);
+            bmin = min(bmin, p);
+            bmax = max(bmax, p);
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+        pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+        pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+        bmin = min(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+        bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    }
+    if (lane == 0) {
+        stat[0] = jmax; stat[1] = pmin; stat[2] = pmax; stat[3] = bmin; stat[4] = bmax;
     }
 }
 
-__device__ __forceinline__ void axis_fill(const RoiGeom& g, int axis, int P, int size, int grid,
-                                          const int* s_start, float* w) {
+// One warp fills one axis' folded weights w[Ja][P]: the lane that owns bin p fixes up its start
+// (bins without a valid sample sit at the two ends; they get a start that keeps the starts
+// monotone, their weights stay zero), clears its column and accumulates its samples -- no other
+// thread touches column p, so no atomics and no barrier in between.
+__device__ __forceinline__ void axis_fill_warp(const RoiGeom& g, int axis, int P, int size, int grid, int* s_start,
+                                               float* w, int Ja, int first_pix, int bin_a, int start_last) {
+    const int lane = threadIdx.x & 31;
     const float inv = 1.0f / (float)grid;
-    for (int p = threadIdx.x; p < P; p += RA_THREADS) {
-        const int st = s_start[p];
+    for (int p = lane; p < P; p += 32) {
+        int st = s_start[p];
+        if (st == INT_MAX) {
+            st = p < bin_a ? first_pix : start_last;
+            s_start[p] = st;
+        }
+        for (int j = 0; j < Ja; ++j) w[j * P + p] = 0.0f;
         for (int i = 0; i < grid; ++i) {
             int lo, hi;
             float l, h;
@@ -390,20 +419,19 @@ __device__ __forceinline__ void axis_fill(const RoiGeom& g, int axis, int P, int
 
 // Returns false (uniformly) when the RoI has no valid sample at all -> output is all zeros.
 // `fits` is set false when the tables alone exceed the shared-memory budget.
+// Warp 0 builds the X axis, warp 1 the Y axis (incl. the packed Y records), the other warps only
+// meet them at the two barriers.
 __device__ DM_COLD bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, int W, float* smem,
                              int smem_floats, int* stat, Tables& t, bool& fits) {
     fits = true;
-    if (threadIdx.x < ST_N) {
-        const int k = threadIdx.x;
-        stat[k] = (k == ST_X0 || k == ST_PA || k == ST_Y0 || k == ST_QA) ? INT_MAX : (k == ST_JX || k == ST_JY ? 0 : -1);
-    }
     t.xs = reinterpret_cast<int*>(smem);
     t.ys = t.xs + Pw;
-    __syncthreads();
     if (g.gw <= 0 || g.gh <= 0) return false;
     if (Pw + Ph > smem_floats) { fits = false; return true; }
-    axis_scan(g, 0, Pw, W, g.gw, t.xs, stat + ST_JX);
-    axis_scan(g, 1, Ph, H, g.gh, t.ys, stat + ST_JY);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy_warp = RA_WARPS > 1 ? 1 : 0;
+    if (warp == 0) axis_scan_warp(g, 0, Pw, W, g.gw, t.xs, stat + ST_JX);
+    if (warp == wy_warp) axis_scan_warp(g, 1, Ph, H, g.gh, t.ys, stat + ST_JY);
     __syncthreads();
     t.JX = stat[ST_JX]; t.X0 = stat[ST_X0]; t.X1 = stat[ST_X1];
     t.JY = stat[ST_JY]; t.Y0 = stat[ST_Y0]; t.Y1 = stat[ST_Y1];
@@ -420,40 +448,37 @@ __device__ DM_COLD bool build_tables(const RoiGeom& g, int Ph, int Pw, int H, in
     const int Rr = t.Y1 - t.Y0 + 1;
     const int rfloats = t.ystride ? ((Rr + 3) & ~3) : 0;
     t.floats = base + wfloats + t.ystride * Ph + rfloats;
+    {
+        const unsigned R = (unsigned)Rr;
+        t.mR = R > 1 ? 0xFFFFFFFFu / R + 1u : 0u;
+    }
     if (t.floats > smem_floats) { fits = false; return true; }
     t.wx = smem + base;
     t.wy = t.wx + t.JXa * Pw;
     t.ytab = smem + base + wfloats;
     t.rcnt = reinterpret_cast<int*>(t.ytab + t.ystride * Ph);
-    // bins without any valid sample sit at the two ends; give them a start that keeps xs / ys
-    // monotone (their weights stay zero)
+    // (the lanes owning bins pb / qb hold valid starts, which the fill never rewrites)
     const int xs_last = t.xs[pb], ys_last = t.ys[qb];
-    if (threadIdx.x == 0) {
-        const unsigned R = (unsigned)(t.Y1 - t.Y0 + 1);
-        stat[ST_MR] = (int)(R > 1 ? 0xFFFFFFFFu / R + 1u : 0u);
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < Pw; p += RA_THREADS)
-        if (t.xs[p] == INT_MAX) t.xs[p] = p < pa ? t.X0 : xs_last;
-    for (int p = threadIdx.x; p < Ph; p += RA_THREADS)
-        if (t.ys[p] == INT_MAX) t.ys[p] = p < qa ? t.Y0 : ys_last;
-    for (int i = threadIdx.x; i < wfloats; i += RA_THREADS) t.wx[i] = 0.0f;
-    for (int i = threadIdx.x; i < rfloats; i += RA_THREADS) t.rcnt[i] = 0;
-    __syncthreads();
-    axis_fill(g, 0, Pw, W, g.gw, t.xs, t.wx);
-    axis_fill(g, 1, Ph, H, g.gh, t.ys, t.wy);
-    __syncthreads();
-    t.mR = (unsigned)stat[ST_MR];
-    if (t.ystride) {
-        for (int i = threadIdx.x; i < Ph * t.ystride; i += RA_THREADS) {
-            const int ph = i / t.ystride, f = i - ph * t.ystride;
-            float v = 0.0f;
-            if (f == 0) atomicAdd(&t.rcnt[t.ys[ph] - t.Y0], 1);
-            v = t.wy[(f >> 1) * Ph + ph];
-            t.ytab[i] = v;
+    if (warp == 0) axis_fill_warp(g, 0, Pw, W, g.gw, t.xs, t.wx, t.JXa, t.X0, pa, xs_last);
+    if (warp == wy_warp) {
+        for (int i = lane; i < rfloats; i += 32) t.rcnt[i] = 0;
+        axis_fill_warp(g, 1, Ph, H, g.gh, t.ys, t.wy, t.JYa, t.Y0, qa, ys_last);
+        __syncwarp();
+        if (t.ystride) {
+            // packed record of pooled row ph: its JYa row weights as broadcast pairs (written by the
+            // lane that just produced them), and the count of pooled rows per first band row
+            for (int ph = lane; ph < Ph; ph += 32) {
+                float* rec = t.ytab + ph * t.ystride;
+                for (int j = 0; j < t.JYa; ++j) {
+                    const float v = t.wy[j * Ph + ph];
+                    rec[2 * j] = v;
+                    rec[2 * j + 1] = v;
+                }
+                atomicAdd(&t.rcnt[t.ys[ph] - t.Y0], 1);
+            }
         }
-        __syncthreads();
     }
+    __syncthreads();
     return true;
 }
 
@@ -869,13 +894,15 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // Forward, TMA path: the same warp-autonomous strip walk, but the warp's patches arrive as TMA box
-// loads -- one cp.async.bulk.tensor.3d per chunk of BH patch rows x 4 channels x BW columns,
+// loads -- one cp.async.bulk.tensor.3d per chunk of BH patch rows x 16 / VEC channels x BW columns,
 // issued by lane 0 into a ring of chunk slots and signalled on one mbarrier per slot -- instead of
-// one 16-byte cp.async per lane and patch row.  The steady state has no copy bookkeeping in the
+// one 16-byte cp.async per lane and patch row.  Lanes = 4 channels x Pw / VEC strips; a lane
+// carries 4 / VEC channels (4 channels apart), so it always produces four pooled values per patch
+// row and the control flow of the walk is shared by twice / four times the arithmetic.  The steady state has no copy bookkeeping in the
 // row loop: per chunk one parity wait, one warp barrier and (lane 0) one expect_tx + one TMA.
 // The last chunk of a channel batch is shifted up so that it ends on the patch's last row (the rows
 // it repeats come from L2 and are skipped), so nothing below the patch is fetched.
-// Requires Pw / VEC <= 8 (four channels per warp pass), fw <= 64, JX, JY <= JW.
+// Requires Pw / VEC <= 8, patch rows of <= 64 floats from the aligned first column, JX, JY <= JW.
 // ---------------------------------------------------------------------------------------------
 struct FwdTmaArgs {
     const void* map;     // tensor map of (level, width class), kernel-parameter space
@@ -891,15 +918,22 @@ struct FwdTmaArgs {
     int Pw, Ph, R, X0, Y0, BW, BH, nslot, nc;   // X0: first column of the boxes (multiple of 4)
     int cidx0;           // tensor coordinate of channel c0 of this RoI's image: batch * C + c0
     int chs, rws;        // floats between channels / between rows inside a slot
+    int diag;            // measurement only (DM_RA_DIAG): 1 = no loads (compute on stale slots), 2 = loads only
 };
+
+// channels per lane on the TMA path: a lane keeps JW window rows x CH channels x VEC columns in
+// registers -- 32 values for JW <= 4 (eight independent chains per patch row), 32 for JW = 8
+__host__ __device__ constexpr int tma_ch(int vec, int jw) { return vec == 1 ? 4 : (jw <= 4 ? 8 / vec : 4 / vec); }
 
 template <int VEC, int JW>
 __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
+    constexpr int CH = tma_ch(VEC, JW);  // channels per lane
+    constexpr int BC = 4 * CH;           // channels per box = per warp pass
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PwV = a.Pw / VEC;
     const int R = a.R, BH = a.BH, nc = a.nc, nslot = a.nslot;
     const int sub = lane / PwV, pv = lane - sub * PwV;
-    const bool lane_on = sub < kTmaCh;
+    const bool lane_on = sub < 4;
     const int subc = lane_on ? sub : 0;
     const float* __restrict__ ytab = a.ytab;
     const int* __restrict__ rcnt = a.rcnt;
@@ -910,26 +944,27 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
     __builtin_assume(__isShared(a.xs));
     __builtin_assume(__isShared(a.wx));
     __builtin_assume(__isShared(a.phase));
-    const int step = RA_WARPS * kTmaCh;
+    const int step = RA_WARPS * BC;
     const int rws = a.rws;
-    const int slotf = kTmaCh * a.BW * BH;                  // floats per slot
+    const int qs = 4 * a.chs;                              // floats between a lane's channels in a slot
+    const int slotf = BC * a.BW * BH;                      // floats per slot
     const unsigned slot_bytes = (unsigned)slotf * 4u;
     const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
     // the padded taps of the last channel's last row run past the ring: that pad must be finite
     if (lane < 8) ring[nslot * slotf + lane] = 0.0f;
     const int nchunk = (R + BH - 1) / BH;                  // chunks per channel batch
     const int last_shift = R >= BH ? nchunk * BH - R : 0;  // rows the last chunk repeats
-    const int nbatch = warp * kTmaCh < nc ? (nc - warp * kTmaCh + step - 1) / step : 0;
+    const int nbatch = warp * BC < nc ? (nc - warp * BC + step - 1) / step : 0;
     const int q_total = nbatch * nchunk;
     unsigned par = *a.phase;
     __syncwarp();
 
     // ---- producer side (warp-uniform bookkeeping, lane 0 issues) -------------------------------
     int q_issue = 0, i_k = 0, i_slot = 0;
-    int i_c = a.cidx0 + warp * kTmaCh;                     // channel coordinate of the next chunk
+    int i_c = a.cidx0 + warp * BC;                         // channel coordinate of the next chunk
     auto issue = [&]() {
         if (q_issue < q_total) {
-            if (lane == 0) {
+            if (lane == 0 && !(a.diag & 1)) {
                 const unsigned bar = a.bar_sa + 8u * (unsigned)i_slot;
                 const int y = a.Y0 + i_k * BH - (i_k == nchunk - 1 ? last_shift : 0);
                 mbar_expect_tx(bar, slot_bytes);
@@ -949,8 +984,10 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
             __syncwarp();
             issue();
         }
-        mbar_wait(a.bar_sa + 8u * (unsigned)c_slot, (par >> c_slot) & 1u);
-        par ^= 1u << c_slot;
+        if (!(a.diag & 1)) {
+            mbar_wait(a.bar_sa + 8u * (unsigned)c_slot, (par >> c_slot) & 1u);
+            par ^= 1u << c_slot;
+        }
         const int skip = c_k == nchunk - 1 ? last_shift : 0;
         rows_left = min(BH, R) - skip;
         pr = ring + c_slot * slotf + skip * rws;
@@ -973,12 +1010,13 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
 #pragma unroll
         for (int j = 0; j < (JW <= 4 ? JW : 1); ++j) ld_vec<VEC>(wxp + j * a.Pw, wx_r[j]);
     }
-    auto consume = [&](float (&v)[VEC]) {
+    // X-interpolates the next patch row of the stream: v[q][e] = channel sub + 4 q, pooled column e
+    auto consume = [&](float (&v)[CH][VEC]) {
         if (rows_left == 0) acquire();
         --rows_left;
 #pragma unroll
         for (int j = 0; j < JW; ++j) {
-            float wj[VEC], pj[VEC];
+            float wj[VEC];
             if (JW <= 4) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) wj[e] = wx_r[JW <= 4 ? j : 0][e];
@@ -986,16 +1024,21 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
                 ld_vec<VEC>(wxp + j * a.Pw, wj);
             }
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) pj[e] = pr[xo_r[e] + j];
-            if (VEC == 1) {
-                v[0] = j == 0 ? wj[0] * pj[0] : v[0] + wj[0] * pj[0];
-            } else {
+            for (int q = 0; q < CH; ++q) {
+                float pj[VEC];
 #pragma unroll
-                for (int e = 0; e + 1 < VEC; e += 2) {
-                    const float2 r = j == 0 ? fmul2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]))
-                                            : ffma2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]), make_float2(v[e], v[e + 1]));
-                    v[e] = r.x;
-                    v[e + 1] = r.y;
+                for (int e = 0; e < VEC; ++e) pj[e] = pr[xo_r[e] + q * qs + j];
+                if (VEC == 1) {
+                    v[q][0] = j == 0 ? wj[0] * pj[0] : v[q][0] + wj[0] * pj[0];
+                } else {
+#pragma unroll
+                    for (int e = 0; e + 1 < VEC; e += 2) {
+                        const float2 r = j == 0 ? fmul2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]))
+                                                : ffma2(make_float2(wj[e], wj[e + 1]), make_float2(pj[e], pj[e + 1]),
+                                                        make_float2(v[q][e], v[q][e + 1]));
+                        v[q][e] = r.x;
+                        v[q][e + 1] = r.y;
+                    }
                 }
             }
         }
@@ -1013,14 +1056,20 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
     for (int d = 0; d < nslot; ++d) issue();
 
     constexpr int YS = 2 * JW;
-    float* o_cb = a.obase + (warp * kTmaCh + subc) * a.osC + pv * VEC;
-    for (int cb = warp * kTmaCh; cb < nc; cb += step, o_cb += step * a.osC) {
-        const bool on = lane_on && sub < nc - cb;
-        float win[JW][VEC];
+    const int oq = 4 * a.osC;   // floats between a lane's channels in the pooled block
+    float* o_cb = a.obase + (warp * BC + subc) * a.osC + pv * VEC;
+    for (int cb = warp * BC; cb < nc; cb += step, o_cb += step * a.osC) {
+        if (a.diag & 2) { skip_rows(R); continue; }
+        bool on[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) on[q] = lane_on && sub + 4 * q < nc - cb;
+        float win[JW][CH][VEC];
 #pragma unroll
         for (int j = 0; j < JW; ++j)
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) win[j][e] = 0.0f;
+            for (int q = 0; q < CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) win[j][q][e] = 0.0f;
         int used = 0;   // patch rows of this batch consumed so far
         float* o = o_cb;
         const float* yrec = ytab;
@@ -1031,26 +1080,32 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
 #pragma unroll
             for (int j = 0; j + 1 < JW; ++j)
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) win[j][e] = win[j + 1][e];
+                for (int q = 0; q < CH; ++q)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) win[j][q][e] = win[j + 1][q][e];
             if (base + JW - 1 < R) {
                 consume(win[JW - 1]);
                 ++used;
             } else {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) win[JW - 1][e] = 0.0f;
+                for (int q = 0; q < CH; ++q)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) win[JW - 1][q][e] = 0.0f;
             }
             if (base < 0) continue;
             const int n = rcnt[base];
-#pragma unroll 2
             for (int k = 0; k < n; ++k) {
                 float2 w[JW];
                 load_yrec<JW>(yrec, w);
                 yrec += YS;
-                float acc[VEC];
-                vmul<VEC>(acc, w[0], win[0]);
 #pragma unroll
-                for (int j = 1; j < JW; ++j) vfma<VEC>(acc, w[j], win[j]);
-                if (on) st_stream_vec<VEC>(o, acc);
+                for (int q = 0; q < CH; ++q) {
+                    float acc[VEC];
+                    vmul<VEC>(acc, w[0], win[0][q]);
+#pragma unroll
+                    for (int j = 1; j < JW; ++j) vfma<VEC>(acc, w[j], win[j][q]);
+                    if (on[q]) st_stream_vec<VEC>(o + q * oq, acc);
+                }
                 o += a.osH;
             }
             left -= n;
@@ -1168,27 +1223,29 @@ __device__ void fwd_unit(const RaParams& p, const TmaMaps& tm, const TmaShared t
     const int Rfull = t.Y1 - t.Y0 + 1;
     const int wc = window_class(max(t.JX, t.JY));
     const int PwV = B.pw / VEC;
-    if (wc && PwV <= 32 / kTmaCh && fw <= kTmaMaxBW - 3 && p.tma_mask[lv] && B.sW == 1 &&
+    if (wc && PwV <= 8 && fw <= kTmaMaxBW - 3 && lv < kTmaLevels && B.sW == 1 &&
         B.sC < (1 << 24) && B.sH < (1 << 24)) {
-        // TMA path: the warps' patches arrive as box loads of 4 channels x BH rows x BW columns
-        // a box must start on a 16-byte boundary of global memory (an unaligned first column is an
+        // TMA path: the warps' patches arrive as box loads of 16 / VEC channels x BH rows x BW columns.
+        // A box must start on a 16-byte boundary of global memory (an unaligned first column is an
         // illegal instruction: tools/tma_probe.cu), so it starts at X0 rounded down to 4 columns
+        const int BC = 4 * tma_ch(VEC, wc);
+        const int set = BC == 4 ? 0 : (BC == 8 ? 1 : 2);
         const int X0a = t.X0 & ~3;
         const int fwa = t.X1 - X0a + 1;
         int cls = 0;
         while (cls < kNumBW - 1 && tma_bw(cls) < fwa) ++cls;
-        const int BW = tma_bw(cls), BH = tma_bh(cls);
-        const int slot_bytes = kTmaCh * BW * BH * 4;
+        const int BW = tma_bw(cls), BH = tma_bh(set, cls);
+        const int slot_bytes = BC * BW * BH * 4;
         // the slots must be 128-byte aligned; every warp's ring ends in a 128-byte pad
         const unsigned tile_sa = (unsigned)__cvta_generic_to_shared(tile);
         const int lead = (int)((128u - (tile_sa & 127u)) & 127u);
         const int per_warp = ((avail * 4 - lead) / RA_WARPS) & ~127;
         int nslot = (per_warp - 128) / slot_bytes;
         nslot = nslot > p.tma_slots ? p.tma_slots : nslot;
-        if (((p.tma_mask[lv] >> cls) & 1u) && nslot >= 2 && fwa <= BW) {
+        if (((p.tma_mask[lv][set] >> cls) & 1u) && nslot >= 2 && fwa <= BW) {
             const int warp = threadIdx.x >> 5;
             FwdTmaArgs a;
-            a.map = &tm.m[lv][cls];
+            a.map = &tm.m[lv][set][cls];
             a.obase = B.ptr + (long long)un.i * B.sN + (long long)c0 * B.sC;
             a.ytab = t.ytab; a.rcnt = t.rcnt; a.xs = t.xs; a.wx = t.wx;
             a.ring = reinterpret_cast<float*>(reinterpret_cast<char*>(tile) + lead + (size_t)warp * per_warp);
@@ -1199,13 +1256,16 @@ __device__ void fwd_unit(const RaParams& p, const TmaMaps& tm, const TmaShared t
             a.nslot = nslot; a.nc = c1 - c0;
             a.cidx0 = batch * p.C + c0;
             a.chs = p.tma_rowmajor ? BW : BH * BW;
-            a.rws = p.tma_rowmajor ? kTmaCh * BW : BW;
+            a.rws = p.tma_rowmajor ? BC * BW : BW;
+            a.diag = p.diag;
+            if (p.diag & 8) return;   // measurement only: tables and unit bookkeeping alone
             if (wc == 2) fwd_warp_tma<VEC, 2>(a);
             else if (wc == 4) fwd_warp_tma<VEC, 4>(a);
             else fwd_warp_tma<VEC, 8>(a);
             return;
         }
     }
+    if (p.diag & 4) return;   // measurement only: units that do not take the TMA path are skipped
     if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
         B.sC < (1 << 24) && B.sH < (1 << 24)) {
         // fast path: every warp streams its channels' patch rows through a private ring of row slots
@@ -1910,7 +1970,7 @@ static int env_int(const char* name, int dflt) {
 // variants; the defaults are the shipped configuration).
 struct RaConfig {
     int want, cg, interleave, fwd_smem_kb, bwd_smem_kb, fwd_dynamic, bwd_dynamic, bias;
-    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2;
+    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2, diag;
 };
 static const RaConfig& config() {
     static const RaConfig c = [] {
@@ -1928,6 +1988,7 @@ static const RaConfig& config() {
         r.tma_rowmajor = env_int("DM_RA_TMA_ROWMAJOR", 1);
         r.tma_slots = env_int("DM_RA_TMA_SLOTS", 3);
         r.tma_l2 = env_int("DM_RA_TMA_L2", 0);
+        r.diag = env_int("DM_RA_DIAG", 0);
         return r;
     }();
     return c;
@@ -1952,7 +2013,7 @@ static EncodeTiledFn encode_fn() {
 
 // The maps of one level: pure host arithmetic, ~0.05 us per map (tools/tma_probe.cu), so they are
 // simply encoded per launch -- no cache, no state.  Returns the bit mask of the usable width classes.
-static unsigned level_maps(const LevelDesc& d, int rowmajor, int l2, CUtensorMap* out) {
+static unsigned level_maps(const LevelDesc& d, int set, int rowmajor, int l2, CUtensorMap* out) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 0u;
     // TMA needs unit inner stride, a 16-byte aligned base, strides that are multiples of 16 bytes,
@@ -1962,6 +2023,7 @@ static unsigned level_maps(const LevelDesc& d, int rowmajor, int l2, CUtensorMap
         return 0u;
     unsigned mask = 0u;
     const cuuint64_t nc = (cuuint64_t)d.N * (cuuint64_t)d.C;
+    const cuuint32_t bc = 4u << set;
     for (int c = 0; c < kNumBW; ++c) {
         cuuint64_t dims[3];
         cuuint64_t strides[2];
@@ -1972,11 +2034,11 @@ static unsigned level_maps(const LevelDesc& d, int rowmajor, int l2, CUtensorMap
         if (rowmajor) {   // (x, channel, y): a box lands as [row][channel][BW]
             dims[1] = nc; dims[2] = (cuuint64_t)d.H;
             strides[0] = (cuuint64_t)d.sC * 4; strides[1] = (cuuint64_t)d.sH * 4;
-            box[1] = kTmaCh; box[2] = (cuuint32_t)tma_bh(c);
+            box[1] = bc; box[2] = (cuuint32_t)tma_bh(set, c);
         } else {          // (x, y, channel): [channel][row][BW]
             dims[1] = (cuuint64_t)d.H; dims[2] = nc;
             strides[0] = (cuuint64_t)d.sH * 4; strides[1] = (cuuint64_t)d.sC * 4;
-            box[1] = (cuuint32_t)tma_bh(c); box[2] = kTmaCh;
+            box[1] = (cuuint32_t)tma_bh(set, c); box[2] = bc;
         }
         const CUtensorMapL2promotion prom = l2 == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                           : l2 == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -1995,7 +2057,7 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
                        const int64_t* feat_strides, const float* spatial_scales, int L,
                        const float* rois, int K, const int32_t* lvl, const int32_t* perm,
                        const int32_t* seg, int nb, const int32_t* out_hw, float* const* out_ptrs,
-                       const int64_t* out_strides, int sampling_ratio, int aligned) {
+                       const int64_t* out_strides, int sampling_ratio, int aligned, bool fwd_tma) {
     if (L < 1 || L > DM_MAX_LEVELS || nb < 1 || nb > DM_MAX_BUCKETS || K < 0) return DM_EINVAL;
     if (!feat_ptrs || !feat_shapes || !feat_strides || !spatial_scales || !out_hw || !out_ptrs || !out_strides)
         return DM_EINVAL;
@@ -2053,9 +2115,11 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
             // SM, but never below what one pass of a CTA's warps covers (8 warps x channels per warp).
             // Measured on the C3 extractor calls (tools/c3_breakdown.py): 7x7 x 1024 RoIs bwd 0.89 ->
             // 0.54 ms, 56x56 single-level x 256 RoIs fwd 1.33 -> 0.78 ms.
-            const int pwv_guess = (d.pw % 4 == 0) ? d.pw / 4 : ((d.pw % 2 == 0) ? d.pw / 2 : d.pw);
+            const int vec_guess = (d.pw % 4 == 0) ? 4 : ((d.pw % 2 == 0) ? 2 : 1);
+            const int pwv_guess = d.pw / vec_guess;
             const int cpw_guess = pwv_guess >= 32 ? 1 : 32 / pwv_guess;
-            const int cg_min = 8 * (cpw_guess > 4 ? 4 : cpw_guess);
+            // (on the TMA path a warp pass covers 4 * tma_ch channels)
+            const int cg_min = 8 * (pwv_guess <= 8 && fwd_tma ? 4 * tma_ch(vec_guess, 4) : (cpw_guess > 4 ? 4 : cpw_guess));
             const long long want = (long long)config().want * sm_count();
             int small = 256;
             while (small > cg_min && (long long)K * ((p.C + small - 1) / small) < want) small >>= 1;
@@ -2140,13 +2204,25 @@ static int launch(RaParams& p, cudaStream_t st, unsigned* sched, const char* whe
         DM_CUDA_CHECK(cudaMemsetAsync(p.tickets, 0, sizeof(unsigned) * DM_MAX_BUCKETS, st), where);
     }
     // tensor maps of the levels (forward patch loads)
-    static_assert(sizeof(TmaMaps) <= 16384, "kernel parameter space");
+    static_assert(sizeof(TmaMaps) + sizeof(RaParams) <= 32000, "kernel parameter space");
     TmaMaps tm;
     p.tma_rowmajor = cf.tma_rowmajor ? 1 : 0;
+    p.diag = cf.diag;
     p.tma_slots = cf.tma_slots < 2 ? 2 : (cf.tma_slots > kTmaMaxSlots ? kTmaMaxSlots : cf.tma_slots);
-    for (int l = 0; l < DM_MAX_LEVELS; ++l) p.tma_mask[l] = 0u;
+    for (int l = 0; l < kTmaLevels; ++l)
+        for (int s2 = 0; s2 < kTmaSets; ++s2) p.tma_mask[l][s2] = 0u;
     if (!BWD && cf.tma && p.mode == 0) {
-        for (int l = 0; l < p.L; ++l) p.tma_mask[l] = level_maps(p.lv[l], p.tma_rowmajor, cf.tma_l2, tm.m[l]);
+        // only the channel sets this launch's buckets can use (buckets with <= 8 strips per pooled row)
+        for (int b = 0; b < p.nb; ++b) {
+            const BucketDesc& d = p.bk[b];
+            if (d.pw / d.vec > 8 || d.sW != 1) continue;
+            for (int jw = 4; jw <= 8; jw += 4) {
+                const int bc = 4 * tma_ch(d.vec, jw);
+                const int set = bc == 4 ? 0 : (bc == 8 ? 1 : 2);
+                for (int l = 0; l < p.L && l < kTmaLevels; ++l)
+                    if (!p.tma_mask[l][set]) p.tma_mask[l][set] = level_maps(p.lv[l], set, p.tma_rowmajor, cf.tma_l2, tm.m[l][set]);
+            }
+        }
     }
     auto kern = dyn ? ra_kernel<BWD, true> : ra_kernel<BWD, false>;
     kern<<<grid, threads, smem_bytes, st>>>(p, tm);
@@ -2166,7 +2242,8 @@ extern "C" int dm_roi_align_fwd(const float* const* feat_ptrs, const int32_t* fe
     dm::RaParams p;
     const int rc = dm::fill_params(p, const_cast<float* const*>(feat_ptrs), feat_shapes, feat_strides,
                                    spatial_scales, num_levels, rois, K, lvl, perm, seg_offsets,
-                                   num_buckets, out_hw, out_ptrs, out_strides, sampling_ratio, aligned);
+                                   num_buckets, out_hw, out_ptrs, out_strides, sampling_ratio, aligned,
+                                   dm::config().tma != 0);
     if (rc != DM_OK) return rc;
     if (K == 0) return DM_OK;
     for (int b = 0; b < num_buckets; ++b)
@@ -2185,7 +2262,7 @@ extern "C" int dm_roi_align_bwd(float* const* grad_feat_ptrs, const int32_t* fea
     const int rc = dm::fill_params(p, grad_feat_ptrs, feat_shapes, feat_strides, spatial_scales,
                                    num_levels, rois, K, lvl, perm, seg_offsets, num_buckets, out_hw,
                                    const_cast<float* const*>(grad_out_ptrs), grad_out_strides,
-                                   sampling_ratio, aligned);
+                                   sampling_ratio, aligned, false);
     if (rc != DM_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (zero_init) {
@@ -2217,7 +2294,7 @@ extern "C" int dm_simple_roi_align_fwd(const float* feat, const int32_t* feat_sh
     float* fp = const_cast<float*>(feat);
     const int32_t hw[2] = {out_h, out_w};
     const int rc = dm::fill_params(p, &fp, feat_shape, feat_strides, &spatial_scale, 1, rois, K, nullptr,
-                                   nullptr, nullptr, 1, hw, &out, out_strides, 0, aligned);
+                                   nullptr, nullptr, 1, hw, &out, out_strides, 0, aligned, false);
     if (rc != DM_OK) return rc;
     if (K == 0) return DM_OK;
     p.mode = 1;
@@ -2234,7 +2311,7 @@ extern "C" int dm_simple_roi_align_bwd(float* grad_feat, const int32_t* feat_sha
     float* go = const_cast<float*>(grad_out);
     const int32_t hw[2] = {out_h, out_w};
     const int rc = dm::fill_params(p, &grad_feat, feat_shape, feat_strides, &spatial_scale, 1, rois, K,
-                                   nullptr, nullptr, nullptr, 1, hw, &go, grad_out_strides, 0, aligned);
+                                   nullptr, nullptr, nullptr, 1, hw, &go, grad_out_strides, 0, aligned, false);
     if (rc != DM_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (zero_init) {
