@@ -156,6 +156,35 @@ __device__ __forceinline__ void red_add_if(float* p, float v, bool on) {
                  ::"l"(__cvta_generic_to_global(p)), "f"(v), "r"((int)on) : "memory");
 }
 
+// Same, the target given as a global base address plus a 32-bit float offset: the address is one wide
+// multiply-add inside the asm block (no generic-to-global conversion, no 64-bit pointer to carry).
+__device__ __forceinline__ void red_add_off(unsigned long long gbase, int off, float v) {
+    asm volatile("{\n.reg .u64 a;\nmad.wide.s32 a, %1, 4, %0;\nred.global.add.f32 [a], %2;\n}"
+                 ::"l"(gbase), "r"(off), "f"(v) : "memory");
+}
+
+// ... and predicated inside the asm block (no branch around the reduction)
+__device__ __forceinline__ void red_add_off_if(unsigned long long gbase, int off, float v, int on) {
+    asm volatile("{\n.reg .pred q;\n.reg .u64 a;\nsetp.ne.s32 q, %3, 0;\nmad.wide.s32 a, %1, 4, %0;\n@q red.global.add.f32 [a], %2;\n}"
+                 ::"l"(gbase), "r"(off), "f"(v), "r"(on) : "memory");
+}
+
+// Four reductions under ONE predicate: elements off, off + sc, off + 2 sc, off + 3 sc (float offsets)
+// from a global base address -- the same pixel of four consecutive channels.
+__device__ __forceinline__ void red4_off_if(unsigned long long gbase, int off, int sc, float v0, float v1, float v2,
+                                            float v3, int on) {
+    asm volatile(
+        "{\n.reg .pred q;\n.reg .u64 a0, a1, a2, a3;\n.reg .s32 o1, o2, o3;\n"
+        "setp.ne.s32 q, %8, 0;\n"
+        "add.s32 o1, %1, %2;\nadd.s32 o2, o1, %2;\nadd.s32 o3, o2, %2;\n"
+        "mad.wide.s32 a0, %1, 4, %0;\nmad.wide.s32 a1, o1, 4, %0;\nmad.wide.s32 a2, o2, 4, %0;\nmad.wide.s32 a3, o3, 4, %0;\n"
+        "@!q bra RED4_SKIP;\n"
+        "red.global.add.f32 [a0], %3;\nred.global.add.f32 [a1], %4;\n"
+        "red.global.add.f32 [a2], %5;\nred.global.add.f32 [a3], %6;\n"
+        "RED4_SKIP:\n}"
+        ::"l"(gbase), "r"(off), "r"(sc), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "r"(0), "r"(on) : "memory");
+}
+
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float2* p, const float2& v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float* p, const float& v) { __stcs(p, v); }

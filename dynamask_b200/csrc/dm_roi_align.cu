@@ -144,6 +144,8 @@ struct RaParams {
     int tma_rowmajor;
     int tma_slots;   // ring depth wanted (2 .. kTmaMaxSlots)
     int diag;        // measurement only (DM_RA_DIAG)
+    int bwd_x;       // backward: X-first walk for small pooled sizes
+    int bwd_groups;  // ... with at most this many lane groups (1, 2, 4)
 };
 
 // exact n / d whenever n * d < 2^32 (indices here are far below that)
@@ -1354,7 +1356,7 @@ constexpr int kRing = DM_BWD_RING;   // ring depth of the grad_out prefetch, in 
 #define DM_BULK_ENABLE 0   // measured slower than the per-lane cp.async ring: 12.2 / 11.0 ms vs 9.9 ms
 #endif
 #ifndef DM_BWD_SMEM_KB
-#define DM_BWD_SMEM_KB (DM_BULK_ENABLE ? 96 : 72)
+#define DM_BWD_SMEM_KB 108
 #endif
 constexpr int kBulkRows = DM_BULK_ROWS;
 constexpr int kBulkSlots = DM_BULK_SLOTS;
@@ -1627,6 +1629,199 @@ __device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward, X-first walk for small pooled sizes.  Lanes are the patch's FEATURE COLUMNS from the
+// start: a lane gathers its column's share of a pooled grad_out row with the transposed X taps
+// (NT scalar shared-memory loads straight from the landed grad_out block), and accumulates the JW
+// band rows that pooled row touches in registers; a completed band row leaves as one RED per lane
+// and channel.  No transposition through a row buffer, no warp barrier per band row, and the lane
+// already owns the address it reduces into.  Four channels per lane (channel pairs as packed FP32).
+// grad_out arrives as bulk copies (cp.async.bulk, completion on an mbarrier ring): the planes of a
+// 4-channel batch are contiguous, so a batch is ONE copy when it fits a slot (P <= 14), else one
+// copy of 8 pooled rows per channel.
+// Requires a dense NCHW grad_out bucket with 16-byte aligned planes, JY <= JW, at most NT pooled
+// columns over any feature column, unit inner stride of the gradient map.
+// ---------------------------------------------------------------------------------------------
+struct BwdXArgs {
+    const float* gbase;  // grad_out element (i, c0, 0, 0)
+    float* dbase;        // gradient-map element (batch, c0, Y0, X0)
+    const float* ytab;   // packed Y records (shared)
+    const int* rcnt;     // pooled rows per band row (shared)
+    const int* plo;      // first pooled column touching feature column x (shared)
+    const int* pcnt;     // pooled columns touching feature column x (shared)
+    const float* wxT;    // transposed X weights [fw][TW] (shared)
+    float* slots;        // this warp's grad_out slots (shared, 16-byte aligned), a pad behind them
+    unsigned bar_sa;     // shared address of this warp's first mbarrier
+    unsigned* phase;     // this warp's parity bits (shared)
+    int dsC, dsH;        // gradient-map strides in floats
+    int Ph, Pw, R, fw, TW, nc, nslot;
+    int rb;              // pooled rows per chunk (== Ph: the whole 4-channel batch is one copy)
+    int slotf;           // floats per slot
+    int diag;            // measurement only (DM_RA_DIAG): 16 = no reductions, 32 = no grad_out loads
+    int groups;          // lane groups (1, 2, 4): narrow patches give every group its own four channels
+};
+
+template <int JW, int NT>
+__device__ __noinline__ void bwd_warp_x(const BwdXArgs a) {
+    constexpr int CH = 4;   // channels per lane
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Ph = a.Ph, Pw = a.Pw, R = a.R, nc = a.nc, nslot = a.nslot, rb = a.rb;
+    const float* __restrict__ ytab = a.ytab;
+    const int* __restrict__ rcnt = a.rcnt;
+    __builtin_assume(__isShared(ytab));
+    __builtin_assume(__isShared(rcnt));
+    __builtin_assume(__isShared(a.slots));
+    __builtin_assume(__isShared(a.plo));
+    __builtin_assume(__isShared(a.pcnt));
+    __builtin_assume(__isShared(a.wxT));
+    __builtin_assume(__isShared(a.phase));
+    // narrow patches: the warp's lanes split into G groups of LG lanes, each group a different set of
+    // four channels, so a warp pass covers 4 G channels
+    const int G = a.groups, LG = 32 / G;
+    const int grp = lane / LG, xl = lane - grp * LG;
+    const int BC = CH * G;                                 // channels per warp pass
+    const int plane = Ph * Pw;
+    const bool whole = rb == Ph;
+    const int chs = whole ? plane : rb * Pw;               // floats between channels inside a slot
+    const int nchunk = (Ph + rb - 1) / rb;
+    const int step = RA_WARPS * BC;
+    const int npass = (a.fw + LG - 1) / LG;                // column passes (patches wider than a group)
+    const int nbatch = warp * BC < nc ? (nc - warp * BC + step - 1) / step : 0;
+    const int q_total = nbatch * npass * nchunk;
+    const unsigned slot_bytes = (unsigned)a.slotf * 4u;
+    const unsigned slots_sa = (unsigned)__cvta_generic_to_shared(a.slots);
+    unsigned par = *a.phase;
+    // stale bytes behind a short chunk and the pad behind the last slot meet zero weights: finite
+    for (int q = lane * 4; q < nslot * a.slotf + 32; q += 128)
+        *reinterpret_cast<float4*>(a.slots + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    // ---- producer side: the chunk stream runs over (channel batch, column pass, chunk) -------------
+    int q_issue = 0, i_k = 0, i_p = 0, i_slot = 0, i_cb = warp * BC;
+    auto issue = [&]() {
+        if (q_issue < q_total) {
+            if (lane == 0 && !(a.diag & 32)) {
+                const unsigned bar = a.bar_sa + 8u * (unsigned)i_slot;
+                const unsigned dst = slots_sa + (unsigned)i_slot * slot_bytes;
+                const int nch = min(BC, nc - i_cb);
+                const int rows = min(rb, Ph - i_k * rb);
+                const float* src = a.gbase + (long long)i_cb * plane + i_k * rb * Pw;
+                if (whole) {
+                    const unsigned bytes = (unsigned)(nch * plane * 4);
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(dst, src, bytes, bar);
+                } else {
+                    const unsigned bytes = (unsigned)(rows * Pw * 4);
+                    mbar_expect_tx(bar, bytes * (unsigned)nch);
+                    for (int c = 0; c < nch; ++c) bulk_g2s(dst + (unsigned)(c * chs * 4), src + (long long)c * plane, bytes, bar);
+                }
+            }
+            ++q_issue;
+            if (++i_k == nchunk) {
+                i_k = 0;
+                if (++i_p == npass) { i_p = 0; i_cb += step; }
+            }
+            i_slot = i_slot + 1 == nslot ? 0 : i_slot + 1;
+        }
+    };
+    int q_cons = 0, c_slot = 0;
+    const float* chunk = a.slots;   // the chunk being read
+    auto acquire = [&]() {
+        if (q_cons > 0) {           // the slot just drained takes the next request
+            __syncwarp();
+            issue();
+        }
+        if (!(a.diag & 32)) {
+            mbar_wait(a.bar_sa + 8u * (unsigned)c_slot, (par >> c_slot) & 1u);
+            par ^= 1u << c_slot;
+        }
+        chunk = a.slots + c_slot * a.slotf;
+        c_slot = c_slot + 1 == nslot ? 0 : c_slot + 1;
+        ++q_cons;
+    };
+    for (int d = 0; d < nslot; ++d) issue();
+
+    constexpr int YS = 2 * JW;
+    for (int cb = warp * BC; cb < nc; cb += step) {
+        const int nact = max(0, min(CH, nc - cb - CH * grp));   // live channels of this lane's group
+        for (int cp = 0; cp < npass; ++cp) {
+            // this lane as owner of feature column x: its taps, weights as broadcast pairs
+            const int x = cp * LG + xl;
+            const bool xon = x < a.fw;
+            const int lo = xon ? a.plo[x] : 0, n = xon ? a.pcnt[x] : 0;
+            float2 wq[NT];
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                const float w = q < n ? a.wxT[x * a.TW + q] : 0.0f;
+                wq[q] = make_float2(w, w);
+            }
+            float2 acc[JW][CH / 2];
+#pragma unroll
+            for (int j = 0; j < JW; ++j)
+#pragma unroll
+                for (int c = 0; c < CH / 2; ++c) acc[j][c] = make_float2(0.0f, 0.0f);
+            // this lane's element of band row 0, first channel of its group: a global address and a
+            // running float offset
+            const unsigned long long dg =
+                (unsigned long long)__cvta_generic_to_global(a.dbase + (long long)(cb + CH * grp) * a.dsC + x);
+            int doff = 0;
+            // (the caller only sends slabs of whole channel groups here: a group's four channels are all live)
+            const int red_on = xon && nact > 0 && !(a.diag & 16);
+            const int lane_off = lo + CH * grp * chs;   // this lane's first tap inside a chunk row, its first channel
+            const float* yrec = ytab;
+            int rows_left = 0;                 // pooled rows of the current chunk not yet read
+            const float* gp = chunk;           // this lane's first tap of the next pooled row
+            // The band rows rotate through the accumulators: in step u of a group of JW band rows the
+            // logical band row j lives in acc[(j + u) % JW] (compile-time after unrolling), so a retired
+            // row's accumulator is simply cleared and reused -- no register moves.
+            for (int base0 = 0; base0 < R; base0 += JW) {
+#pragma unroll
+                for (int u = 0; u < JW; ++u) {
+                    const int base = base0 + u;
+                    if (base < R) {
+                        const int nrow = rcnt[base];
+                        for (int k = 0; k < nrow; ++k) {
+                            if (rows_left == 0) {
+                                acquire();
+                                rows_left = rb;
+                                gp = chunk + lane_off;
+                            }
+                            __builtin_assume(__isShared(gp));   // (LDS, not generic LD)
+                            --rows_left;
+                            float2 w[JW];
+                            load_yrec<JW>(yrec, w);
+                            yrec += YS;
+                            float2 t[CH / 2];
+#pragma unroll
+                            for (int q = 0; q < NT; ++q) {
+#pragma unroll
+                                for (int c = 0; c < CH / 2; ++c) {
+                                    const float2 g2 = make_float2(gp[(2 * c) * chs + q], gp[(2 * c + 1) * chs + q]);
+                                    t[c] = q == 0 ? fmul2(wq[0], g2) : ffma2(wq[q], g2, t[c]);
+                                }
+                            }
+                            gp += Pw;
+#pragma unroll
+                            for (int j = 0; j < JW; ++j)
+#pragma unroll
+                                for (int c = 0; c < CH / 2; ++c) acc[(j + u) % JW][c] = ffma2(w[j], t[c], acc[(j + u) % JW][c]);
+                        }
+                        // band row `base` is complete: one RED per channel from the lane that owns the pixel
+                        red4_off_if(dg, doff, a.dsC, acc[u][0].x, acc[u][0].y, acc[u][1].x, acc[u][1].y, red_on);
+                        doff += a.dsH;
+#pragma unroll
+                        for (int c = 0; c < CH / 2; ++c) acc[u][c] = make_float2(0.0f, 0.0f);
+                    }
+                }
+            }
+            // (every pooled row starts a band inside the patch, so the pass has read all its chunks)
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *a.phase = par;
+}
+
 template <int VEC, int JW>
 __device__ __forceinline__ void bwd_warp(const BwdWarpArgs& a, int need) {
     // tap windows: 8 pooled columns per lane when that covers every feature column, else 20
@@ -1695,7 +1890,8 @@ __device__ DM_COLD void bwd_row_pass(const LevelDesc& Lv, const BucketDesc& B, c
 }
 
 template <int VEC>
-__device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, float* smem, int* stat) {
+__device__ void bwd_unit(const RaParams& p, const TmaShared ts, const Unit& un, const int* s_seg, float* smem,
+                         int* stat) {
     const BucketDesc& B = p.bk[un.b];
     const int pos = s_seg[un.b] + un.i;
     const int k = p.perm ? p.perm[pos] : pos;
@@ -1769,6 +1965,51 @@ __device__ void bwd_unit(const RaParams& p, const Unit& un, const int* s_seg, fl
         wxT[e] = w;
     }
     const int wc = (t.JYa == 2 || t.JYa == 4 || t.JYa == 8) ? t.JYa : 0;  // rows the Y table really has
+    if (p.diag & 64) { __syncthreads(); return; }   // measurement only: tables and unit bookkeeping alone
+    if (wc && p.bwd_x && *s_tw <= 8 && B.sW == 1 && B.sH == B.pw && B.sC == (long long)B.ph * B.pw && Lv.sW == 1 &&
+        ((c1 - c0) & 3) == 0 && (c0 & 3) == 0 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24)) {
+        // X-first walk (small pooled sizes): lanes own feature columns, grad_out lands by bulk copies
+        const float* gbase = B.ptr + (long long)un.i * B.sN + (long long)c0 * B.sC;
+        const int plane = B.ph * B.pw;
+        const int per_warp = (int)((avail / RA_WARPS) & ~3ll);   // floats
+        // lane groups for narrow patches (each group four channels), as far as two slots fit
+        int G = fw <= 8 ? 4 : (fw <= 16 ? 2 : 1);
+        G = G > p.bwd_groups ? p.bwd_groups : G;
+        while (G > 1 && (((c1 - c0) % (4 * G)) != 0)) G >>= 1;
+        int rb = 0, slotf = 0, nslot = 0;
+        for (; G >= 1 && nslot < 2; G >>= 1) {
+            const int cap = (per_warp - 32) / 2;   // floats a slot may take
+            rb = 0;
+            if (4 * G * plane <= cap) { rb = B.ph; slotf = 4 * G * plane; }
+            else if ((B.pw & 3) == 0 && B.pw <= 32) {
+                for (int r = 8; r >= 2 && !rb; r >>= 1)
+                    if (4 * G * r * B.pw <= cap && r < B.ph) { rb = r; slotf = 4 * G * r * B.pw; }
+            }
+            nslot = rb ? (per_warp - 32) / slotf : 0;
+            nslot = nslot > 3 ? 3 : nslot;
+            if (nslot >= 2) break;
+        }
+        if (rb && nslot >= 2 && (reinterpret_cast<uintptr_t>(gbase) & 15u) == 0) {
+            __syncthreads();
+            const int warp = threadIdx.x >> 5;
+            BwdXArgs a;
+            a.gbase = gbase;
+            a.dbase = Lv.ptr + (long long)batch * Lv.sN + (long long)c0 * Lv.sC + (long long)t.Y0 * Lv.sH + t.X0;
+            a.ytab = t.ytab; a.rcnt = t.rcnt; a.plo = plo; a.pcnt = pcnt; a.wxT = wxT;
+            a.slots = smem + t.floats + extra + (size_t)warp * per_warp;
+            a.bar_sa = (unsigned)__cvta_generic_to_shared(ts.bars + warp * kTmaMaxSlots);
+            a.phase = ts.phase + warp;
+            a.dsC = (int)Lv.sC; a.dsH = (int)Lv.sH;
+            a.Ph = B.ph; a.Pw = B.pw; a.R = R; a.fw = fw; a.TW = TW; a.nc = c1 - c0; a.nslot = nslot;
+            a.rb = rb; a.slotf = slotf; a.diag = p.diag; a.groups = G;
+            const bool nt4 = *s_tw <= 4;
+            if (wc == 2) { if (nt4) bwd_warp_x<2, 4>(a); else bwd_warp_x<2, 8>(a); }
+            else if (wc == 4) { if (nt4) bwd_warp_x<4, 4>(a); else bwd_warp_x<4, 8>(a); }
+            else { if (nt4) bwd_warp_x<8, 4>(a); else bwd_warp_x<8, 8>(a); }
+            return;
+        }
+    }
+    if (p.diag & 128) { __syncthreads(); return; }   // measurement only: units off the X-first walk are skipped
     {
         const int PwV = B.pw / VEC;
         if (wc && PwV <= 32 && B.sW == 1 && Lv.sW == 1 && Lv.sC < (1 << 24) && Lv.sH < (1 << 24) &&
@@ -1822,13 +2063,13 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
     extern __shared__ __align__(128) float smem[];
     __shared__ int s_seg[DM_MAX_BUCKETS + 1];
     __shared__ int s_stat[ST_N];
-    __shared__ __align__(8) unsigned long long s_bars[(BWD ? 1 : 32) * kTmaMaxSlots];
+    __shared__ __align__(8) unsigned long long s_bars[32 * kTmaMaxSlots];
     __shared__ unsigned s_phase[32];
     TmaShared ts;
     ts.bars = s_bars;
     ts.phase = s_phase;
     if (threadIdx.x <= p.nb) s_seg[threadIdx.x] = p.seg ? p.seg[threadIdx.x] : (threadIdx.x == 0 ? 0 : p.K);
-    if (!BWD) {
+    {
         // one mbarrier per (warp, chunk slot), initialised once per CTA; parities carry over from unit to unit
         if (threadIdx.x < RA_WARPS * kTmaMaxSlots)
             mbar_init((unsigned)__cvta_generic_to_shared(s_bars + threadIdx.x), 1);
@@ -1893,9 +2134,9 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
             un.slab = (int)(u - (unsigned)un.i * (unsigned)p.bk[un.b].nslab);
             const int vec = BWD ? p.bk[un.b].bvec : p.bk[un.b].vec;
             if (BWD) {
-                if (vec == 4) bwd_unit<4>(p, un, s_seg, smem, s_stat);
-                else if (vec == 2) bwd_unit<2>(p, un, s_seg, smem, s_stat);
-                else bwd_unit<1>(p, un, s_seg, smem, s_stat);
+                if (vec == 4) bwd_unit<4>(p, ts, un, s_seg, smem, s_stat);
+                else if (vec == 2) bwd_unit<2>(p, ts, un, s_seg, smem, s_stat);
+                else bwd_unit<1>(p, ts, un, s_seg, smem, s_stat);
             } else {
                 if (vec == 4) fwd_unit<4>(p, tm, ts, un, s_seg, smem, s_stat);
                 else if (vec == 2) fwd_unit<2>(p, tm, ts, un, s_seg, smem, s_stat);
@@ -1946,9 +2187,9 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
         }
         const int vec = BWD ? p.bk[un.b].bvec : p.bk[un.b].vec;
         if (BWD) {
-            if (vec == 4) bwd_unit<4>(p, un, s_seg, smem, s_stat);
-            else if (vec == 2) bwd_unit<2>(p, un, s_seg, smem, s_stat);
-            else bwd_unit<1>(p, un, s_seg, smem, s_stat);
+            if (vec == 4) bwd_unit<4>(p, ts, un, s_seg, smem, s_stat);
+            else if (vec == 2) bwd_unit<2>(p, ts, un, s_seg, smem, s_stat);
+            else bwd_unit<1>(p, ts, un, s_seg, smem, s_stat);
         } else {
             if (vec == 4) fwd_unit<4>(p, tm, ts, un, s_seg, smem, s_stat);
             else if (vec == 2) fwd_unit<2>(p, tm, ts, un, s_seg, smem, s_stat);
@@ -1970,7 +2211,7 @@ static int env_int(const char* name, int dflt) {
 // variants; the defaults are the shipped configuration).
 struct RaConfig {
     int want, cg, interleave, fwd_smem_kb, bwd_smem_kb, fwd_dynamic, bwd_dynamic, bias;
-    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2, diag;
+    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2, diag, bwd_x, bwd_groups;
 };
 static const RaConfig& config() {
     static const RaConfig c = [] {
@@ -1989,6 +2230,8 @@ static const RaConfig& config() {
         r.tma_slots = env_int("DM_RA_TMA_SLOTS", 3);
         r.tma_l2 = env_int("DM_RA_TMA_L2", 0);
         r.diag = env_int("DM_RA_DIAG", 0);
+        r.bwd_x = env_int("DM_RA_BWD_X", 1);
+        r.bwd_groups = env_int("DM_RA_BWD_GROUPS", 4);
         return r;
     }();
     return c;
@@ -2208,6 +2451,8 @@ static int launch(RaParams& p, cudaStream_t st, unsigned* sched, const char* whe
     TmaMaps tm;
     p.tma_rowmajor = cf.tma_rowmajor ? 1 : 0;
     p.diag = cf.diag;
+    p.bwd_x = (cf.bwd_x && p.mode == 0) ? 1 : 0;
+    p.bwd_groups = cf.bwd_groups >= 4 ? 4 : (cf.bwd_groups >= 2 ? 2 : 1);
     p.tma_slots = cf.tma_slots < 2 ? 2 : (cf.tma_slots > kTmaMaxSlots ? kTmaMaxSlots : cf.tma_slots);
     for (int l = 0; l < kTmaLevels; ++l)
         for (int s2 = 0; s2 < kTmaSets; ++s2) p.tma_mask[l][s2] = 0u;
