@@ -321,6 +321,148 @@ extern "C" int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, in
     return DM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device side: transitions -> pycocotools' compressed "counts" strings (rleToString), so that only
+// the strings cross PCIe and the host does no per-run work.  One CTA per instance, three launches:
+//   compact   drops the coinciding transition pairs (a run continuing across a column boundary;
+//             they only ever come in pairs, so "has an equal neighbour" is the host's
+//             skip-both rule), writes the survivors to `compact` and the string length to str_len
+//   scan      exclusive scan of the N string lengths (one CTA) -> str_offsets[N+1]
+//   write     count k = t'[k] - t'[k-1] (and the closing run); from the fourth count on the
+//             difference to the count two before is stored; base-32 varint, 6 bits per char + 48
+// ---------------------------------------------------------------------------------------------
+namespace dm {
+
+// chars of rleToString's code for x (signed base-32 varint, continuation bit 0x20)
+__device__ __forceinline__ int rle_code_len(long long x) {
+    int n = 0;
+    bool more = true;
+    while (more) {
+        const int c = (int)(x & 0x1f);
+        x >>= 5;
+        more = (c & 0x10) ? x != -1 : x != 0;
+        ++n;
+    }
+    return n;
+}
+
+__device__ __forceinline__ void rle_code_write(long long x, char* out) {
+    bool more = true;
+    while (more) {
+        int c = (int)(x & 0x1f);
+        x >>= 5;
+        more = (c & 0x10) ? x != -1 : x != 0;
+        if (more) c |= 0x20;
+        *out++ = (char)(c + 48);
+    }
+}
+
+// value stored for count k of an instance whose surviving transitions are tp[0..m): the count itself
+// for k < 3, else its difference to the count two before.  k == m is the closing run.
+__device__ __forceinline__ long long rle_count(const int32_t* tp, int m, int k, long long total_pixels) {
+    auto t = [&](int i) -> long long { return i < 0 ? 0ll : (i < m ? (long long)tp[i] : total_pixels); };
+    return t(k) - t(k - 1);
+}
+__device__ __forceinline__ long long rle_stored(const int32_t* tp, int m, int k, long long total_pixels) {
+    const long long c = rle_count(tp, m, k, total_pixels);
+    return k > 2 ? c - rle_count(tp, m, k - 2, total_pixels) : c;
+}
+
+template <int PASS>   // 1: compact + lengths, 2: write strings
+__global__ void __launch_bounds__(kRleThreads)
+rle_string_kernel(const int32_t* __restrict__ trans, const int64_t* __restrict__ inst_offsets, long long total_pixels,
+                  int32_t* __restrict__ compact, int32_t* __restrict__ kept, int32_t* __restrict__ str_len,
+                  const int64_t* __restrict__ str_offsets, char* __restrict__ out) {
+    __shared__ int s_warp[kRleThreads / 32];
+    const int n = blockIdx.x;
+    const long long o0 = inst_offsets[n];
+    const int cnt = (int)(inst_offsets[n + 1] - o0);
+    const int32_t* t = trans + o0;
+    int32_t* tp = compact + o0;
+    if (PASS == 1) {
+        int m = 0;
+        for (int i0 = 0; i0 < cnt; i0 += kRleThreads) {
+            const int i = i0 + threadIdx.x;
+            int keep = 0, v = 0;
+            if (i < cnt) {
+                v = t[i];
+                keep = (i == 0 || t[i - 1] != v) && (i + 1 >= cnt || t[i + 1] != v);
+            }
+            int tot;
+            const int pos = block_exclusive_scan(keep, s_warp, tot);
+            if (keep) tp[m + pos] = v;
+            m += tot;
+        }
+        __syncthreads();
+        // counts 0 .. m-1 from the transitions, and the closing run when the last one ends early
+        const long long last = m > 0 ? (long long)tp[m - 1] : 0ll;
+        const int nc = m + ((last < total_pixels || m == 0) ? 1 : 0);
+        int len = 0;
+        for (int k = threadIdx.x; k < nc; k += kRleThreads) len += rle_code_len(rle_stored(tp, m, k, total_pixels));
+        int tot;
+        block_exclusive_scan(len, s_warp, tot);
+        if (threadIdx.x == 0) {
+            kept[n] = m;
+            str_len[n] = tot;
+        }
+    } else {
+        const int m = kept[n];
+        const long long last = m > 0 ? (long long)tp[m - 1] : 0ll;
+        const int nc = m + ((last < total_pixels || m == 0) ? 1 : 0);
+        char* dst = out + str_offsets[n];
+        int base = 0;
+        for (int k0 = 0; k0 < nc; k0 += kRleThreads) {
+            const int k = k0 + threadIdx.x;
+            long long x = 0;
+            int len = 0;
+            if (k < nc) {
+                x = rle_stored(tp, m, k, total_pixels);
+                len = rle_code_len(x);
+            }
+            int tot;
+            const int pos = block_exclusive_scan(len, s_warp, tot);
+            if (k < nc) rle_code_write(x, dst + base + pos);
+            base += tot;
+        }
+    }
+}
+
+// exclusive scan of N string lengths -> str_offsets[N+1] (one CTA; N is a few hundred)
+__global__ void __launch_bounds__(kRleThreads) rle_offsets_kernel(const int32_t* __restrict__ str_len, int N,
+                                                                  int64_t* __restrict__ str_offsets) {
+    __shared__ int s_warp[kRleThreads / 32];
+    long long base = 0;
+    for (int i0 = 0; i0 < N; i0 += kRleThreads) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < N ? str_len[i] : 0;
+        int tot;
+        const int pos = block_exclusive_scan(v, s_warp, tot);
+        if (i < N) str_offsets[i] = base + pos;
+        base += tot;
+    }
+    if (threadIdx.x == 0) str_offsets[N] = base;
+}
+
+}  // namespace dm
+
+extern "C" int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int N, int64_t total_pixels,
+                              int32_t* compact, int32_t* kept, int32_t* str_len, int64_t* str_offsets, char* out,
+                              dm_stream_t stream) {
+    if (N < 0 || total_pixels < 0) return DM_EINVAL;
+    if (N == 0) return DM_OK;
+    if (!transitions || !inst_offsets || !compact || !kept || !str_len || !str_offsets || !out) return DM_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    dm::rle_string_kernel<1><<<N, dm::kRleThreads, 0, st>>>(transitions, inst_offsets, (long long)total_pixels, compact,
+                                                           kept, str_len, nullptr, nullptr);
+    DM_LAUNCH_CHECK("dm_rle_strings/compact");
+    dm::rle_offsets_kernel<<<1, dm::kRleThreads, 0, st>>>(str_len, N, str_offsets);
+    DM_LAUNCH_CHECK("dm_rle_strings/scan");
+    dm::rle_string_kernel<2><<<N, dm::kRleThreads, 0, st>>>(transitions, inst_offsets, (long long)total_pixels, compact,
+                                                           kept, str_len, str_offsets, out);
+    DM_LAUNCH_CHECK("dm_rle_strings/write");
+    return DM_OK;
+}
+
 // Host side: transitions of ONE instance -> pycocotools' compressed counts string.
 // counts = run lengths alternating from a run of zeros; the string is rleToString's base-32 varint
 // code with each count beyond the second stored as a difference from the count two before.

@@ -328,29 +328,43 @@ def _(gt_blob, img_offsets, img_ghw, boxes, inds, roi_img, clip, sizes_hw):
 # dm_paste_rle / dm_rle_from_canvas / dm_rle_compress_host  
 # --------------------------------------------------------------------------------------------
 def _rle_finish(N, rh, rw, totals, run_pass2):
-    """Shared tail of the two RLE entry points: scan the per-instance totals, run pass 2, bring the
-    transitions to the host (a few KB per instance) and compress them to pycocotools strings."""
+    """Shared tail of the two RLE entry points.  The per-instance totals reach the host through
+    pinned memory (the first of two synchronisations: the host sizes the buffers), pass 2 writes the
+    transitions, ``dm_rle_strings`` turns them into pycocotools strings ON THE DEVICE, and one pinned
+    copy brings ``[string offsets | strings]`` back (second synchronisation).  The host only slices
+    N ``bytes`` objects out of that blob."""
     import numpy as np
-    totals_h = totals.cpu().numpy().astype(np.int64)         # one small D2H + sync
-    offsets_h = np.zeros(N + 1, np.int64)
-    np.cumsum(totals_h, out=offsets_h[1:])
-    total = int(offsets_h[-1])
     dev = totals.device
-    offsets = torch.from_numpy(offsets_h[:-1].copy()).to(dev)
+    stream = torch.cuda.current_stream(dev)
+    totals_pin = torch.empty(N, dtype=torch.int32, pin_memory=True)
+    totals_pin.copy_(totals, non_blocking=True)
+    stream.synchronize()
+    offsets_pin = torch.empty(N + 1, dtype=torch.int64, pin_memory=True)
+    offsets_h = offsets_pin.numpy()
+    offsets_h[0] = 0
+    np.cumsum(totals_pin.numpy(), out=offsets_h[1:])
+    total = int(offsets_h[-1])
+    offsets = offsets_pin.to(dev, non_blocking=True)
     trans = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     run_pass2(offsets, trans)
-    trans_h = np.ascontiguousarray(trans[:max(total, 1)].cpu().numpy())
-    lib = _lib.load()
+    head = 8 * (N + 1)
     cap = 6 * total + 8 * N + 8
-    buf = np.empty(cap, np.uint8)
-    str_off = np.empty(N + 1, np.int64)
-    ln = lib.dm_rle_compress_batch_host(ctypes.c_void_p(trans_h.ctypes.data), ctypes.c_void_p(offsets_h.ctypes.data),
-                                        N, int(rh) * int(rw), ctypes.c_void_p(buf.ctypes.data), cap,
-                                        ctypes.c_void_p(str_off.ctypes.data))
-    if ln < 0:
-        raise RuntimeError('dm_rle_compress_batch_host: buffer too small')
-    raw = buf[:ln].tobytes()
-    return [{'size': [int(rh), int(rw)], 'counts': raw[str_off[n]:str_off[n + 1]]} for n in range(N)]
+    blob = torch.empty(head + cap, dtype=torch.uint8, device=dev)
+    str_offsets = blob[:head].view(torch.int64)
+    scratch = torch.empty(max(total, 1) + 2 * N, dtype=torch.int32, device=dev)
+    compact, kept, str_len = scratch[:max(total, 1)], scratch[max(total, 1):max(total, 1) + N], scratch[max(total, 1) + N:]
+    with torch.cuda.device(dev):
+        rc = _lib.load().dm_rle_strings(_ptr(trans), _ptr(offsets), N, int(rh) * int(rw), _ptr(compact), _ptr(kept),
+                                        _ptr(str_len), _ptr(str_offsets), ctypes.c_void_p(blob.data_ptr() + head),
+                                        _stream(dev))
+    _lib.check(rc, 'dm_rle_strings')
+    blob_pin = torch.empty(head + cap, dtype=torch.uint8, pin_memory=True)
+    blob_pin.copy_(blob, non_blocking=True)
+    stream.synchronize()
+    so = blob_pin[:head].view(torch.int64).tolist()
+    raw = blob_pin[head:head + so[-1]].numpy().tobytes()
+    size = [int(rh), int(rw)]
+    return [{'size': size, 'counts': raw[so[n]:so[n + 1]]} for n in range(N)]
 
 
 def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,

@@ -172,6 +172,20 @@ int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int
                        int32_t* inst_totals, const int64_t* inst_offsets, int32_t* transitions,
                        dm_stream_t stream);
 /*
+ * Device side of rleToString: the transitions of N instances (instance n owns
+ * transitions[inst_offsets[n] .. inst_offsets[n+1]); inst_offsets has N+1 entries, device) become
+ * pycocotools' compressed "counts" strings, written back to back into `out` with string n at
+ * out[str_offsets[n] .. str_offsets[n+1]) -- only the strings need to cross PCIe.  Caller-owned
+ * device scratch: compact [sum of transitions] int32, kept [N] int32, str_len [N] int32;
+ * str_offsets [N+1] int64 and out (6 bytes per transition + 8 per instance always suffice) are
+ * outputs.  Three small launches (compact + lengths, scan, write), no host synchronisation.
+ * Replaces the string building of pycocotools mask.encode reached from
+ * mmdet/core/mask/utils.py:36-63.
+ */
+int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int N, int64_t total_pixels,
+                   int32_t* compact, int32_t* kept, int32_t* str_len, int64_t* str_offsets, char* out,
+                   dm_stream_t stream);
+/*
  * HOST function: the transitions of one instance (host memory) -> pycocotools' compressed "counts"
  * string (rleToString).  Coinciding transition pairs cancel.  Returns the length written to `out`
  * (no terminator) or -1 if `cap` is too small.

@@ -284,3 +284,56 @@ def test_forward_pure_relative_error_report():
     if path:
         with open(path, 'a') as f:
             f.write(json.dumps({'forward_relative_error': report}) + '\n')
+
+
+# ------------------------------------------------------------------------------------------
+# device-side rleToString (dm_rle_strings) == the host compressor on the same transitions
+# ------------------------------------------------------------------------------------------
+def test_device_rle_strings_equal_host_compressor():
+    import numpy as np
+    from dynamask_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    H, W = 431, 637
+    total_pixels = H * W
+    per = [0, 1, 2, 7, 300, 1500, 5000]
+    lists = []
+    for n in per:
+        t = np.sort(rng.choice(total_pixels + 1, size=n, replace=False)).astype(np.int32)
+        # coinciding pairs (a run continuing across a column boundary) and a run reaching the last pixel
+        if n >= 7:
+            t = np.sort(np.concatenate([t, t[3:4], t[5:6]])).astype(np.int32)
+        lists.append(t)
+    lists.append(np.array([17, total_pixels], dtype=np.int32))           # ends exactly at the last pixel
+    lists.append(np.array([0, 5, 5, 9], dtype=np.int32))                 # starts with foreground
+    N = len(lists)
+    offs = np.zeros(N + 1, np.int64)
+    offs[1:] = np.cumsum([len(t) for t in lists])
+    trans = np.concatenate(lists).astype(np.int32)
+    total = int(offs[-1])
+    cap = 6 * total + 8 * N + 8
+    buf = np.empty(cap, np.uint8)
+    so = np.empty(N + 1, np.int64)
+    ln = lib.dm_rle_compress_batch_host(ctypes.c_void_p(trans.ctypes.data), ctypes.c_void_p(offs.ctypes.data), N,
+                                        total_pixels, ctypes.c_void_p(buf.ctypes.data), cap, ctypes.c_void_p(so.ctypes.data))
+    assert ln >= 0
+    want = [buf[so[n]:so[n + 1]].tobytes() for n in range(N)]
+    d_trans = torch.from_numpy(trans).cuda()
+    d_offs = torch.from_numpy(offs).cuda()
+    compact = torch.empty(total, dtype=torch.int32, device='cuda')
+    kept = torch.empty(N, dtype=torch.int32, device='cuda')
+    slen = torch.empty(N, dtype=torch.int32, device='cuda')
+    soff = torch.empty(N + 1, dtype=torch.int64, device='cuda')
+    out = torch.zeros(cap, dtype=torch.uint8, device='cuda')
+    vp = ctypes.c_void_p
+    rc = lib.dm_rle_strings(vp(d_trans.data_ptr()), vp(d_offs.data_ptr()), N, total_pixels, vp(compact.data_ptr()),
+                            vp(kept.data_ptr()), vp(slen.data_ptr()), vp(soff.data_ptr()), vp(out.data_ptr()),
+                            vp(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    so_d = soff.cpu().numpy()
+    raw = out.cpu().numpy()
+    assert int(so_d[-1]) == ln
+    for n in range(N):
+        assert raw[so_d[n]:so_d[n + 1]].tobytes() == want[n], n
+        # and the host string decodes to the run list the oracle builds from the same transitions
+        assert O.rle_from_string(want[n]) is not None
