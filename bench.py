@@ -51,10 +51,11 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the C3 / C4 / C5 workloads')
     ap.add_argument('--no-competitor', action='store_true', help='skip the torchvision-CUDA leg (e.g. under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--e2e-chunk-images', type=int, default=2)
-    ap.add_argument('--cpu-sample-rois', type=int, default=8, help='RoIs per image in the CPU sample')
+    ap.add_argument('--cpu-sample-rois', type=int, default=512, help='RoIs per image in the CPU sample (config: 512)')
     return ap.parse_args()
 
 
@@ -253,11 +254,27 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU path (oracle port) used by cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------------
+def _reference_extractors():
+    """The reference's own, unmodified SingleRoIExtractor (one per pooled size) when its tree is
+    present (the build container; /root/reference does not exist on the GPU box), else None.  The
+    RoIAlign layer under it is torchvision's CPU kernel either way (mmcv is not installable)."""
+    try:
+        from oracle import ref_shim
+        if not ref_shim.available():
+            return None
+        ns = ref_shim.load()
+        return [ns.SingleRoIExtractor(dict(type='RoIAlign', output_size=p, sampling_ratio=0), 256, STRIDES)
+                for p in BUCKET_SIZES]
+    except Exception:
+        return None
+
+
 def cpu_extract_fwd_bwd(n_images, rois_per_img, channels, seed, threads):
-    """Reference host path on CPU for a bounded sample of C2: per image, the per-level
-    select / RoIAlign / scatter loop (oracle.single_roi_extractor) at the RoI's selected size, plus
-    autograd backward, with torchvision's CPU roi_align as the stand-in for the absent mmcv kernel.
-    Images are sharded over a thread pool (ATen releases the GIL).  Returns (rois, seconds)."""
+    """Reference host path on CPU for a sample of C2: per image, the per-level select / RoIAlign /
+    scatter loop at each RoI's selected size, plus autograd backward, with torchvision's CPU roi_align
+    as the stand-in for the absent mmcv kernel.  The loop is the reference's unmodified
+    SingleRoIExtractor where its tree exists, the oracle's restatement of it elsewhere.  Images are
+    sharded over a thread pool (ATen releases the GIL).  Returns (rois, seconds, kind)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle as O
@@ -268,12 +285,17 @@ def cpu_extract_fwd_bwd(n_images, rois_per_img, channels, seed, threads):
         rois = synth.make_rois(1, rois_per_img, IMG_H, IMG_W, g)
         onehot = synth.make_onehot(rois_per_img, g)
         work.append((feats, rois, onehot))
+    ref_ext = _reference_extractors()
 
     def one(item):
         torch.set_num_threads(1)
         feats, rois, onehot = item
         fr = [f.clone().requires_grad_() for f in feats]
-        outs, _, _ = O.bucketed_extract(fr, rois, onehot, BUCKET_SIZES, STRIDES, kernel=O.roi_align_tv)
+        if ref_ext is not None:
+            bucket = onehot.argmax(1)
+            outs = [ref_ext[b](fr, rois[bucket == b]) for b in range(len(BUCKET_SIZES)) if bool((bucket == b).any())]
+        else:
+            outs, _, _ = O.bucketed_extract(fr, rois, onehot, BUCKET_SIZES, STRIDES, kernel=O.roi_align_tv)
         loss = sum((o * o).sum() for o in outs) * 0.5   # grad_out = out, like the GPU step
         loss.backward()
         return float(fr[0].grad.abs().sum())
@@ -282,7 +304,7 @@ def cpu_extract_fwd_bwd(n_images, rois_per_img, channels, seed, threads):
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(one, work))
     dt = time.perf_counter() - t0
-    return n_images * rois_per_img, dt
+    return n_images * rois_per_img, dt, ('reference' if ref_ext is not None else 'port')
 
 
 def run_reference(args, rank, world):
@@ -292,26 +314,32 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 32))
-    n_img = max(1, min(threads, 16))
-    times, nrois = [], 0
+    # one step = the config's batch: 16 images x 512 RoIs, one image per worker thread
+    n_img = args.batch
+    times, nrois, kind = [], 0, 'port'
+    warm = args.warmup
     for i in range(args.warmup + args.steps):
-        n, dt = cpu_extract_fwd_bwd(n_img, args.cpu_sample_rois, args.channels, 1234 + i, threads)
-        if i >= args.warmup:
+        n, dt, kind = cpu_extract_fwd_bwd(n_img, args.cpu_sample_rois, args.channels, 1234 + i, threads)
+        if i == 0 and dt > 20.0:
+            warm = min(warm, 1)          # a step of many seconds needs no three warm-ups
+        if i >= warm:
             times.append(dt)
             nrois = n
-        if sum(times) > 150:
+        if sum(times) > 120 or len(times) >= args.steps:
             break
     steps_done = max(len(times), 1)
     ms = 1000.0 * sum(times) / steps_done
     val = nrois / (ms / 1000.0)
-    sample = '%d images x %d RoIs (uniform 14/28/56/112 mix), C=%d, fwd+bwd, thread pool over images' % (
-        n_img, args.cpu_sample_rois, args.channels)
+    sample = ('%d images x %d RoIs (uniform 14/28/56/112 mix), C=%d, fwd+bwd, thread pool over images (%d workers); %s' % (
+        n_img, args.cpu_sample_rois, args.channels, min(threads, n_img),
+        "the reference's unmodified SingleRoIExtractor over torchvision's CPU roi_align" if kind == 'reference'
+        else "oracle restatement of the reference loop over torchvision's CPU roi_align"))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': steps_done, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args),
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': min(threads, n_img), 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -461,6 +489,11 @@ def main():
     if not args.no_extras:
         line['extras'] = run_extras(dm, ops, dev, rank, peak)
 
+    # ---- BASELINE.json configs[2..4] on EVERY rank (times reduced with MAX, units summed) ---------
+    if not args.no_configs:
+        import bench_configs
+        line['configs'] = bench_configs.run_all(dm, ops, dev, rank, world, peak)
+
     if not args.no_extras and not args.no_competitor and rank == 0 and world == 1:
         line['gpu_competitor'] = run_competitor(dm, dev, rank, feats, rois, onehot)
         if 'c2_torchvision_cuda_ms' in line['gpu_competitor']:
@@ -483,13 +516,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, 32))
-        n_img = max(1, min(threads, 16))
-        n, dt = cpu_extract_fwd_bwd(n_img, args.cpu_sample_rois, C, 1234, threads)
+        # bounded sample: half the config's batch at the config's 512 RoIs per image (one image per worker)
+        n_img = max(1, min(threads, args.batch // 2))
+        n, dt, kind = cpu_extract_fwd_bwd(n_img, args.cpu_sample_rois, C, 1234, threads)
         line['cpu_baseline'] = {
-            'value': n / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'value': n / dt, 'unit': UNIT, 'cores': min(threads, n_img), 'kind': kind,
             'sample': '%d images x %d RoIs of the C2 workload (uniform size mix), fwd+bwd, one pass, '
-                      'torchvision CPU roi_align under the reference host loop, thread pool over images' % (
-                          n_img, args.cpu_sample_rois)}
+                      'torchvision CPU roi_align under the %s, thread pool over images' % (
+                          n_img, args.cpu_sample_rois,
+                          "reference's unmodified SingleRoIExtractor" if kind == 'reference' else 'reference host loop (oracle port)')}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -571,9 +606,21 @@ def run_extras(dm, ops, dev, rank, peak):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
-    ex['dm_mask_target'] = {'workload': 'C3: 2 images x 128 positives, G~U{1..20} 800x1344 bitmaps, sizes 14/28/56/112, '
-                                        'includes the per-step upload of the bitmaps',
+    ex['dm_mask_target'] = {'workload': 'C3: 2 images x 128 positives, G~U{1..20} 800x1344 bitmaps, sizes 14/28/56/112; the '
+                                        "batch's bitmaps are packed and uploaded on EVERY call (one pinned staging copy, "
+                                        '~10 MB per image) -- the same host arrays each time, so the host side is warm',
                             'ms': ms, 'rois_per_s': 256 / ms * 1e3}
+    # the kernel alone on bitmaps that are already resident (single image: the per-object device cache)
+    one = dm.BitmapMasks(masks_l[0].masks, IMG_H, IMG_W)
+    for _ in range(3):
+        t = one.crop_and_resize_device(props[0], [(14, 14), (28, 28), (56, 56), (112, 112)], inds[0], dev, clip=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        t = one.crop_and_resize_device(props[0], [(14, 14), (28, 28), (56, 56), (112, 112)], inds[0], dev, clip=True)
+    b.record()
+    torch.cuda.synchronize()
+    ex['dm_mask_target']['resident_bitmaps_one_image_ms'] = a.elapsed_time(b) / reps
     del t, masks_l
 
     def timed(fn, reps=10, warm=3):
@@ -606,15 +653,18 @@ def run_extras(dm, ops, dev, rank, peak):
     sra = {}
     for P, s in ((14, 16), (28, 8), (56, 4)):
         f = torch.randn(1, 256, IMG_H // s, IMG_W // s, device=dev, requires_grad=True)
-        layer = dm.SimpleRoIAlign(P, 1.0 / s)
+        # the reference builds every SFMStage with spatial_scale = 1 / semantic_out_stride[-1] = 1/4 while
+        # feeding it the stride 16 / 8 / 4 maps (dynamask_head.py:192, :228): measured as it runs there
+        layer = dm.SimpleRoIAlign(P, 1.0 / 4)
         ms_f, o = timed(lambda: layer(f, rois100))
         go = torch.ones_like(o)
-        ms_b, _ = timed(lambda: ops.simple_roi_align_backward(go, rois100, list(f.shape), 1.0 / s, True))
+        ms_b, _ = timed(lambda: ops.simple_roi_align_backward(go, rois100, list(f.shape), 1.0 / 4, True))
         by = o.numel() * 4
         sra['P%d_stride%d' % (P, s)] = {'fwd_ms': ms_f, 'bwd_ms_incl_zero_init': ms_b, 'out_bytes': by,
                                         'fwd_out_gbs': by / ms_f / 1e6}
         del f, o, go
-    ex['dm_simple_roi_align'] = {'workload': 'SFMStage gathers: 100 RoIs x 256 ch at 14/28/56 from stride 16/8/4 maps', **sra}
+    ex['dm_simple_roi_align'] = {'workload': 'SFMStage gathers: 100 RoIs x 256 ch at 14/28/56 from the stride 16/8/4 maps, '
+                                             "every stage with the reference's spatial_scale = 1/4", **sra}
     # fused stage-to-stage refinement, one chunk of 100 detections (28 -> 56 -> 112)
     st = [torch.randn(100, 1, sz, sz, device=dev) * 3 for sz in (28, 56, 112)]
     ms, _ = timed(lambda: dm.refine_stage_instance_preds(st))

@@ -17,6 +17,7 @@ from .roi_extractors import (BaseRoIExtractor, BucketedRoIExtractor, BucketedRoI
                              SingleRoIExtractor)
 from .sharding import checksum64, gather_checksums, image_shard, shard_rois
 from .switch import get_mask_label, gumbel_softmax
+from .switched import forward_switched, simple_test_mask_switched
 
 __version__ = '0.1.0'
 
@@ -25,5 +26,5 @@ __all__ = [
     'BucketedRoIExtractor', 'BucketedRoIFeats', 'BitmapMasks', 'PolygonMasks', 'mask_target',
     'mask_target_single', 'multi_size_mask_targets', '_do_paste_mask', 'get_seg_masks',
     'paste_masks_in_image', 'get_seg_masks_rle', 'get_seg_masks_switched', 'refine_stage_instance_preds', 'encode_mask_results', 'DynaMaskHeadMixin', 'get_mask_label', 'gumbel_softmax',
-    'image_shard', 'shard_rois', 'checksum64', 'gather_checksums'
+    'forward_switched', 'simple_test_mask_switched', 'image_shard', 'shard_rois', 'checksum64', 'gather_checksums'
 ]

@@ -4,14 +4,14 @@ variant ``DynaMaskHead.get_targets``, ``.../mask_heads/dynamask_head.py:246-271`
 The reference walks images x sizes; every step does D2H of the proposals and indices, a clip in
 numpy, an H2D upload of all the image's masks, RoIAlign, D2H of the bool result and H2D of its
 float copy.  Here the whole batch is one ``dm_mask_target`` launch: proposals and indices never
-leave the device, the clip is fused, each image's bitmaps are uploaded once (cached on the
-``BitmapMasks`` object) and all sizes are produced together.
+leave the device, the clip is fused, the bitmaps of the batch are uploaded once per step (one pinned
+staging buffer, one copy) and all sizes are produced together.
 """
 import torch
 from torch.nn.modules.utils import _pair
 
 from . import ops
-from .mask_structures import BitmapMasks, PolygonMasks, pack_polygons
+from .mask_structures import BitmapMasks, PolygonMasks, pack_bitmaps, pack_polygons
 
 
 def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list, sizes):
@@ -34,21 +34,11 @@ def _batched_targets(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_lis
         blob, offs, ghw = gt_masks_list[keep[0]].to_device(device)
         roi_img = None
     else:
-        # every image's bitmaps are uploaded once and cached on its BitmapMasks; the kernel
-        # addresses them relative to the first blob, so nothing is re-packed per step
-        blobs = [gt_masks_list[i].to_device(device)[0] for i in keep]
-        blob = blobs[0]
-        meta = torch.empty(len(keep) * 5, dtype=torch.int64, pin_memory=True)
-        meta_np = meta.numpy()
-        for j, i in enumerate(keep):
-            meta_np[j] = blobs[j].data_ptr() - blob.data_ptr() if blobs[j].numel() else 0
-        ghw_np = meta_np[len(keep):].view('int32')
-        for j, i in enumerate(keep):
-            m = gt_masks_list[i].masks
-            ghw_np[3 * j:3 * j + 3] = (m.shape[0], m.shape[1], m.shape[2])
-        meta_dev = meta.to(device, non_blocking=True)
-        offs = meta_dev[:len(keep)]
-        ghw = meta_dev[len(keep):].view(torch.int32)[:3 * len(keep)]
+        # a training step brings new ground truth: the bitmaps of the whole batch go through ONE pinned
+        # staging buffer and ONE host -> device copy into one blob the op owns for the launch
+        # (pack_bitmaps; no pointer arithmetic between separate allocations, no per-object cache to go
+        # stale), with the per-image offsets / shapes beside it
+        blob, offs, ghw = pack_bitmaps([gt_masks_list[i].masks for i in keep], device)
         counts = torch.tensor([pos_proposals_list[i].size(0) for i in keep])
         roi_img = torch.repeat_interleave(torch.arange(len(keep), dtype=torch.int32), counts).to(
             device, non_blocking=True)

@@ -337,3 +337,89 @@ def test_device_rle_strings_equal_host_compressor():
         assert raw[so_d[n]:so_d[n + 1]].tobytes() == want[n], n
         # and the host string decodes to the run list the oracle builds from the same transitions
         assert O.rle_from_string(want[n]) is not None
+
+
+# ------------------------------------------------------------------------------------------
+# switch-driven inference end to end: only the selected stages run
+# ------------------------------------------------------------------------------------------
+class _FakeStage(torch.nn.Module):
+    """SFMStage's call signature (dynamask_head.py:228) over two small convolutions."""
+
+    def __init__(self, cin, cout, ncls):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(cin, cout, 3, padding=1)
+        self.logits = torch.nn.Conv2d(cin, ncls, 1)
+        self.calls = []
+
+    def forward(self, feats, semantic_feat, rois, roi_labels, upsample):
+        self.calls.append(int(feats.size(0)))
+        pred = self.logits(feats)[torch.arange(feats.size(0), device=feats.device), roi_labels][:, None]
+        out = torch.relu(self.conv(feats))
+        if upsample:
+            out = torch.nn.functional.interpolate(out, scale_factor=2, mode='bilinear', align_corners=False)
+        return pred, pred, out
+
+
+class _FakeHead(torch.nn.Module):
+    def __init__(self, c=16, ncls=3):
+        super().__init__()
+        self.instance_convs = torch.nn.ModuleList([torch.nn.Conv2d(c, c, 3, padding=1)])
+        self.stages = torch.nn.ModuleList([_FakeStage(c, c // 2, ncls), _FakeStage(c // 2, c // 4, ncls),
+                                           _FakeStage(c // 4, c // 4, ncls)])
+        self.final_instance_logits = torch.nn.Conv2d(c // 4, ncls, 1)
+        self.stage_num_classes = [ncls] * 4
+        self.stage_sup_size = [14, 28, 56, 112]
+        self.pre_upsample_last_stage = False
+
+    def forward(self, feats, x, rois, roi_labels):     # every stage for every detection (the reference)
+        for conv in self.instance_convs:
+            feats = conv(feats)
+        preds = []
+        for idx, stage in enumerate(self.stages):
+            p, _, feats = stage(feats, x[-idx - 3], rois, roi_labels, idx < len(self.stages) - 1)
+            preds.append(p)
+        p = self.final_instance_logits(feats)[torch.arange(len(rois), device=feats.device), roi_labels][:, None]
+        preds.append(torch.nn.functional.interpolate(p, scale_factor=2, mode='bilinear', align_corners=True))
+        return preds
+
+
+def test_switch_driven_inference_runs_only_selected_stages():
+    import numpy as np
+    from dynamask_b200 import switched
+    torch.manual_seed(7)
+    g = gen(301)
+    C, K = 16, 37
+    feats = [f.cuda() for f in synth.make_features(1, C, 800, 1344, g, strides=(4, 8, 16, 32, 64))]
+    boxes = synth.make_boxes(K, 800, 1333, g, s_lo=16, s_hi=400)
+    det = torch.cat([boxes, torch.rand(K, 1, generator=g)], 1).cuda()
+    labels = torch.randint(0, 3, (K, ), generator=g).cuda()
+    head = _FakeHead(C).cuda().eval()
+    predictor = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(C, 4)).cuda().eval()
+    ext14 = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=14, sampling_ratio=0), C, STRIDES)
+    ext56 = dm().SingleRoIExtractor(dict(type='RoIAlign', output_size=56, sampling_ratio=0), C, [4])
+    noise = torch.randn(K, 4, generator=g).cuda() * 3          # spreads the labels over all four buckets
+    metas = [dict(ori_shape=(800, 1333, 3), scale_factor=1.0)]
+    cfg = type('Cfg', (), {'mask_thr_binary': 0.5})
+    with torch.no_grad():
+        got = switched.simple_test_mask_switched(head, predictor, ext14, ext56, feats, metas, det, labels, cfg,
+                                                 rescale=False, noise=noise)
+        calls_switched = [s.calls[-1] for s in head.stages]
+        # the reference's sketch: every stage for every detection, four pastes, pick by label
+        rois = dm().bbox2roi([det[:, :4]])
+        sem = ext56([feats[0]], rois)
+        onehot = dm().get_mask_label(predictor(sem), noise)
+        bucket = onehot.argmax(1)
+        preds = head(ext14(feats[:4], rois), feats, rois, labels)
+        per_stage = [dm().get_seg_masks(p, det[:, :4], labels, cfg, (800, 1333, 3), 1.0, False) for p in preds]
+    counts = torch.bincount(bucket.cpu(), minlength=4).tolist()
+    assert min(counts) > 0, counts
+    # stage s ran on the detections of buckets >= s only
+    assert calls_switched == [K, K - counts[0], K - counts[0] - counts[1]], (calls_switched, counts)
+    flat = {c: list(v) for c, v in enumerate(got)}
+    agree = total = 0
+    for j in range(K):
+        want = per_stage[int(bucket[j])][j]
+        mine = flat[int(labels[j])].pop(0)
+        agree += int((mine == want).sum())
+        total += want.size
+    assert agree / total >= 0.9999, agree / total
