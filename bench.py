@@ -485,6 +485,16 @@ def main():
         'checksums': sums,
     }
 
+    # which of the absent third-party libraries (the arithmetic of the RLE / polygon / SimpleRoIAlign rows lives
+    # in them) could be imported here: when False the rows' oracles are restatements, "parity unpinned"
+    pins = {}
+    for name in ('pycocotools', 'mmcv'):
+        try:
+            pins[name] = getattr(__import__(name), '__file__', None) is not None
+        except Exception:
+            pins[name] = False
+    line['third_party_importable'] = pins
+
     # ---- extras: the other two kernels on their own configs (rank 0 reports) ------------------
     if not args.no_extras:
         line['extras'] = run_extras(dm, ops, dev, rank, peak)

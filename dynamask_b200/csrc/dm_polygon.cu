@@ -14,9 +14,12 @@
 // column-major run-length code.  A pixel is foreground when an odd number of run ends lie at or
 // before its column-major index; polygons of one object are OR-ed.
 //
-// One CTA per (RoI, size).  Warps own edges, lanes own the up-sampled steps of an edge; run ends
-// are counted into a shared-memory histogram over the (h*w + 1) column-major positions, a
-// column-parallel parity scan turns it into the bitmap.  All coordinate arithmetic is the
+// One CTA per (RoI, size, band of columns).  Warps own edges, lanes own the up-sampled steps of an
+// edge; run ends are counted into a shared-memory histogram over the band's column-major
+// positions, a column-parallel parity scan turns it into the bitmap.  A target that fits shared
+// memory is one band; a large one (PolygonMasks.to_ndarray / to_tensor rasterise at IMAGE size,
+// mmdet/core/mask/structures.py:541-558) is cut into bands of columns: every band walks all edges,
+// keeps the run ends that fall inside it and carries in the parity of those that fall before it.  All coordinate arithmetic is the
 // reference's float32 / float64 / int sequence with FMA contraction off, so targets are bit-exact.
 #include "dm_common.cuh"
 
@@ -35,6 +38,7 @@ struct PolyParams {
     const int32_t* roi_img;   // [K] or null
     float* out[kPolyMaxSizes];
     int sh[kPolyMaxSizes], sw[kPolyMaxSizes];
+    int wb[kPolyMaxSizes];    // columns per band
     int B, K, clip, n_sizes, G;
 };
 
@@ -97,11 +101,16 @@ __device__ __forceinline__ int crossing(int u0, int v0, int u1, int v1, int h, i
 __global__ void __launch_bounds__(kPolyThreads) polygon_target_kernel(const __grid_constant__ PolyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_carry[1024];
+    __shared__ int s_cin;                                             // run ends before the band
     const int k = blockIdx.x, si = blockIdx.y;
     const int h = p.sh[si], w = p.sw[si];
-    const int npx = h * w;
+    const int x0 = blockIdx.z * p.wb[si];
+    if (x0 >= w) return;
+    const int bw_ = min(p.wb[si], w - x0);                            // columns of this band
+    const int npx = h * bw_;
+    const int a0 = x0 * h;                                            // column-major position of the band's first pixel
     int* cnt = reinterpret_cast<int*>(smem_raw);                      // [npx + 1]
-    uint8_t* bitmap = reinterpret_cast<uint8_t*>(cnt + ((npx + 4) & ~3));  // [npx] row-major
+    uint8_t* bitmap = reinterpret_cast<uint8_t*>(cnt + ((npx + 4) & ~3));  // [npx] row-major within the band
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = kPolyThreads >> 5;
 
     for (int i = threadIdx.x; i < npx; i += kPolyThreads) bitmap[i] = 0;
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(kPolyThreads) polygon_target_kernel(const __gr
         const double* __restrict__ poly = p.xy + 2 * v0;
         __syncthreads();
         for (int i = threadIdx.x; i <= npx; i += kPolyThreads) cnt[i] = 0;
+        if (threadIdx.x == 0) s_cin = 0;
         __syncthreads();
         for (int j = warp; j < kv; j += nwarp) {
             int xa, ya, xb, yb;
@@ -155,37 +165,41 @@ __global__ void __launch_bounds__(kPolyThreads) polygon_target_kernel(const __gr
                     edge_point(pe, pe.n - 1, u0, v0p);
                 }
                 const int a = crossing(u0, v0p, u1, v1, h, w);
-                if (a >= 0 && a < npx) atomicAdd(&cnt[a], 1);
+                if (a >= 0 && a < a0) atomicAdd(&s_cin, 1);
+                else if (a >= a0 && a < a0 + npx) atomicAdd(&cnt[a - a0], 1);
             }
         }
         __syncthreads();
         // parity scan in column-major order: column totals, exclusive prefix, then each column
-        for (int x = threadIdx.x; x < w; x += kPolyThreads) {
+        for (int x = threadIdx.x; x < bw_; x += kPolyThreads) {
             int t = 0;
             for (int y = 0; y < h; ++y) t ^= cnt[x * h + y];
             s_carry[x] = t & 1;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int c = 0;
-            for (int x = 0; x < w; ++x) {
+            int c = s_cin & 1;
+            for (int x = 0; x < bw_; ++x) {
                 const int t = s_carry[x];
                 s_carry[x] = c;
                 c ^= t;
             }
         }
         __syncthreads();
-        for (int x = threadIdx.x; x < w; x += kPolyThreads) {
+        for (int x = threadIdx.x; x < bw_; x += kPolyThreads) {
             int par = s_carry[x];
             for (int y = 0; y < h; ++y) {
                 par ^= cnt[x * h + y] & 1;
-                if (par) bitmap[y * w + x] = 1;
+                if (par) bitmap[y * bw_ + x] = 1;
             }
         }
     }
     __syncthreads();
-    float* o = p.out[si] + (size_t)k * npx;
-    for (int i = threadIdx.x; i < npx; i += kPolyThreads) o[i] = bitmap[i] ? 1.0f : 0.0f;
+    float* o = p.out[si] + (size_t)k * h * w + x0;
+    for (int i = threadIdx.x; i < npx; i += kPolyThreads) {
+        const int y = i / bw_, x = i - y * bw_;
+        o[(size_t)y * w + x] = bitmap[i] ? 1.0f : 0.0f;
+    }
 }
 
 }  // namespace dm
@@ -212,19 +226,29 @@ extern "C" int dm_polygon_target(const double* poly_xy, const int64_t* vert_offs
     p.G = G;
     p.clip = clip ? 1 : 0;
     p.n_sizes = n_sizes;
-    int max_px = 0;
+    // a band = as many columns as fit ~96 KB of shared memory (4 bytes of histogram + 1 of bitmap per pixel),
+    // at most 1024 (the per-column carry array); one band for the usual target sizes
+    constexpr int kBandPx = 19000;
+    int max_px = 0, max_bands = 1;
     for (int s = 0; s < n_sizes; ++s) {
         p.sh[s] = sizes_hw[2 * s];
         p.sw[s] = sizes_hw[2 * s + 1];
         p.out[s] = out_ptrs[s];
-        if (p.sh[s] < 1 || p.sw[s] < 1 || p.sw[s] > 1024 || !p.out[s]) return DM_EINVAL;
-        if (p.sh[s] * p.sw[s] > max_px) max_px = p.sh[s] * p.sw[s];
+        if (p.sh[s] < 1 || p.sw[s] < 1 || !p.out[s]) return DM_EINVAL;
+        if (p.sh[s] > kBandPx) return DM_EUNSUPPORTED;   // a single column would not fit
+        int wb = kBandPx / p.sh[s];
+        wb = wb > 1024 ? 1024 : wb;
+        wb = wb > p.sw[s] ? p.sw[s] : wb;
+        p.wb[s] = wb;
+        const int bands = (p.sw[s] + wb - 1) / wb;
+        if (bands > max_bands) max_bands = bands;
+        if (p.sh[s] * wb > max_px) max_px = p.sh[s] * wb;
     }
+    if (max_bands > 65535) return DM_EUNSUPPORTED;
     const size_t smem = (size_t)((max_px + 4) & ~3) * 4 + (size_t)max_px;
-    if (smem > 200 * 1024) return DM_EUNSUPPORTED;
     DM_CUDA_CHECK(cudaFuncSetAttribute(dm::polygon_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem), "dm_polygon_target");
-    dm::polygon_target_kernel<<<dim3(K, n_sizes), dm::kPolyThreads, smem, (cudaStream_t)stream>>>(p);
+    dm::polygon_target_kernel<<<dim3(K, n_sizes, max_bands), dm::kPolyThreads, smem, (cudaStream_t)stream>>>(p);
     DM_LAUNCH_CHECK("dm_polygon_target");
     return DM_OK;
 }

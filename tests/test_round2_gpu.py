@@ -423,3 +423,28 @@ def test_switch_driven_inference_runs_only_selected_stages():
         agree += int((mine == want).sum())
         total += want.size
     assert agree / total >= 0.9999, agree / total
+
+
+# ------------------------------------------------------------------------------------------
+# polygon ground truth rasterised at IMAGE size (PolygonMasks.to_ndarray / to_tensor / to_bitmap,
+# mmdet/core/mask/structures.py:541-558): the kernel cuts large targets into bands of columns
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('hw', [(800, 1333), (427, 640), (1024, 2048)])
+def test_polygon_masks_rasterise_at_image_size(hw):
+    import numpy as np
+    H, W = hw
+    rng = np.random.default_rng(41 + H)
+    objs = synth.make_polygons(6, H, W, rng)
+    # one object spanning the whole image and one thin sliver, both crossing many band boundaries
+    objs.append([np.array([3.2, 4.9, W - 2.5, 7.1, W - 8.4, H - 3.3, 5.6, H - 6.2], np.float64)])
+    objs.append([np.array([10.0, H / 2.0, W - 10.0, H / 2.0 + 1.5, W - 10.0, H / 2.0 + 3.0, 10.0, H / 2.0 + 2.0], np.float64)])
+    pm = dm().PolygonMasks(objs, H, W)
+    got = pm.to_ndarray()
+    assert got.shape == (len(objs), H, W)
+    for i, polys in enumerate(objs):
+        want = O.polygon_to_bitmap(polys, H, W).astype(bool)
+        assert np.array_equal(got[i].astype(bool), want), 'object %d differs in %d pixels' % (i, int((got[i].astype(bool) != want).sum()))
+    assert int(got[-2].sum()) > 0.9 * H * W
+    t = pm.to_tensor(torch.float32, 'cuda')
+    assert t.shape == (len(objs), H, W) and float(t.sum()) == float(got.sum())
+    assert pm.to_bitmap().masks.shape == (len(objs), H, W)
