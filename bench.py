@@ -520,6 +520,7 @@ def main():
         line['e2e'] = e2e
         if numa:
             line['e2e']['cpus_bound_per_rank'] = numa
+        line['e2e'].update(host_copy_ceiling(world, e2e))
     del feats
     torch.cuda.empty_cache()
 
@@ -789,6 +790,21 @@ def run_competitor(dm, dev, rank, feats, rois, onehot):
         torch.autograd.backward([o7, o14], [o7.detach(), o14.detach()])
         return o56
     res['c3_extractors_ours_ms'] = timed(ours_c3, reps=10, warm=3)
+    # the same ~12 launches replayed as one CUDA graph: what the set costs without the host's launch gaps
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            ours_c3()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ours_c3()
+        res['c3_extractors_ours_cuda_graph_ms'] = timed(graph.replay, reps=10, warm=3)
+        del graph
+    except Exception as e:  # noqa: BLE001
+        res['c3_cuda_graph_error'] = str(e)[:120]
     try:
         res['c3_extractors_torchvision_cuda_ms'] = timed(tv_c3, reps=10, warm=3)
     except Exception as e:  # noqa: BLE001
@@ -796,6 +812,26 @@ def run_competitor(dm, dev, rank, feats, rois, onehot):
     res['workload'] = ('c2: the bench step (8192 RoIs, mixed sizes, fwd+bwd); c3: extractor calls of one training step, '
                        '2 images -- 7x7 x 1024 RoIs fwd+bwd, 14x14 x 256 fwd+bwd, 56x56 single-level x 256 fwd')
     return res
+
+
+def host_copy_ceiling(world, e2e):
+    """The e2e leg is a host <-> device copy problem (37 GB per rank and step against ~15 ms of kernels):
+    report the copy rate it reached beside the box's measured ceiling for the same byte mix at the same
+    number of ranks (tools/pcie_ceiling.py, table kept in profiles/pcie_ceiling.json)."""
+    out = {}
+    try:
+        per_rank = (e2e['h2d_bytes_per_step'] + e2e['d2h_bytes_per_step']) / (e2e['ms_per_step'] / 1e3) / 1e9
+        out['copy_gbs_per_rank'] = per_rank
+        with open(os.path.join(ROOT, 'profiles', 'pcie_ceiling.json')) as f:
+            table = json.load(f)
+        row = table.get(str(world))
+        if row:
+            out['host_copy_ceiling_gbs_per_rank'] = row['e2e_step_mix_gbs_per_rank']
+            out['frac_of_host_copy_ceiling'] = per_rank / row['e2e_step_mix_gbs_per_rank']
+            out['host_copy_ceiling_source'] = row.get('source', 'profiles/pcie_ceiling.json')
+    except Exception:
+        pass
+    return out
 
 
 def run_e2e(args, dm, dev, rank, world, feats_dev, rois_h, onehot_h, counts):

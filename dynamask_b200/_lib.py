@@ -44,6 +44,8 @@ SIGNATURES = {
     'dm_simple_roi_align_bwd': (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
 }
 
+DM_ECUDA = -2   # include/dynamask_sm100.h
+
 _lib = None
 
 
@@ -85,7 +87,8 @@ def check(rc, what):
     if rc != 0:
         lib = load()
         msg = lib.dm_error_string(rc).decode()
-        cuda = lib.dm_last_cuda_error().decode()
+        # the CUDA text is thread-local and never cleared: only a DM_ECUDA return owns it
+        cuda = lib.dm_last_cuda_error().decode() if rc == DM_ECUDA else ''
         raise RuntimeError('%s failed: %s%s' % (what, msg, (' [' + cuda + ']') if cuda else ''))
 
 

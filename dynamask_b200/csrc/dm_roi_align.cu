@@ -65,9 +65,12 @@ namespace dm {
 #define DM_BWD_REGS 128
 #endif
 #ifndef DM_BWD_DYNAMIC
-#define DM_BWD_DYNAMIC 0   // dynamic unit scheduling in the backward: measured 8.32 ms vs 8.25 ms static on the same box
-                           // (it evens out the SMs -- 96 % active instead of 92 % -- but the launch time does not follow); the
-                           // forward defaults to dynamic (6.61 vs 7.58 ms)
+#define DM_BWD_DYNAMIC 1   // dynamic unit scheduling in the backward: 0 never, 1 except single-bucket launches of tiny
+                           // pooled sizes, 2 always.  Round 1 measured it level with static ownership (8.32 vs 8.25 ms on
+                           // C2); since the scheduling thread moved off the table-building warps and fetches the next
+                           // unit's RoI with its ticket it wins at every size but 7x7 (kernel-only, 2048 RoIs per size:
+                           // 14x14 609 -> 547 us, 28x28 849 -> 798, 56x56 2019 -> 1782, 112x112 4702 -> 4510,
+                           // 56x56 single-level x 256 RoIs 2169 -> 1415; 7x7 x 1024 RoIs 290 -> 327: stays static)
 #endif
 constexpr int kBwdThreads = DM_BWD_THREADS;   // backward: 2 CTAs/SM x 8 warps at 128 registers
 #ifndef DM_FWD_THREADS
@@ -144,6 +147,7 @@ struct RaParams {
     int tma_rowmajor;
     int tma_slots;   // ring depth wanted (2 .. kTmaMaxSlots)
     int diag;        // measurement only (DM_RA_DIAG)
+    int l2_prefetch; // forward: L2 prefetch of a unit's patch while its tables are built
     int bwd_x;       // backward: X-first walk for small pooled sizes
     int bwd_groups;  // ... with at most this many lane groups (1, 2, 4)
 };
@@ -212,6 +216,27 @@ __device__ __forceinline__ void st_stream_vec(float* p, const float (&a)[VEC]) {
     if (VEC == 4) st_stream(reinterpret_cast<float4*>(p), make_float4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]));
     else if (VEC == 2) st_stream(reinterpret_cast<float2*>(p), make_float2(a[0], a[1 % VEC]));
     else st_stream(p, a[0]);
+}
+
+// Pooled-row store of the TMA forward path: streaming (evict-first) like every other pooled store.  Plain
+// write-back stores were measured and make no difference (14x14: 351.7 vs 349.2 us, 7x7: 201.8 vs 199.3).
+#ifndef DM_TMA_ROTATE
+#define DM_TMA_ROTATE 0   // forward TMA walk: rotating register window (unrolled JW deep) instead of shifting it.
+                          // Measured SLOWER (kernel-only, ncu): 14x14 349 -> 370 us, 28x28 557 -> 624-642, 7x7 x 1024 RoIs 199 -> 241:
+                          // the walk is fetch-bound (no_inst is its top stall) and the unrolled body is four times the code
+#endif
+#ifndef DM_TMA_STREAM_STORES
+#define DM_TMA_STREAM_STORES 1
+#endif
+template <int VEC>
+__device__ __forceinline__ void st_out_vec(float* p, const float (&a)[VEC]) {
+#if DM_TMA_STREAM_STORES
+    st_stream_vec<VEC>(p, a);
+#else
+    if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]);
+    else if (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(a[0], a[1 % VEC]);
+    else *p = a[0];
+#endif
 }
 
 // Packed FP32 pairs (FFMA2 / FMUL2 on sm_100a): two FMAs per issued instruction.  The hot loops are
@@ -316,6 +341,11 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const void* map, int c
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// L2 prefetch of one box (SASS: UTMAPF): no shared-memory destination, no completion to wait for
+__device__ __forceinline__ void tma_prefetch_3d(const void* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -503,7 +533,29 @@ struct Unit {
     int b;      // bucket
     int i;      // position inside the bucket (row of the bucket's output tensor)
     int slab;   // channel slab
+    // the RoI's record and pyramid level when the scheduler already fetched them (dynamic scheduling:
+    // the thread that takes the next ticket also loads that unit's RoI, so the two dependent global
+    // loads perm -> rois / lvl are off the unit's critical path)
+    int have;
+    int lv;
+    float r[5];
 };
+
+// the unit's RoI record (5 floats) and level: prefetched by the scheduler, else read here
+__device__ __forceinline__ void unit_roi(const RaParams& p, const Unit& un, const int* s_seg, float (&rr)[5], int& lv) {
+    if (un.have) {
+#pragma unroll
+        for (int e = 0; e < 5; ++e) rr[e] = un.r[e];
+        lv = un.lv;
+    } else {
+        const int pos = s_seg[un.b] + un.i;
+        const int k = p.perm ? p.perm[pos] : pos;
+        const float* roi = p.rois + 5 * (size_t)k;
+#pragma unroll
+        for (int e = 0; e < 5; ++e) rr[e] = roi[e];
+        lv = p.lvl ? p.lvl[k] : 0;
+    }
+}
 
 __device__ __forceinline__ long long total_units(const RaParams& p, const int* s_seg) {
     long long tot = 0;
@@ -519,6 +571,7 @@ __device__ __forceinline__ Unit decode_unit(const RaParams& p, const int* s_seg,
     un.b = p.order[p.nb - 1];
     un.i = 0;
     un.slab = 0;
+    un.have = 0;
     for (int j = 0; j < p.nb; ++j) {
         const int b = p.order[j];
         const long long n = (long long)(s_seg[b + 1] - s_seg[b]) * p.bk[b].nslab;
@@ -721,7 +774,29 @@ struct FwdWarpArgs {
 };
 
 template <int VEC, int JW>
-__device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
+__device__ __noinline__ void fwd_warp_core(const float* src0_, float* obase_, const float* ytab_, const int* rcnt_, const int* xs_, const float* wx_, float* ring_, int sC_, int sH_, int osC_, int osH_, int Pw_, int Ph_, int R_, int X0a_, int fws_, int cpr_, int cw_, int cpw_, int nc_, int nring_) {
+    FwdWarpArgs a;   // (scalars across the call, see fwd_warp_tma_core)
+    a.src0 = src0_;
+    a.obase = obase_;
+    a.ytab = ytab_;
+    a.rcnt = rcnt_;
+    a.xs = xs_;
+    a.wx = wx_;
+    a.ring = ring_;
+    a.sC = sC_;
+    a.sH = sH_;
+    a.osC = osC_;
+    a.osH = osH_;
+    a.Pw = Pw_;
+    a.Ph = Ph_;
+    a.R = R_;
+    a.X0a = X0a_;
+    a.fws = fws_;
+    a.cpr = cpr_;
+    a.cw = cw_;
+    a.cpw = cpw_;
+    a.nc = nc_;
+    a.nring = nring_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PwV = a.Pw / VEC;
     const int R = a.R, cpw = a.cpw, nc = a.nc;
@@ -894,6 +969,11 @@ __device__ __noinline__ void fwd_warp(const FwdWarpArgs a) {
     cp_async_wait<0>();
 }
 
+template <int VEC, int JW>
+__device__ __forceinline__ void fwd_warp(const FwdWarpArgs& a) {
+    fwd_warp_core<VEC, JW>(a.src0, a.obase, a.ytab, a.rcnt, a.xs, a.wx, a.ring, a.sC, a.sH, a.osC, a.osH, a.Pw, a.Ph, a.R, a.X0a, a.fws, a.cpr, a.cw, a.cpw, a.nc, a.nring);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward, TMA path: the same warp-autonomous strip walk, but the warp's patches arrive as TMA box
 // loads -- one cp.async.bulk.tensor.3d per chunk of BH patch rows x 16 / VEC channels x BW columns,
@@ -927,8 +1007,35 @@ struct FwdTmaArgs {
 // registers -- 32 values for JW <= 4 (eight independent chains per patch row), 32 for JW = 8
 __host__ __device__ constexpr int tma_ch(int vec, int jw) { return vec == 1 ? 4 : (jw <= 4 ? 8 / vec : 4 / vec); }
 
+// (The arguments cross the call as scalars: a struct passed by value to a __noinline__ function goes
+// through local memory -- ~30 STL / LDL / generic LD per warp and unit in front of the first TMA request.)
 template <int VEC, int JW>
-__device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
+__device__ __noinline__ void fwd_warp_tma_core(const void* map_, float* obase_, const float* ytab_, const int* rcnt_, const int* xs_, const float* wx_, float* ring_, unsigned bar_sa_, unsigned* phase_, int osC_, int osH_, int Pw_, int Ph_, int R_, int X0_, int Y0_, int BW_, int BH_, int nslot_, int nc_, int cidx0_, int chs_, int rws_, int diag_) {
+    FwdTmaArgs a;
+    a.map = map_;
+    a.obase = obase_;
+    a.ytab = ytab_;
+    a.rcnt = rcnt_;
+    a.xs = xs_;
+    a.wx = wx_;
+    a.ring = ring_;
+    a.bar_sa = bar_sa_;
+    a.phase = phase_;
+    a.osC = osC_;
+    a.osH = osH_;
+    a.Pw = Pw_;
+    a.Ph = Ph_;
+    a.R = R_;
+    a.X0 = X0_;
+    a.Y0 = Y0_;
+    a.BW = BW_;
+    a.BH = BH_;
+    a.nslot = nslot_;
+    a.nc = nc_;
+    a.cidx0 = cidx0_;
+    a.chs = chs_;
+    a.rws = rws_;
+    a.diag = diag_;
     constexpr int CH = tma_ch(VEC, JW);  // channels per lane
     constexpr int BC = 4 * CH;           // channels per box = per warp pass
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1076,8 +1183,47 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
         float* o = o_cb;
         const float* yrec = ytab;
         int left = a.Ph;
-        // patch-row major: the window slides one patch row per step (the first JW - 1 steps only
-        // fill it); all pooled rows whose band starts at `base` share one window
+        // patch-row major: one patch row enters the window per step (the first JW - 1 steps only fill
+        // it); all pooled rows whose band starts at `base` share one window.  The window ROTATES: patch
+        // row r lives in win[r % JW], and the walk is unrolled JW deep so that the slot of every logical
+        // band row is a compile-time index -- no register moves when the window advances.
+#if DM_TMA_ROTATE
+        bool more = true;
+        for (int r0 = 0; more; r0 += JW) {
+#pragma unroll
+            for (int u = 0; u < JW; ++u) {
+                const int r = r0 + u;
+                if (r < R) {
+                    consume(win[u]);
+                    ++used;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) win[u][q][e] = 0.0f;
+                }
+                const int base = r - (JW - 1);
+                if (base < 0) continue;
+                const int n = rcnt[base];
+                for (int k = 0; k < n; ++k) {
+                    float2 w[JW];
+                    load_yrec<JW>(yrec, w);
+                    yrec += YS;
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) {
+                        float acc[VEC];
+                        vmul<VEC>(acc, w[0], win[(u + 1) % JW][q]);
+#pragma unroll
+                        for (int j = 1; j < JW; ++j) vfma<VEC>(acc, w[j], win[(u + 1 + j) % JW][q]);
+                        if (on[q]) st_out_vec<VEC>(o + q * oq, acc);
+                    }
+                    o += a.osH;
+                }
+                left -= n;
+                if (left <= 0) { more = false; break; }
+            }
+        }
+#else
         for (int base = 1 - JW;; ++base) {
 #pragma unroll
             for (int j = 0; j + 1 < JW; ++j)
@@ -1106,18 +1252,24 @@ __device__ __noinline__ void fwd_warp_tma(const FwdTmaArgs a) {
                     vmul<VEC>(acc, w[0], win[0][q]);
 #pragma unroll
                     for (int j = 1; j < JW; ++j) vfma<VEC>(acc, w[j], win[j][q]);
-                    if (on[q]) st_stream_vec<VEC>(o + q * oq, acc);
+                    if (on[q]) st_out_vec<VEC>(o + q * oq, acc);
                 }
                 o += a.osH;
             }
             left -= n;
             if (left <= 0) break;
         }
+#endif
         skip_rows(R - used);   // keep the stream aligned: every batch spans exactly R rows
     }
     // every requested chunk has been waited for: nothing is in flight when the slots are reused
     __syncwarp();
     if (lane == 0) *a.phase = par;
+}
+
+template <int VEC, int JW>
+__device__ __forceinline__ void fwd_warp_tma(const FwdTmaArgs& a) {
+    fwd_warp_tma_core<VEC, JW>(a.map, a.obase, a.ytab, a.rcnt, a.xs, a.wx, a.ring, a.bar_sa, a.phase, a.osC, a.osH, a.Pw, a.Ph, a.R, a.X0, a.Y0, a.BW, a.BH, a.nslot, a.nc, a.cidx0, a.chs, a.rws, a.diag);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1186,15 +1338,53 @@ struct TmaShared {
     unsigned* phase;            // [warps]
 };
 
+// (Experiment, off by default -- DM_RA_L2_PREFETCH=1.)  While the first two warps build the unit's tables, the
+// others ask the TMA unit to pull the unit's patch into L2 (cp.async.bulk.prefetch.tensor): the walk's box loads then find their data in L2, so
+// neither the cold start of a unit's ring nor its steady state waits on DRAM latency.  The bounds come
+// straight from the first and last sample coordinate of each axis (what the table scan will find,
+// give or take rejected samples -- this is a hint, a column too many or too few costs nothing but
+// a few bytes); the last chunk of a batch is shifted up like the loader's, so no row below the patch
+// is touched.
+template <int VEC>
+__device__ __forceinline__ void prefetch_patch(const RaParams& p, const TmaMaps& tm, const LevelDesc& Lv,
+                                               const RoiGeom& g, int lv, int Pw, int Ph, int cidx0, int nc) {
+    const int set = VEC == 4 ? 1 : 2;                // the boxes of the JW <= 4 walk: 8 / 16 channels
+    const int BC = 4 << set;
+    const unsigned mask = p.tma_mask[lv][set];
+    if (!mask || g.gw <= 0 || g.gh <= 0) return;
+    const float vx0 = sample_coord(g.rsw, g.bw, g.gw, 0, 0), vx1 = sample_coord(g.rsw, g.bw, g.gw, Pw - 1, g.gw - 1);
+    const float vy0 = sample_coord(g.rsh, g.bh, g.gh, 0, 0), vy1 = sample_coord(g.rsh, g.bh, g.gh, Ph - 1, g.gh - 1);
+    if (!(vx1 >= -1.0f && vx0 <= (float)Lv.W && vy1 >= -1.0f && vy0 <= (float)Lv.H)) return;
+    const int X0 = min(max((int)floorf(fmaxf(vx0, 0.0f)), 0), Lv.W - 1);
+    const int X1 = min(max((int)floorf(fmaxf(vx1, 0.0f)) + 1, 0), Lv.W - 1);
+    const int Y0 = min(max((int)floorf(fmaxf(vy0, 0.0f)), 0), Lv.H - 1);
+    const int Y1 = min(max((int)floorf(fmaxf(vy1, 0.0f)) + 1, 0), Lv.H - 1);
+    const int X0a = X0 & ~3, fwa = X1 - X0a + 1, R = Y1 - Y0 + 1;
+    if (fwa > kTmaMaxBW) return;
+    int cls = 0;
+    while (cls < kNumBW - 1 && tma_bw(cls) < fwa) ++cls;
+    if (!((mask >> cls) & 1u)) return;
+    const int BH = tma_bh(set, cls);
+    const int nchunk = (R + BH - 1) / BH, nbatch = (nc + BC - 1) / BC;
+    const void* map = &tm.m[lv][set][cls];
+    const int stride = (RA_WARPS - 2) * 32;
+    for (int q = (int)threadIdx.x - 64; q < nbatch * nchunk; q += stride) {
+        const int b = q / nchunk, k = q - b * nchunk;
+        const int y = (k == nchunk - 1 && R >= BH) ? Y1 + 1 - BH : Y0 + k * BH;
+        const int c = cidx0 + b * BC;
+        if (p.tma_rowmajor) tma_prefetch_3d(map, X0a, c, y);
+        else tma_prefetch_3d(map, X0a, y, c);
+    }
+}
+
 template <int VEC>
 __device__ void fwd_unit(const RaParams& p, const TmaMaps& tm, const TmaShared ts, const Unit& un,
                          const int* s_seg, float* smem, int* stat) {
     const BucketDesc& B = p.bk[un.b];
-    const int pos = s_seg[un.b] + un.i;
-    const int k = p.perm ? p.perm[pos] : pos;
     const int c0 = un.slab * B.cg, c1 = min(c0 + B.cg, p.C);
-    const float* roi = p.rois + 5 * (size_t)k;
-    const int lv = p.lvl ? p.lvl[k] : 0;
+    float roi[5];
+    int lv;
+    unit_roi(p, un, s_seg, roi, lv);
     const int batch = (int)roi[0];
     if (lv < 0 || lv >= p.L || batch < 0 || batch >= p.lv[lv < 0 || lv >= p.L ? 0 : lv].N) {
         zero_unit(B, un.i, c0, c1);
@@ -1208,6 +1398,8 @@ __device__ void fwd_unit(const RaParams& p, const TmaMaps& tm, const TmaShared t
         direct_unit<false>(Lv, B, g, batch, un.i, c0, c1);
         return;
     }
+    if (p.l2_prefetch && g.mode == 0 && B.pw / VEC <= 8 && lv < kTmaLevels && RA_WARPS > 2 && (threadIdx.x >> 5) >= 2)
+        prefetch_patch<VEC>(p, tm, Lv, g, lv, B.pw, B.ph, batch * p.C + c0, c1 - c0);
     Tables t;
     bool fits;
     if (!build_tables(g, B.ph, B.pw, Lv.H, Lv.W, smem, p.smem_floats, stat, t, fits)) {
@@ -1415,7 +1607,29 @@ struct BwdWarpArgs {
 // starting at (plo[x] & ~3) + 4 * NV * part in registers, reads them from the row buffer with NV
 // 16-byte loads, and the parts are summed with shuffles: one RED per touched feature pixel.
 template <int VEC, int JW, int NV>
-__device__ __noinline__ void bwd_warp_core(const BwdWarpArgs a) {
+__device__ __noinline__ void bwd_warp_core_s(const float* gbase_, float* dbase_, const float* ytab_, const int* rcnt_, const int* plo_, const int* pcnt_, const float* wxT_, float* wsm_, int gsC_, int gsH_, int dsC_, int dsH_, int Ph_, int Pw_, int R_, int fw_, int TW_, int cpw_, int nc_, int split_, int wide_) {
+    BwdWarpArgs a;   // (scalars across the call, see fwd_warp_tma_core)
+    a.gbase = gbase_;
+    a.dbase = dbase_;
+    a.ytab = ytab_;
+    a.rcnt = rcnt_;
+    a.plo = plo_;
+    a.pcnt = pcnt_;
+    a.wxT = wxT_;
+    a.wsm = wsm_;
+    a.gsC = gsC_;
+    a.gsH = gsH_;
+    a.dsC = dsC_;
+    a.dsH = dsH_;
+    a.Ph = Ph_;
+    a.Pw = Pw_;
+    a.R = R_;
+    a.fw = fw_;
+    a.TW = TW_;
+    a.cpw = cpw_;
+    a.nc = nc_;
+    a.split = split_;
+    a.wide = wide_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Pw = a.Pw, Ph = a.Ph, R = a.R, cpw = a.cpw, nc = a.nc;
     const int PwV = Pw / VEC;
@@ -1662,7 +1876,7 @@ struct BwdXArgs {
 };
 
 template <int JW, int NT>
-__device__ __noinline__ void bwd_warp_x(const BwdXArgs a) {
+__device__ __forceinline__ void bwd_warp_x_body(const BwdXArgs& a) {
     constexpr int CH = 4;   // channels per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Ph = a.Ph, Pw = a.Pw, R = a.R, nc = a.nc, nslot = a.nslot, rb = a.rb;
@@ -1822,6 +2036,24 @@ __device__ __noinline__ void bwd_warp_x(const BwdXArgs a) {
     if (lane == 0) *a.phase = par;
 }
 
+template <int VEC, int JW, int NV>
+__device__ __forceinline__ void bwd_warp_core(const BwdWarpArgs& a) {
+    bwd_warp_core_s<VEC, JW, NV>(a.gbase, a.dbase, a.ytab, a.rcnt, a.plo, a.pcnt, a.wxT, a.wsm, a.gsC, a.gsH, a.dsC, a.dsH, a.Ph, a.Pw, a.R, a.fw, a.TW, a.cpw, a.nc, a.split, a.wide);
+}
+
+// (By value, unlike the other three hot functions: the scalar-argument shell of this one -- 23 arguments --
+// produced illegal / misaligned addresses on the device with nvcc 12.9 whatever the argument order;
+// the struct goes through local memory once per warp and unit.)
+template <int JW, int NT>
+__device__ __noinline__ void bwd_warp_x_byval(const BwdXArgs a) {
+    bwd_warp_x_body<JW, NT>(a);
+}
+
+template <int JW, int NT>
+__device__ __forceinline__ void bwd_warp_x(const BwdXArgs& a) {
+    bwd_warp_x_byval<JW, NT>(a);
+}
+
 template <int VEC, int JW>
 __device__ __forceinline__ void bwd_warp(const BwdWarpArgs& a, int need) {
     // tap windows: 8 pooled columns per lane when that covers every feature column, else 20
@@ -1893,11 +2125,10 @@ template <int VEC>
 __device__ void bwd_unit(const RaParams& p, const TmaShared ts, const Unit& un, const int* s_seg, float* smem,
                          int* stat) {
     const BucketDesc& B = p.bk[un.b];
-    const int pos = s_seg[un.b] + un.i;
-    const int k = p.perm ? p.perm[pos] : pos;
     const int c0 = un.slab * B.cg, c1 = min(c0 + B.cg, p.C);
-    const float* roi = p.rois + 5 * (size_t)k;
-    const int lv = p.lvl ? p.lvl[k] : 0;
+    float roi[5];
+    int lv;
+    unit_roi(p, un, s_seg, roi, lv);
     const int batch = (int)roi[0];
     if (lv < 0 || lv >= p.L) return;
     const LevelDesc& Lv = p.lv[lv];
@@ -2085,16 +2316,21 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
         // (same fractional pace for every bucket, as in the static interleaved walk; holding the smaller
         // buckets back so that the launch ends on small units was measured and does not pay).
         __shared__ int s_next[2];
+        __shared__ float s_roi[5];   // the next unit's RoI record and level, loaded by the scheduling thread
+        __shared__ int s_lv;
+        // the scheduling thread is lane 0 of the LAST warp: the first two warps build the unit's tables,
+        // and must not start late because one of their lanes waits for a ticket to come back from L2
+        const bool sched_thread = threadIdx.x == (unsigned)(RA_THREADS - 32);
         // thread 0's view: units this CTA has taken per bucket, buckets found exhausted.  Pacing by the
         // CTA's own counts (every CTA ends up with ~1/grid of each bucket) costs one L2 round trip per
         // unit -- the ticket -- instead of two (reading the global counters first).
         __shared__ int taken[DM_MAX_BUCKETS];   // touched by thread 0 only (kept out of its registers)
         __shared__ unsigned gone;
-        if (threadIdx.x == 0) {
+        if (sched_thread) {
             gone = 0u;
             for (int j = 0; j < DM_MAX_BUCKETS; ++j) taken[j] = 0;
         }
-        auto fetch = [&]() {   // thread 0
+        auto fetch = [&]() {   // the scheduling thread
             for (;;) {
                 int jsel = -1;
                 float best = 0.0f;
@@ -2114,20 +2350,30 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
                     ++taken[jsel];
                     s_next[0] = jsel;
                     s_next[1] = (int)t;
+                    const int pos = s_seg[b] + (int)(t / (unsigned)p.bk[b].nslab);
+                    const int k = p.perm ? p.perm[pos] : pos;
+                    const float* roi = p.rois + 5 * (size_t)k;
+#pragma unroll
+                    for (int e = 0; e < 5; ++e) s_roi[e] = roi[e];
+                    s_lv = p.lvl ? p.lvl[k] : 0;
                     return;
                 }
                 gone |= 1u << jsel;
             }
         };
-        if (threadIdx.x == 0) fetch();
+        if (sched_thread) fetch();
         __syncthreads();
         for (;;) {
             const int jsel = s_next[0];
             const unsigned u = (unsigned)s_next[1];
-            __syncthreads();   // everyone holds the unit: thread 0 may fetch the next one
-            if (jsel < 0) break;
-            if (threadIdx.x == 0) fetch();
             Unit un;
+            un.have = 1;
+            un.lv = s_lv;
+#pragma unroll
+            for (int e = 0; e < 5; ++e) un.r[e] = s_roi[e];
+            __syncthreads();   // everyone holds the unit: the scheduling thread may fetch the next one
+            if (jsel < 0) break;
+            if (sched_thread) fetch();
             un.b = p.order[jsel];
             // slab-major inside a RoI so concurrent CTAs share one RoI's patch in L2
             un.i = (int)(u / (unsigned)p.bk[un.b].nslab);
@@ -2177,6 +2423,7 @@ __global__ void __maxnreg__(BWD ? DM_BWD_REGS : DM_FWD_REGS) ra_kernel(const __g
         }
         if (jsel < 0) break;
         Unit un;
+        un.have = 0;
         {
             const long long u = first[jsel] + (long long)done[jsel] * gridDim.x;
             ++done[jsel];
@@ -2211,7 +2458,7 @@ static int env_int(const char* name, int dflt) {
 // variants; the defaults are the shipped configuration).
 struct RaConfig {
     int want, cg, interleave, fwd_smem_kb, bwd_smem_kb, fwd_dynamic, bwd_dynamic, bias;
-    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2, diag, bwd_x, bwd_groups;
+    int fwd_threads, tma, tma_rowmajor, tma_slots, tma_l2, diag, bwd_x, bwd_groups, l2_prefetch;
 };
 static const RaConfig& config() {
     static const RaConfig c = [] {
@@ -2232,6 +2479,9 @@ static const RaConfig& config() {
         r.diag = env_int("DM_RA_DIAG", 0);
         r.bwd_x = env_int("DM_RA_BWD_X", 1);
         r.bwd_groups = env_int("DM_RA_BWD_GROUPS", 4);
+        // off: measured slower (kernel-only: 14x14 352 -> 396 us, 28x28 557 -> 650, 7x7 x 1024 RoIs 202 -> 218);
+        // the walk waits on the TMA unit's turnaround, not on DRAM, and the prefetches queue in front of its loads
+        r.l2_prefetch = env_int("DM_RA_L2_PREFETCH", 0);
         return r;
     }();
     return c;
@@ -2436,7 +2686,8 @@ static int launch(RaParams& p, cudaStream_t st, unsigned* sched, const char* whe
     const int threads = BWD ? kBwdThreads : cf.fwd_threads;
     p.smem_floats = smem_bytes / 4;
     // static and dynamic scheduling are separate instantiations (each with its own register allocation)
-    const bool dyn = sched != nullptr && (BWD ? cf.bwd_dynamic : cf.fwd_dynamic) != 0;
+    bool dyn = sched != nullptr && (BWD ? cf.bwd_dynamic : cf.fwd_dynamic) != 0;
+    if (BWD && cf.bwd_dynamic == 1 && p.nb == 1 && p.bk[0].ph * p.bk[0].pw <= 100) dyn = false;
     int grid = 0;
     const int rc = kernel_grid<BWD>(dyn, threads, smem_bytes, where, grid);
     if (rc != DM_OK) return rc;
@@ -2451,6 +2702,7 @@ static int launch(RaParams& p, cudaStream_t st, unsigned* sched, const char* whe
     TmaMaps tm;
     p.tma_rowmajor = cf.tma_rowmajor ? 1 : 0;
     p.diag = cf.diag;
+    p.l2_prefetch = (!BWD && cf.tma && cf.l2_prefetch) ? 1 : 0;
     p.bwd_x = (cf.bwd_x && p.mode == 0) ? 1 : 0;
     p.bwd_groups = cf.bwd_groups >= 4 ? 4 : (cf.bwd_groups >= 2 ? 2 : 1);
     p.tma_slots = cf.tma_slots < 2 ? 2 : (cf.tma_slots > kTmaMaxSlots ? kTmaMaxSlots : cf.tma_slots);

@@ -97,6 +97,23 @@ def _level_arrays(feats):
     return L, ptrs, _arr(ctypes.c_int32, shapes), _arr(ctypes.c_int64, strides)
 
 
+def _tma_rows(f):
+    """A level whose rows are not a multiple of 16 bytes (W = 42 on the stride-32 map of an 800x1344
+    image) cannot be described by a tensor map, and its RoIs would take the slow 8-byte cp.async path
+    of the forward (measured: 9 % of the RoIs, a third of a 7x7 call's time).  Such a level is copied
+    once per call into a buffer with a 16-byte row pitch and handed to the library as a strided view
+    (same shape, pitch rounded up to 4 floats); the pad columns are never read (the tensor map's extent
+    is W, out-of-range box columns are zero-filled by the TMA unit).  A backbone that allocates the
+    level with that pitch avoids the copy."""
+    if f.dim() != 4 or f.size(3) % 4 == 0 or not f.is_contiguous():
+        return f
+    n, c, h, w = f.shape
+    buf = torch.empty((n, c, h, (w + 3) & ~3), dtype=f.dtype, device=f.device)
+    view = buf[..., :w]
+    view.copy_(f)
+    return view
+
+
 def _bucket_arrays(tensors, out_hw):
     ptrs = _arr(ctypes.c_void_p, [t.data_ptr() for t in tensors])
     strides = []
@@ -123,12 +140,19 @@ def roi_align_forward(feats: Sequence[Tensor], rois: Tensor, lvl: Optional[Tenso
     rois = _f32c(rois, 'rois').contiguous()
     dev = rois.device
     K = rois.size(0)
+    # the kernel enumerates a bucket's rows from the device-side seg_offsets; the outputs are sized from the
+    # host counts, which therefore must be the seg differences of THIS call (stale counts would write past
+    # the end of a bucket tensor).  The total is checkable without a device read-back:
+    if sum(int(c) for c in counts) != K:
+        raise ValueError('counts must sum to the number of RoIs (%d), got %s' % (K, list(counts)))
     C = feats[0].size(1)
     fmt = torch.channels_last if channels_last else torch.contiguous_format
     outs = [torch.empty((int(counts[b]), C, int(out_hw[2 * b]), int(out_hw[2 * b + 1])),
                         dtype=torch.float32, device=dev, memory_format=fmt) for b in range(nb)]
     if K == 0:
         return outs
+    if any(int(out_hw[2 * b + 1]) <= 32 for b in range(nb)):   # pooled rows of <= 8 strips: TMA patch loads
+        feats = [_tma_rows(f) for f in feats]
     L, fptrs, fshapes, fstrides = _level_arrays(feats)
     optrs, ohw, ostrides = _bucket_arrays(outs, out_hw)
     scales = _arr(ctypes.c_float, [float(s) for s in spatial_scales])

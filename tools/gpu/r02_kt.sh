@@ -4,7 +4,7 @@
 TAG=$1; shift
 mkdir -p gpurun_out
 for cfg in "$@"; do
-  name=$(echo $cfg | tr ' =' '__')
+  name=$(echo $cfg | tr ' =/' '___')
   for prog in bucket_breakdown c3_breakdown; do
     env $cfg timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ra_kernel --csv --log-file gpurun_out/${TAG}_${prog}_${name}.csv python tools/$prog.py > /dev/null 2> gpurun_out/${TAG}_${prog}_${name}.err
   done
