@@ -77,15 +77,31 @@ __device__ __forceinline__ bool window_rows(const PasteParams& p, int n, int& wy
     return wya < wyb && wxa < wxb;
 }
 
-// zero `nbytes` bytes at `q` (any alignment) with one warp: 16-byte stores for the aligned middle
-__device__ __forceinline__ void warp_zero(unsigned char* q, int nbytes, int lane) {
+constexpr int kZeroPage = 2048;   // bytes of zeros in shared memory, the source of the TMA fill
+
+// shared -> global bulk copy (TMA, SASS: UBLKCP.G.S), tracked by the issuing thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src_sa, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// zero `nbytes` bytes at `q` (any alignment) with one warp: 16-byte stores for the aligned middle, or --
+// with the CTA's zero page at shared address `zero_sa` -- bulk copies of up to kZeroPage bytes issued by
+// the first lanes (the TMA unit writes them; nothing waits in the SM's store queue)
+__device__ __forceinline__ void warp_zero(unsigned char* q, int nbytes, int lane, unsigned zero_sa = 0u) {
     if (nbytes <= 0) return;
     const int head = min(nbytes, (int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(q) & 15u)) & 15u));
     if (lane < head) q[lane] = 0;
     q += head;
     nbytes -= head;
     const int nv = nbytes >> 4;
-    for (int i = lane; i < nv; i += 32) __stcs(reinterpret_cast<uint4*>(q) + i, make_uint4(0u, 0u, 0u, 0u));
+    if (zero_sa) {
+        const int mid = nv << 4;
+        for (int o = lane * kZeroPage; o < mid; o += 32 * kZeroPage) bulk_s2g(q + o, zero_sa, (unsigned)min(kZeroPage, mid - o));
+    } else {
+        for (int i = lane; i < nv; i += 32) __stcs(reinterpret_cast<uint4*>(q) + i, make_uint4(0u, 0u, 0u, 0u));
+    }
     if (lane < (nbytes & 15)) q[(nv << 4) + lane] = 0;
 }
 
@@ -93,7 +109,7 @@ __device__ __forceinline__ void warp_zero(unsigned char* q, int nbytes, int lane
 // FULL = true: every element of the window's ROWS is written -- zeros outside the window's columns and
 // where the sample misses the mask -- so the rows need no zero fill and the fill can run beside it.
 template <int MODE, bool FULL>
-__device__ __forceinline__ void paste_window_body(const PasteParams& p, int bxi, int nbx, int byi, int nby) {
+__device__ __forceinline__ void paste_window_body(const PasteParams& p, int bxi, int nbx, int byi, int nby, unsigned zero_sa = 0u) {
     __shared__ __align__(16) float s_mask[kMaskStage];          // sigmoid(mask) rows, one-pixel zero border
     __shared__ __align__(8) float2 s_col[kColTab];              // per window column {VD index, wh}
     __shared__ __align__(8) float2 s_vd[kPasteThreads / 32][kVPairs];
@@ -135,8 +151,8 @@ __device__ __forceinline__ void paste_window_body(const PasteParams& p, int bxi,
             for (int r = r0 + warp; r < r1; r += kPasteThreads / 32) {
                 if (FULL) {
                     unsigned char* row8 = reinterpret_cast<unsigned char*>(p.out) + (obase + (long long)r * p.rw) * ES;
-                    warp_zero(row8, wxa * ES, lane);
-                    warp_zero(row8 + (long long)wxb * ES, (p.rw - wxb) * ES, lane);
+                    if (r == wya) warp_zero(row8, wxa * ES, lane, zero_sa);
+                    warp_zero(row8 + (long long)wxb * ES, (p.rw - wxb + (r + 1 < wyb ? wxa : 0)) * ES, lane, zero_sa);
                 }
                 for (int c = wxa + lane; c < wxb; c += 32) {
                     const float v = in.eval(p.x_lo + c, p.y_lo + r);
@@ -193,13 +209,17 @@ __device__ __forceinline__ void paste_window_body(const PasteParams& p, int bxi,
             const float4 rt = s_row[r - r0];
             const int rstate = __float_as_int(rt.w);
             if (FULL) {
+                // The zeros right of this row's window and left of the next row's are one contiguous run:
+                // a row's warp writes [wxa, rw) of its row and [0, wxa) of the next window row (the first
+                // window row also its own left part), so each row costs one zero run instead of two.
                 unsigned char* row8 = reinterpret_cast<unsigned char*>(p.out) + (obase + (long long)r * p.rw) * ES;
+                if (r == wya) warp_zero(row8, wxa * ES, lane, zero_sa);
+                const int tail = p.rw - wxb + (r + 1 < wyb ? wxa : 0);
                 if (rstate == 0) {  // the row's samples miss the mask: all zeros
-                    warp_zero(row8, p.rw * ES, lane);
+                    warp_zero(row8 + (long long)wxa * ES, (wxb - wxa + tail) * ES, lane, zero_sa);
                     continue;
                 }
-                warp_zero(row8, wxa * ES, lane);
-                warp_zero(row8 + (long long)wxb * ES, (p.rw - wxb) * ES, lane);
+                warp_zero(row8 + (long long)wxb * ES, tail * ES, lane, zero_sa);
             }
             if (rstate == 0) continue;  // warp-uniform
             __syncwarp();
@@ -260,32 +280,43 @@ paste_window_kernel(const __grid_constant__ PasteParams p) {
 constexpr int kFillVecs = 16;                              // 16-byte stores per fill thread
 constexpr int kFillTile = kPasteThreads * kFillVecs * 16;   // bytes per fill tile (64 KB)
 
+// The byte range of instance n's window rows (what the fill skips), absolute in the output; empty
+// (0, 0) when the instance is not pasted or lies behind the output.
 template <int ES>
-__device__ __forceinline__ void fill_tile(const PasteParams& p, long long tile, long long nbytes) {
-    const long long t0 = tile * kFillTile;
+__device__ __forceinline__ void skip_range(const PasteParams& p, long long n, long long t0, bool second,
+                                           long long& lo, long long& hi) {
     const long long TB = (long long)p.rh * p.rw * ES;   // bytes per instance (>= kFillTile on this path)
-    // the tile touches at most two instances: their skipped byte ranges (window rows), absolute.
-    // Every thread derives them itself (two box loads, broadcast): no barrier here.
-    long long a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
-    {
-        const long long n = t0 / TB;
-        float4 bx;
-        int wya, wyb, wxa, wxb;
-        if (n < p.N && window_rows(p, (int)n, wya, wyb, wxa, wxb, bx)) {
-            a_lo = n * TB + (long long)wya * p.rw * ES;
-            a_hi = n * TB + (long long)wyb * p.rw * ES;
-        }
-        if (n + 1 < p.N && (n + 1) * TB < t0 + kFillTile && window_rows(p, (int)n + 1, wya, wyb, wxa, wxb, bx)) {
-            b_lo = (n + 1) * TB + (long long)wya * p.rw * ES;
-            b_hi = (n + 1) * TB + (long long)wyb * p.rw * ES;
-        }
+    lo = hi = 0;
+    float4 bx;
+    int wya, wyb, wxa, wxb;
+    if (n >= p.N || (second && n * TB >= t0 + kFillTile)) return;
+    if (window_rows(p, (int)n, wya, wyb, wxa, wxb, bx)) {
+        lo = n * TB + (long long)wya * p.rw * ES;
+        hi = n * TB + (long long)wyb * p.rw * ES;
     }
+}
+
+// One 64 KB tile of the zero fill.  The tile touches at most two instances; [a_lo, a_hi) and
+// [b_lo, b_hi) are their skipped byte ranges (window rows).
+template <int ES>
+__device__ __forceinline__ void fill_tile(const PasteParams& p, long long tile, long long nbytes, long long a_lo,
+                                          long long a_hi, long long b_lo, long long b_hi, unsigned zero_sa) {
+    const long long t0 = tile * kFillTile;
     unsigned char* const out8 = reinterpret_cast<unsigned char*>(p.out);
     // CTA-uniform fast paths: a tile wholly inside window rows has nothing to do, a whole tile clear
     // of them is 16 plain streaming stores per thread; only tiles on a boundary test every vector
     const long long t1 = min(t0 + kFillTile, nbytes);
     if ((t0 >= a_lo && t1 <= a_hi) || (t0 >= b_lo && t1 <= b_hi)) return;
     if (t1 - t0 == kFillTile && (t1 <= a_lo || t0 >= a_hi) && (t1 <= b_lo || t0 >= b_hi)) {
+        if (zero_sa) {
+            // TMA fill: the tile leaves as 32 bulk copies of the CTA's zero page (shared -> global), one per
+            // lane of warp 0.  The copies are carried out by the TMA unit, not by the LSU: the SM's
+            // load / store queues stay free for the window role that follows, where 16 x 8 warp-wide
+            // streaming stores per tile used to sit in them until HBM had taken the bytes.
+            if (threadIdx.x < kFillTile / kZeroPage)
+                bulk_s2g(out8 + t0 + (long long)threadIdx.x * kZeroPage, zero_sa, kZeroPage);
+            return;
+        }
         uint4* q = reinterpret_cast<uint4*>(out8 + t0) + threadIdx.x;
 #pragma unroll
         for (int k = 0; k < kFillVecs; ++k) __stcs(q + k * kPasteThreads, make_uint4(0u, 0u, 0u, 0u));
@@ -306,12 +337,59 @@ __device__ __forceinline__ void fill_tile(const PasteParams& p, long long tile, 
     }
 }
 
+// Persistent: the launch holds as many CTAs as the GPU keeps resident (5 per SM) and each walks the
+// "virtual CTAs" v = blockIdx.x, blockIdx.x + gridDim.x, ... of the 8-per-instance-slot decomposition:
+// the fill tiles of v first, then v's window bands.  (One CTA per virtual CTA was 6400 CTAs of 43 KB of
+// shared memory for the C4 shape: 47 us of the launch went into starting and retiring CTAs that found
+// nothing to paste -- measured with both roles switched off, DM_PASTE_DIAG=3.)
 template <int MODE>
 __global__ void __launch_bounds__(kPasteThreads, 5)
-paste_fused_kernel(const __grid_constant__ PasteParams p, int win_y, long long n_fill, long long nbytes) {
+paste_fused_kernel(const __grid_constant__ PasteParams p, int win_y, int n_virtual, long long n_fill, long long nbytes,
+                   int tma_fill, int diag) {
     constexpr int ES = MODE == DM_PASTE_F32 ? 4 : 1;
-    for (long long tile = blockIdx.x; tile < n_fill; tile += gridDim.x) fill_tile<ES>(p, tile, nbytes);
-    paste_window_body<MODE, true>(p, (int)(blockIdx.x % kBandCtas), kBandCtas, (int)(blockIdx.x / kBandCtas), win_y);
+    // The skip ranges of a virtual CTA's tiles (two box loads and two window computations per tile) are
+    // worked out ONCE by two threads per tile and handed to the others through shared memory: with every
+    // thread deriving them the fill role spent ~20 % of the kernel's instructions on geometry.
+    constexpr int kSlots = 16;
+    __shared__ long long s_rng[kSlots][4];
+    __shared__ __align__(128) unsigned char s_zero[kZeroPage];
+    const long long TB = (long long)p.rh * p.rw * ES;
+    unsigned zero_sa = 0u;
+    if (tma_fill) {
+        if (threadIdx.x < kZeroPage / 16) reinterpret_cast<uint4*>(s_zero)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy reads
+        zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
+    }
+    for (int v = blockIdx.x; v < n_virtual; v += gridDim.x) {
+        __syncthreads();   // s_rng of the previous round is no longer read
+        {
+            const int k = threadIdx.x >> 1, which = threadIdx.x & 1;
+            const long long tile = v + (long long)k * n_virtual;
+            if (k < kSlots && tile < n_fill) {
+                const long long t0 = tile * kFillTile;
+                long long lo, hi;
+                skip_range<ES>(p, t0 / TB + which, t0, which != 0, lo, hi);
+                s_rng[k][2 * which] = lo;
+                s_rng[k][2 * which + 1] = hi;
+            }
+        }
+        __syncthreads();
+        int k = 0;
+        for (long long tile = v; tile < n_fill && !(diag & 2); tile += n_virtual, ++k) {   // (diag: measurement only)
+            long long a_lo, a_hi, b_lo, b_hi;
+            if (k < kSlots) {
+                a_lo = s_rng[k][0]; a_hi = s_rng[k][1]; b_lo = s_rng[k][2]; b_hi = s_rng[k][3];
+            } else {
+                const long long t0 = tile * kFillTile;
+                skip_range<ES>(p, t0 / TB, t0, false, a_lo, a_hi);
+                skip_range<ES>(p, t0 / TB + 1, t0, true, b_lo, b_hi);
+            }
+            fill_tile<ES>(p, tile, nbytes, a_lo, a_hi, b_lo, b_hi, zero_sa);
+        }
+        if (!(diag & 1)) paste_window_body<MODE, true>(p, v % kBandCtas, kBandCtas, v / kBandCtas, win_y, (diag & 4) ? 0u : zero_sa);
+    }
+    // the zero page must outlive the copies that read it
+    if (tma_fill) { bulk_commit(); bulk_wait_all(); }
 }
 
 }  // namespace dm
@@ -356,17 +434,25 @@ static int paste_impl(const float* masks, int64_t mask_stride_n, int64_t mask_st
     const int ES = out_mode == DM_PASTE_F32 ? 4 : 1;
     cudaStream_t st = (cudaStream_t)stream;
     const long long nbytes_all = p.total * ES;
-    const char* fenv = getenv("DM_PASTE_FUSED");
-    const bool fused = zero_fill && per_inst * ES >= dm::kFillTile && !(fenv && *fenv == '0');
+    // A/B knobs, read once: DM_PASTE_FUSED=0 takes the two-launch form, DM_PASTE_TMA=0 fills with plain stores
+    static const bool fused_on = [] { const char* e = getenv("DM_PASTE_FUSED"); return !(e && *e == '0'); }();
+    static const int tma_fill = [] { const char* e = getenv("DM_PASTE_TMA"); return (e && *e == '0') ? 0 : 1; }();
+    static const int diag = [] { const char* e = getenv("DM_PASTE_DIAG"); return e ? atoi(e) : 0; }();   // 1: no windows, 2: no fill
+    const bool fused = zero_fill && per_inst * ES >= dm::kFillTile && fused_on;
     if (fused) {
         // one launch: every CTA issues its share of the zero fill, then pastes its window bands
         const int win_y = N < 65535 ? N : 65535;
-        const unsigned n_win = (unsigned)(dm::kBandCtas * win_y);
+        const int n_virtual = dm::kBandCtas * win_y;
         const long long n_fill = (nbytes_all + dm::kFillTile - 1) / dm::kFillTile;
+        int dev = 0, sms = 0;
+        DM_CUDA_CHECK(cudaGetDevice(&dev), "dm_paste_masks/fused");
+        DM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "dm_paste_masks/fused");
+        static const int persist = [] { const char* e = getenv("DM_PASTE_PERSIST"); return e ? atoi(e) : 0; }();   // > 0: persistent launch with this many CTAs per SM (measured slower: static round robin loses the hardware scheduler's load balancing, 221 vs 176 us)
+        const unsigned grid = persist > 0 && (long long)sms * persist < n_virtual ? (unsigned)(sms * persist) : (unsigned)n_virtual;
         switch (out_mode) {
-            case DM_PASTE_BOOL: dm::paste_fused_kernel<DM_PASTE_BOOL><<<n_win, dm::kPasteThreads, 0, st>>>(p, win_y, n_fill, nbytes_all); break;
-            case DM_PASTE_U8: dm::paste_fused_kernel<DM_PASTE_U8><<<n_win, dm::kPasteThreads, 0, st>>>(p, win_y, n_fill, nbytes_all); break;
-            default: dm::paste_fused_kernel<DM_PASTE_F32><<<n_win, dm::kPasteThreads, 0, st>>>(p, win_y, n_fill, nbytes_all); break;
+            case DM_PASTE_BOOL: dm::paste_fused_kernel<DM_PASTE_BOOL><<<grid, dm::kPasteThreads, 0, st>>>(p, win_y, n_virtual, n_fill, nbytes_all, tma_fill, diag); break;
+            case DM_PASTE_U8: dm::paste_fused_kernel<DM_PASTE_U8><<<grid, dm::kPasteThreads, 0, st>>>(p, win_y, n_virtual, n_fill, nbytes_all, tma_fill, diag); break;
+            default: dm::paste_fused_kernel<DM_PASTE_F32><<<grid, dm::kPasteThreads, 0, st>>>(p, win_y, n_virtual, n_fill, nbytes_all, tma_fill, diag); break;
         }
         DM_LAUNCH_CHECK("dm_paste_masks/fused");
         return DM_OK;

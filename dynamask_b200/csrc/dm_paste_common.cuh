@@ -6,8 +6,16 @@
 namespace dm {
 
 constexpr int kPasteThreads = 256;
-constexpr int kBandRows = 32;       // window rows per band
-constexpr int kBandCtas = 8;        // CTAs per instance (grid.x); CTA b takes bands b, b + 8, ...
+#ifndef DM_BAND_ROWS
+#define DM_BAND_ROWS 16
+#endif
+#ifndef DM_BAND_CTAS
+#define DM_BAND_CTAS 8
+#endif
+constexpr int kBandRows = DM_BAND_ROWS;       // window rows per band of the paste kernels (C4 shape, fused launch: 32 rows 172 us,
+                                              // 16 rows 167 us, 8 rows 181 us; 16 CTAs per instance 180 / 167 / 180 us)
+constexpr int kRleBandRows = 32;              // canvas rows per staging band of the paste -> RLE kernels
+constexpr int kBandCtas = DM_BAND_CTAS;        // CTAs per instance (grid.x); CTA b takes bands b, b + 8, ...
 constexpr int kColTab = 1024;       // window columns whose x terms are staged in shared memory (8 KB)
 constexpr int kVPairs = 128;        // (value, slope) pairs of one warp's y-interpolated mask row: S + 3 <= 128
 constexpr int kMaskStage = 6144;    // floats of sigmoid(mask) window staged per CTA (24 KB)

@@ -103,7 +103,7 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
         const long long cls = p.labels ? p.labels[n] : 0;
         const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
         // band height: as many canvas rows as keep the reachable mask rows inside the scratch
-        int hb = kBandRows;
+        int hb = kRleBandRows;
         {
             const float ratio = fabsf((float)p.sh / (bx.w - bx.y));  // mask rows per canvas row
             const int cap = kMaskStage / st_w - 3;
