@@ -164,10 +164,10 @@ def _tail_setup(dm, dev, seed, n_img, dets, img_hw, channels, small_frac):
     return feats, stages, labels, ext, images
 
 
-def _tail_image(dm, ext, feats, stages, labels, rois, det, ori_shape):
+def _tail_image(dm, ext, feats, stages, labels, rois, det, ori_shape, wait=True):
     ins = ext(feats, rois)                                                # 14x14 instance features -> the head
     final = dm.refine_stage_instance_preds([t.clone() for t in stages])   # dynamask_roi_head.py:136-148, fused
-    rles = dm.get_seg_masks_rle(final, det, labels, _Cfg, ori_shape, 1.0, False)
+    rles = dm.get_seg_masks_rle(final, det, labels, _Cfg, ori_shape, 1.0, False, wait=wait)
     return ins, rles
 
 
@@ -184,12 +184,26 @@ def run_tail(dm, dev, rank, world, peak, total_images, dets, img_hw, ori_hw, str
     _barrier(world)
     rle_bytes = 0
     t0 = time.perf_counter()
+    # The loop of mmdet/apis/test.py:24-57, software-pipelined one image deep: image i+1 is enqueued before the
+    # strings of image i are collected (get_seg_masks_rle(wait=False) enqueues without a host synchronisation),
+    # so the host's launch work overlaps the device's.  Every image's strings are on the host, as Python bytes,
+    # before the clock stops.
     for _ in range(reps):
+        pending = None
         for i in range(mine):
-            _, rles = _tail_image(dm, ext, feats, stages, labels, images[i][0], images[i][1], ori_shape)
-            rle_bytes += sum(len(r['counts']) for r in rles)
+            _, nxt = _tail_image(dm, ext, feats, stages, labels, images[i][0], images[i][1], ori_shape, wait=False)
+            if pending is not None:
+                rle_bytes += sum(len(r['counts']) for r in pending.result())
+            pending = nxt
+        if pending is not None:
+            rle_bytes += sum(len(r['counts']) for r in pending.result())
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) / reps * 1e3
+    # the same images one at a time (collect before the next image is enqueued): the latency view
+    t1 = time.perf_counter()
+    for i in range(mine):
+        _tail_image(dm, ext, feats, stages, labels, images[i][0], images[i][1], ori_shape)
+    serial_ms = (time.perf_counter() - t1) * 1e3 / max(mine, 1)
     ms = _reduce_max(wall_ms, dev, world)
     n_total = total_images if strong else total_images * world
     # device time of the same calls (CUDA events around one pass), for the share of host work
@@ -205,6 +219,7 @@ def run_tail(dm, dev, rank, world, peak, total_images, dets, img_hw, ori_hw, str
         by += dets * 4.0 * 112 * 112                                                                  # paste reads the logits
     return {'images': n_total, 'images_this_rank': mine, 'ms_per_pass': ms, 'img_per_s': n_total / ms * 1e3,
             'instances_per_s': n_total * dets / ms * 1e3, 'ms_per_image_this_rank': wall_ms / max(mine, 1),
+            'ms_per_image_unpipelined': serial_ms, 'pipeline': 'one image deep (image i+1 enqueued before image i is collected)',
             'rle_bytes_to_host_per_image': rle_bytes / max(reps * mine, 1),
             'roofline': {'bound': 'latency (per-image calls of ~0.1 ms kernels; results leave as ~100 KB of RLE)',
                          'algorithmic_bytes_this_rank': by, 'achieved': by / wall_ms / 1e6, 'peak': peak, 'unit': 'GB/s',

@@ -33,6 +33,8 @@ struct RleParams {
     const int64_t* inst_offsets;  // [N] exclusive scan of inst_totals (pass 2)
     int32_t* trans;               // [sum] transitions, instance after instance (pass 2)
     const uint8_t* canvas;        // canvas source, or null
+    const int32_t* status;        // optional device word: non-zero = the transitions do not fit the caller's buffers,
+                                  // pass 2 writes nothing (dm_paste_rle_strings)
 };
 
 constexpr int kRleThreads = 256;
@@ -70,6 +72,7 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int st_w = p.sw + 2;
     const int zero_i = p.sw + 1, nan_i = p.sw + 2;
+    if (PASS == 2 && q.status && *q.status) return;   // CTA-uniform
     for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
         const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
         int xa, xb, ya, yb;
@@ -267,11 +270,11 @@ static int rle_fill(dm::RleParams& q, int N, int rh, int rw, int pass, int32_t* 
     return DM_OK;
 }
 
-extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
-                            const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
-                            const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
-                            int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
-                            const int64_t* inst_offsets, int32_t* transitions, dm_stream_t stream) {
+static int paste_rle_impl(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                          const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                          const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                          int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
+                          const int64_t* inst_offsets, int32_t* transitions, const int32_t* status, dm_stream_t stream) {
     if (N < 0 || S_h < 1 || S_w < 1 || img_h < 0 || img_w < 0) return DM_EINVAL;
     if (x_lo < 0 || y_lo < 0 || x_hi > img_w || y_hi > img_h || x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
     dm::RleParams q;
@@ -293,6 +296,7 @@ extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t m
     q.p.x_lo = x_lo;
     q.p.y_lo = y_lo;
     q.p.thr = thr;
+    q.status = status;
     q.p.total = (long long)q.p.rh * q.p.rw * N;
     dim3 grid((unsigned)((q.p.rw + dm::kRleThreads - 1) / dm::kRleThreads), (unsigned)(N < 65535 ? N : 65535));
     cudaStream_t st = (cudaStream_t)stream;
@@ -300,6 +304,26 @@ extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t m
     else dm::paste_rle_kernel<2><<<grid, dm::kRleThreads, 0, st>>>(q);
     DM_LAUNCH_CHECK("dm_paste_rle");
     return DM_OK;
+}
+
+extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                            const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                            const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                            int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
+                            const int64_t* inst_offsets, int32_t* transitions, dm_stream_t stream) {
+    return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
+                          x_lo, y_lo, x_hi, y_hi, thr, pass, col_counts, inst_totals, inst_offsets, transitions, nullptr,
+                          stream);
+}
+
+static int paste_rle_pass2_guarded(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                                   const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                                   const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi, int y_hi,
+                                   float thr, int32_t* col_counts, int32_t* inst_totals, const int64_t* inst_offsets,
+                                   int32_t* transitions, const int32_t* status, cudaStream_t st) {
+    return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
+                          x_lo, y_lo, x_hi, y_hi, thr, 2, col_counts, inst_totals, inst_offsets, transitions, status,
+                          (dm_stream_t)st);
 }
 
 extern "C" int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int32_t* col_counts,
@@ -372,8 +396,9 @@ template <int PASS>   // 1: compact + lengths, 2: write strings
 __global__ void __launch_bounds__(kRleThreads)
 rle_string_kernel(const int32_t* __restrict__ trans, const int64_t* __restrict__ inst_offsets, long long total_pixels,
                   int32_t* __restrict__ compact, int32_t* __restrict__ kept, int32_t* __restrict__ str_len,
-                  const int64_t* __restrict__ str_offsets, char* __restrict__ out) {
+                  const int64_t* __restrict__ str_offsets, char* __restrict__ out, const int32_t* __restrict__ status) {
     __shared__ int s_warp[kRleThreads / 32];
+    if (status && *status) return;   // CTA-uniform: nothing was written by pass 2
     const int n = blockIdx.x;
     const long long o0 = inst_offsets[n];
     const int cnt = (int)(inst_offsets[n + 1] - o0);
@@ -443,6 +468,37 @@ __global__ void __launch_bounds__(kRleThreads) rle_offsets_kernel(const int32_t*
     if (threadIdx.x == 0) str_offsets[N] = base;
 }
 
+// exclusive scan of the N per-instance transition counts -> inst_offsets[N+1]; header[0] = status (1 when the
+// total exceeds `capacity`: the later launches of the same call then write nothing), header[1] = total
+__global__ void __launch_bounds__(kRleThreads) rle_totals_scan_kernel(const int32_t* __restrict__ totals, int N,
+                                                                      long long capacity, int64_t* __restrict__ inst_offsets,
+                                                                      int32_t* __restrict__ status, int64_t* __restrict__ header) {
+    __shared__ int s_warp[kRleThreads / 32];
+    long long base = 0;
+    for (int i0 = 0; i0 < N; i0 += kRleThreads) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < N ? totals[i] : 0;
+        int tot;
+        const int pos = block_exclusive_scan(v, s_warp, tot);
+        if (i < N) inst_offsets[i] = base + pos;
+        base += tot;
+    }
+    if (threadIdx.x == 0) {
+        inst_offsets[N] = base;
+        const int over = base > capacity ? 1 : 0;
+        *status = over;
+        header[0] = over;
+        header[1] = base;
+    }
+}
+
+// an overflowing call still hands the host a well-formed (all-zero) offset table
+__global__ void __launch_bounds__(kRleThreads) rle_clear_offsets_kernel(int64_t* __restrict__ str_offsets, int N,
+                                                                        const int32_t* __restrict__ status) {
+    if (!*status) return;
+    for (int i = threadIdx.x; i <= N; i += kRleThreads) str_offsets[i] = 0;
+}
+
 }  // namespace dm
 
 extern "C" int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int N, int64_t total_pixels,
@@ -453,13 +509,80 @@ extern "C" int dm_rle_strings(const int32_t* transitions, const int64_t* inst_of
     if (!transitions || !inst_offsets || !compact || !kept || !str_len || !str_offsets || !out) return DM_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     dm::rle_string_kernel<1><<<N, dm::kRleThreads, 0, st>>>(transitions, inst_offsets, (long long)total_pixels, compact,
-                                                           kept, str_len, nullptr, nullptr);
+                                                           kept, str_len, nullptr, nullptr, nullptr);
     DM_LAUNCH_CHECK("dm_rle_strings/compact");
     dm::rle_offsets_kernel<<<1, dm::kRleThreads, 0, st>>>(str_len, N, str_offsets);
     DM_LAUNCH_CHECK("dm_rle_strings/scan");
     dm::rle_string_kernel<2><<<N, dm::kRleThreads, 0, st>>>(transitions, inst_offsets, (long long)total_pixels, compact,
-                                                           kept, str_len, str_offsets, out);
+                                                           kept, str_len, str_offsets, out, nullptr);
     DM_LAUNCH_CHECK("dm_rle_strings/write");
+    return DM_OK;
+}
+
+// Whole paste -> RLE-string pipeline in ONE call with no host round trip in the middle: count, scan
+// the counts on the device, write the transitions, build the strings.  The caller sizes the buffers
+// from a transition CAPACITY instead of the exact total; when the masks need more, the call writes
+// status = 1 into header[0] and nothing else (the caller repeats with header[1] transitions).
+//   workspace  device scratch of dm_paste_rle_strings_workspace(N, x_hi - x_lo, capacity) bytes, 16-byte aligned
+//   header     device int64 [2 + N + 1]: status, total transitions, string offsets (N + 1)
+//   out        device chars, at least 6 * capacity + 8 * N + 8 bytes
+extern "C" int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacity) {
+    if (N < 0 || rw < 0 || capacity < 0) return -1;
+    const int64_t n = N, w = rw > 0 ? rw : 1, cap = capacity > 0 ? capacity : 1;
+    // col_counts [N*rw] + totals [N] + kept [N] + str_len [N] + status [4] (int32), offsets [N+1] (int64), trans + compact [cap] each
+    int64_t b = 4 * (n * w + 3 * n + 4);
+    b = (b + 15) & ~15ll;
+    b += 8 * (n + 1);
+    b = (b + 15) & ~15ll;
+    b += 2 * 4 * cap;
+    return b + 16;
+}
+
+extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                                    const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                                    const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                                    int y_hi, float thr, void* workspace, int64_t capacity, int64_t* header,
+                                    char* out, dm_stream_t stream) {
+    if (N < 0 || capacity < 0) return DM_EINVAL;
+    if (N == 0) return DM_OK;
+    if (!workspace || !header || !out || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return DM_EINVAL;
+    if (x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
+    const int64_t n = N, w = (x_hi - x_lo) > 0 ? (x_hi - x_lo) : 1, cap = capacity > 0 ? capacity : 1;
+    char* base = static_cast<char*>(workspace);
+    int32_t* col_counts = reinterpret_cast<int32_t*>(base);
+    int32_t* totals = col_counts + n * w;
+    int32_t* kept = totals + n;
+    int32_t* str_len = kept + n;
+    int32_t* status = str_len + n;
+    int64_t off = (4 * (n * w + 3 * n + 4) + 15) & ~15ll;
+    int64_t* inst_offsets = reinterpret_cast<int64_t*>(base + off);
+    off = (off + 8 * (n + 1) + 15) & ~15ll;
+    int32_t* trans = reinterpret_cast<int32_t*>(base + off);
+    int32_t* compact = trans + cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    DM_CUDA_CHECK(cudaMemsetAsync(totals, 0, sizeof(int32_t) * (3 * n + 4), st), "dm_paste_rle_strings/memset");
+    int rc = dm_paste_rle(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
+                          x_lo, y_lo, x_hi, y_hi, thr, 1, col_counts, totals, nullptr, nullptr, stream);
+    if (rc != DM_OK) return rc;
+    dm::rle_totals_scan_kernel<<<1, dm::kRleThreads, 0, st>>>(totals, N, (long long)capacity, inst_offsets, status, header);
+    DM_LAUNCH_CHECK("dm_paste_rle_strings/scan");
+    if ((y_hi - y_lo) > 0 && (x_hi - x_lo) > 0) {
+        rc = paste_rle_pass2_guarded(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h,
+                                     img_w, x_lo, y_lo, x_hi, y_hi, thr, col_counts, totals, inst_offsets, trans, status, st);
+        if (rc != DM_OK) return rc;
+    }
+    const long long total_pixels = (long long)(y_hi - y_lo) * (x_hi - x_lo);
+    int64_t* str_offsets = header + 2;
+    dm::rle_string_kernel<1><<<N, dm::kRleThreads, 0, st>>>(trans, inst_offsets, total_pixels, compact, kept, str_len,
+                                                           nullptr, nullptr, status);
+    DM_LAUNCH_CHECK("dm_paste_rle_strings/compact");
+    dm::rle_offsets_kernel<<<1, dm::kRleThreads, 0, st>>>(str_len, N, str_offsets);
+    DM_LAUNCH_CHECK("dm_paste_rle_strings/offsets");
+    dm::rle_clear_offsets_kernel<<<1, dm::kRleThreads, 0, st>>>(str_offsets, N, status);
+    DM_LAUNCH_CHECK("dm_paste_rle_strings/clear");
+    dm::rle_string_kernel<2><<<N, dm::kRleThreads, 0, st>>>(trans, inst_offsets, total_pixels, compact, kept, str_len,
+                                                           str_offsets, out, status);
+    DM_LAUNCH_CHECK("dm_paste_rle_strings/write");
     return DM_OK;
 }
 

@@ -110,13 +110,15 @@ def _to_host(t):
 
 
 def get_seg_masks_rle(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape, scale_factor,
-                      rescale):
+                      rescale, wait=True):
     """``encode_mask_results`` of ``get_seg_masks`` in one device pass.
 
     Same arguments as :func:`get_seg_masks`; returns n COCO RLE dicts ``{'size': [h, w], 'counts':
     bytes}`` -- what ``pycocotools.mask.encode`` returns for each pasted mask
     (``mmdet/core/mask/utils.py:36-63``) -- without materialising or copying the ``[n, h, w]``
-    canvases: only the run boundaries cross PCIe.
+    canvases: only the run boundaries cross PCIe.  ``wait=False`` returns an ``ops.PendingRle`` instead:
+    the call is enqueued without a host synchronisation and ``.result()`` collects the dicts later,
+    so a test loop (``mmdet/apis/test.py:24-57``) can enqueue the next image first.
     """
     if rcnn_test_cfg.mask_thr_binary < 0:
         raise ValueError('RLE needs a binary mask: mask_thr_binary must be >= 0')
@@ -132,8 +134,9 @@ def get_seg_masks_rle(mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shap
     bboxes = bboxes / scale_factor
     img_h, img_w = int(img_h), int(img_w)
     labels = det_labels if mask_pred.shape[1] > 1 else None
-    return ops.paste_rle(mask_pred.to(torch.float32), bboxes, labels, img_h, img_w,
-                         [0, 0, img_w, img_h], True, float(rcnn_test_cfg.mask_thr_binary))
+    pending = ops.paste_rle_async(mask_pred.to(torch.float32), bboxes, labels, img_h, img_w,
+                                  [0, 0, img_w, img_h], True, float(rcnn_test_cfg.mask_thr_binary))
+    return pending.result() if wait else pending
 
 
 def encode_mask_results(mask_results):

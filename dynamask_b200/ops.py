@@ -391,11 +391,7 @@ def _rle_finish(N, rh, rw, totals, run_pass2):
     return [{'size': size, 'counts': raw[so[n]:so[n + 1]]} for n in range(N)]
 
 
-def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,
-              region: Sequence[int], apply_sigmoid: bool, thr: float):
-    """Fused paste -> COCO RLE: same arguments as :func:`paste_masks` in bool mode, but returns a
-    list of N ``{'size': [h, w], 'counts': bytes}`` dicts (what ``pycocotools.mask.encode`` gives for
-    each pasted canvas) without ever materialising the canvases."""
+def _paste_rle_args(masks, boxes, labels, region):
     if masks.dim() != 4:
         raise ValueError('masks must be [N,C,S_h,S_w]')
     if not masks.is_cuda:
@@ -403,17 +399,23 @@ def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int
     masks = _f32c(masks, 'masks')
     if masks.stride(3) != 1 or masks.stride(2) != masks.size(3):
         masks = masks.contiguous()
-    N, _, sh, sw = masks.shape
-    dev = masks.device
+    N = masks.size(0)
     boxes = _f32c(boxes, 'boxes')[:, :4].contiguous()
     if boxes.size(0) != N:
         raise ValueError('boxes must be [N,4]')
     if labels is not None:
         labels = labels.to(torch.int64).contiguous()
     x_lo, y_lo, x_hi, y_hi = [int(v) for v in region]
+    return masks, boxes, labels, (x_lo, y_lo, x_hi, y_hi)
+
+
+def _paste_rle_two_pass(masks, boxes, labels, img_h, img_w, reg, apply_sigmoid, thr):
+    """Exact-size form: the host reads the per-instance totals between the two passes (two
+    synchronisations).  Used when the capacity guess of :func:`paste_rle_async` was too small."""
+    N, _, sh, sw = masks.shape
+    dev = masks.device
+    x_lo, y_lo, x_hi, y_hi = reg
     rh, rw = y_hi - y_lo, x_hi - x_lo
-    if N == 0:
-        return []
     col_counts = torch.empty((N, max(rw, 1)), dtype=torch.int32, device=dev)
     totals = torch.zeros(N, dtype=torch.int32, device=dev)
 
@@ -428,6 +430,90 @@ def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int
 
     run(1, None, None)
     return _rle_finish(N, rh, rw, totals, lambda off, tr: run(2, off, tr))
+
+
+# transitions per instance the next paste_rle_async call provisions for (adapts to what the masks needed)
+_RLE_HINT = {'per_inst': 4096, 'str_bytes': 1 << 16}
+
+
+class PendingRle:
+    """RLE strings of one :func:`paste_rle_async` call on their way to the host.  ``result()`` waits
+    for the call's event (one synchronisation) and returns the list of COCO RLE dicts."""
+
+    def __init__(self, n, size, event=None, pinned=None, head=0, prefix=0, blob=None, keep=None, redo=None, ready=None):
+        self.n, self.size, self.event, self.pinned = n, size, event, pinned
+        self.head, self.prefix, self.blob, self.keep, self.redo, self._ready = head, prefix, blob, keep, redo, ready
+
+    def result(self):
+        if self._ready is not None:
+            return self._ready
+        self.event.synchronize()
+        hdr = self.pinned[:self.head].view(torch.int64)
+        status, total = int(hdr[0]), int(hdr[1])
+        _RLE_HINT['per_inst'] = max(1024, min(1 << 20, int(1.5 * total / max(self.n, 1)) + 256))
+        if status != 0:
+            # more transitions than provisioned: nothing was written, repeat with exact sizes
+            self._ready = self.redo()
+        else:
+            so = hdr[2:3 + self.n].tolist()
+            nbytes = so[-1]
+            _RLE_HINT['str_bytes'] = max(1 << 14, 2 * nbytes)
+            if nbytes <= self.prefix:
+                raw = self.pinned[self.head:self.head + nbytes].numpy().tobytes()
+            else:   # the strings are longer than the prefix that travelled with the header
+                rest = torch.empty(nbytes - self.prefix, dtype=torch.uint8, pin_memory=True)
+                rest.copy_(self.blob[self.head + self.prefix:self.head + nbytes], non_blocking=True)
+                torch.cuda.current_stream(self.blob.device).synchronize()
+                raw = self.pinned[self.head:self.head + self.prefix].numpy().tobytes() + rest.numpy().tobytes()
+            self._ready = [{'size': self.size, 'counts': raw[so[i]:so[i + 1]]} for i in range(self.n)]
+        self.blob = self.keep = self.redo = self.pinned = None
+        return self._ready
+
+
+def paste_rle_async(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,
+                    region: Sequence[int], apply_sigmoid: bool, thr: float) -> PendingRle:
+    """Fused paste -> COCO RLE strings, enqueued without any host synchronisation
+    (``dm_paste_rle_strings``: count, device-side scan, write, string building in one call; buffers
+    sized from a transition capacity that adapts to the previous calls).  The header, the string
+    offsets and the strings leave in ONE pinned copy behind the kernels; ``PendingRle.result()``
+    waits for it.  An inference loop can therefore enqueue the next image before it collects this
+    one's strings.  Same arguments and results as :func:`paste_rle`."""
+    masks, boxes, labels, reg = _paste_rle_args(masks, boxes, labels, region)
+    N, _, sh, sw = masks.shape
+    dev = masks.device
+    x_lo, y_lo, x_hi, y_hi = reg
+    rh, rw = y_hi - y_lo, x_hi - x_lo
+    size = [int(rh), int(rw)]
+    if N == 0:
+        return PendingRle(0, size, ready=[])
+    lib = _lib.load()
+    cap = int(N * _RLE_HINT['per_inst'])
+    ws_bytes = int(lib.dm_paste_rle_strings_workspace(N, max(rw, 1), cap))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    head = (8 * (N + 3) + 15) & ~15
+    out_cap = 6 * cap + 8 * N + 8
+    blob = torch.empty(head + out_cap, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.dm_paste_rle_strings(_ptr(masks), masks.stride(0), masks.stride(1), _ptr(labels), N, sh, sw,
+                                      int(bool(apply_sigmoid)), _ptr(boxes), int(img_h), int(img_w), x_lo, y_lo,
+                                      x_hi, y_hi, float(thr), _ptr(ws), cap, _ptr(blob),
+                                      ctypes.c_void_p(blob.data_ptr() + head), _stream(dev))
+    _lib.check(rc, 'dm_paste_rle_strings')
+    prefix = min(out_cap, int(_RLE_HINT['str_bytes']))
+    pinned = torch.empty(head + prefix, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(blob[:head + prefix], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    redo = lambda: _paste_rle_two_pass(masks, boxes, labels, img_h, img_w, reg, apply_sigmoid, thr)  # noqa: E731
+    return PendingRle(N, size, ev, pinned, head, prefix, blob, (ws, masks, boxes, labels), redo)
+
+
+def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,
+              region: Sequence[int], apply_sigmoid: bool, thr: float):
+    """Fused paste -> COCO RLE: same arguments as :func:`paste_masks` in bool mode, but returns a
+    list of N ``{'size': [h, w], 'counts': bytes}`` dicts (what ``pycocotools.mask.encode`` gives for
+    each pasted canvas) without ever materialising the canvases.  One host synchronisation."""
+    return paste_rle_async(masks, boxes, labels, img_h, img_w, region, apply_sigmoid, thr).result()
 
 
 def rle_from_canvas(canvas: Tensor):

@@ -186,6 +186,30 @@ int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int 
                    int32_t* compact, int32_t* kept, int32_t* str_len, int64_t* str_offsets, char* out,
                    dm_stream_t stream);
 /*
+ * The whole paste -> RLE-string pipeline of one image in ONE call, with no host round trip in the
+ * middle: count (dm_paste_rle pass 1), scan the per-instance counts on the device, write the
+ * transitions (pass 2), build the strings (dm_rle_strings).  The caller sizes the buffers from a
+ * transition CAPACITY instead of the exact total, so the call can be enqueued without waiting for
+ * anything; results are read after one synchronisation (or an event) chosen by the caller, which
+ * lets an inference loop enqueue image i+1 while image i's strings travel to the host
+ * (mmdet/apis/test.py:24-57 handles one image after the other).
+ *   workspace  device scratch of dm_paste_rle_strings_workspace(N, x_hi - x_lo, capacity) bytes,
+ *              16-byte aligned, owned by the caller until the call has finished on `stream`
+ *   capacity   transitions the buffers hold (all instances together)
+ *   header     device int64 [2 + N + 1]: header[0] = status (0 ok, 1 = the masks have more
+ *              transitions than `capacity`: nothing else was written, repeat with capacity >=
+ *              header[1]), header[1] = total transitions, header[2 .. 2+N] = string offsets
+ *   out        device chars, at least 6 * capacity + 8 * N + 8 bytes
+ * Other arguments as dm_paste_rle.  Replaces get_seg_masks + encode_mask_results
+ * (mmdet/models/roi_heads/mask_heads/dynamask_head.py:279-342, mmdet/core/mask/utils.py:36-63).
+ */
+int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacity);
+int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
+                         const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
+                         const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
+                         int y_hi, float thr, void* workspace, int64_t capacity, int64_t* header,
+                         char* out, dm_stream_t stream);
+/*
  * HOST function: the transitions of one instance (host memory) -> pycocotools' compressed "counts"
  * string (rleToString).  Coinciding transition pairs cancel.  Returns the length written to `out`
  * (no terminator) or -1 if `cap` is too small.

@@ -448,3 +448,63 @@ def test_polygon_masks_rasterise_at_image_size(hw):
     t = pm.to_tensor(torch.float32, 'cuda')
     assert t.shape == (len(objs), H, W) and float(t.sum()) == float(got.sum())
     assert pm.to_bitmap().masks.shape == (len(objs), H, W)
+
+
+# ------------------------------------------------------------------------------------------
+# dm_paste_rle_strings: the whole paste -> RLE pipeline enqueued without a host round trip
+# (capacity-sized buffers, one synchronisation when the strings are collected)
+# ------------------------------------------------------------------------------------------
+def _rle_inputs(seed, n, hw):
+    g = torch.Generator().manual_seed(seed)
+    H, W = hw
+    logits = synth.make_mask_logits(n, 28, g).cuda()
+    boxes = synth.make_boxes(n, H, W, g).cuda()
+    return logits, boxes
+
+
+def test_paste_rle_async_equals_two_pass_and_recovers_from_small_capacity():
+    from dynamask_b200 import ops
+    H, W = 203, 317
+    logits, boxes = _rle_inputs(11, 23, (H, W))
+    reg = (0, 0, W, H)
+    want = ops._paste_rle_two_pass(logits, boxes, None, H, W, reg, True, 0.5)
+    canv = ops.paste_masks(logits, boxes, None, H, W, list(reg), True, 0.5, ops.PASTE_BOOL)
+    assert [r['counts'] for r in ops.rle_from_canvas(canv)] == [r['counts'] for r in want]
+    saved = dict(ops._RLE_HINT)
+    try:
+        got = ops.paste_rle_async(logits, boxes, None, H, W, list(reg), True, 0.5).result()
+        assert got == want
+        # capacity far too small: the device reports it (nothing written), the call repeats with exact sizes
+        ops._RLE_HINT['per_inst'] = 1
+        assert ops.paste_rle_async(logits, boxes, None, H, W, list(reg), True, 0.5).result() == want
+        assert ops._RLE_HINT['per_inst'] > 1          # ... and the next call provisions for what was needed
+        # strings longer than the prefix that travels with the header: second copy for the rest
+        ops._RLE_HINT['str_bytes'] = 16
+        assert ops.paste_rle_async(logits, boxes, None, H, W, list(reg), True, 0.5).result() == want
+        # a sub-region of the canvas, class-specific masks
+        g = torch.Generator().manual_seed(12)
+        multi = torch.randn(23, 3, 28, 28, generator=g).cuda() * 3
+        labels = torch.randint(0, 3, (23,), generator=g).cuda()
+        sub = (16, 8, W - 5, H - 9)
+        want2 = ops._paste_rle_two_pass(multi, boxes, labels, H, W, sub, True, 0.5)
+        assert ops.paste_rle_async(multi, boxes, labels, H, W, list(sub), True, 0.5).result() == want2
+        assert ops.paste_rle_async(multi[:0], boxes[:0], labels[:0], H, W, list(sub), True, 0.5).result() == []
+    finally:
+        ops._RLE_HINT.update(saved)
+
+
+def test_paste_rle_async_pipelined_images():
+    """Three images enqueued back to back, strings collected afterwards (the C4 test loop of bench.py)."""
+    from dynamask_b200 import ops
+    H, W = 160, 240
+    imgs = [_rle_inputs(20 + i, 9 + 4 * i, (H, W)) for i in range(3)]
+    want = [ops._paste_rle_two_pass(l, b, None, H, W, (0, 0, W, H), True, 0.5) for l, b in imgs]
+    pend = [ops.paste_rle_async(l, b, None, H, W, [0, 0, W, H], True, 0.5) for l, b in imgs]
+    assert [p.result() for p in pend] == want
+    class Cfg:
+        mask_thr_binary = 0.5
+    l, b = imgs[1]
+    det = torch.cat([b, torch.ones(b.size(0), 1, device=b.device)], 1)
+    lab = torch.zeros(b.size(0), dtype=torch.long, device=b.device)
+    p = dm().get_seg_masks_rle(l, det, lab, Cfg, (H, W, 3), 1.0, False, wait=False)
+    assert p.result() == dm().get_seg_masks_rle(l, det, lab, Cfg, (H, W, 3), 1.0, False)
