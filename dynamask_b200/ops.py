@@ -450,14 +450,17 @@ class PendingRle:
         self.event.synchronize()
         hdr = self.pinned[:self.head].view(torch.int64)
         status, total = int(hdr[0]), int(hdr[1])
-        _RLE_HINT['per_inst'] = max(1024, min(1 << 20, int(1.5 * total / max(self.n, 1)) + 256))
+        # provision for 1.5x what the densest image so far needed, in powers of two: the buffer sizes then stay the
+        # same from call to call and come out of the caching allocators (no cudaMalloc / cudaHostAlloc per image)
+        need = int(1.5 * total / max(self.n, 1)) + 256
+        _RLE_HINT['per_inst'] = min(1 << 20, max(_RLE_HINT['per_inst'], 1 << (need - 1).bit_length()))
         if status != 0:
             # more transitions than provisioned: nothing was written, repeat with exact sizes
             self._ready = self.redo()
         else:
             so = hdr[2:3 + self.n].tolist()
             nbytes = so[-1]
-            _RLE_HINT['str_bytes'] = max(1 << 14, 2 * nbytes)
+            _RLE_HINT['str_bytes'] = max(_RLE_HINT['str_bytes'], 1 << (2 * nbytes - 1).bit_length()) if nbytes else _RLE_HINT['str_bytes']
             if nbytes <= self.prefix:
                 raw = self.pinned[self.head:self.head + nbytes].numpy().tobytes()
             else:   # the strings are longer than the prefix that travelled with the header
