@@ -677,7 +677,9 @@ def run_extras(dm, ops, dev, rank, peak):
     ex['dm_simple_roi_align'] = {'workload': 'SFMStage gathers: 100 RoIs x 256 ch at 14/28/56 from the stride 16/8/4 maps, '
                                              "every stage with the reference's spatial_scale = 1/4", **sra}
     # fused stage-to-stage refinement, one chunk of 100 detections (28 -> 56 -> 112)
-    st = [torch.randn(100, 1, sz, sz, device=dev) * 3 for sz in (28, 56, 112)]
+    # every stage predicts the same object: radial blob + N(0,1) noise per pixel at each stage's resolution
+    g_st = torch.Generator().manual_seed(77)
+    st = [synth.make_mask_logits(100, sz, g_st).to(dev) for sz in (28, 56, 112)]
     ms, _ = timed(lambda: dm.refine_stage_instance_preds(st))
     ex['dm_refine_stages'] = {'workload': '100 detections, stages 28/56/112, in place', 'ms': ms,
                               'instances_per_s': 100 / ms * 1e3}
@@ -701,7 +703,8 @@ def run_extras(dm, ops, dev, rank, peak):
     dt = (_time.perf_counter() - t0) / 5
     ex['inference_tail_per_image'] = {
         'workload': 'one 800x1333 image, 100 detections: 14x14 mask RoIAlign (256 ch) + refinement 28/56/112 + '
-                    'fused paste->RLE, results on the host as RLE strings; head convolutions excluded (PyTorch)',
+                    'fused paste->RLE, results on the host as RLE strings; head convolutions excluded (PyTorch); stage logits: '
+                    'blob + N(0,1) noise at every stage',
         'ms': dt * 1e3, 'img_per_s': 1.0 / dt}
     return ex
 

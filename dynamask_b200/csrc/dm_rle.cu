@@ -33,11 +33,16 @@ struct RleParams {
     const int64_t* inst_offsets;  // [N] exclusive scan of inst_totals (pass 2)
     int32_t* trans;               // [sum] transitions, instance after instance (pass 2)
     const uint8_t* canvas;        // canvas source, or null
+    int32_t* slots;               // optional [N][rw][kRleSlots]: pass 1 also RECORDS a column's first kRleSlots transitions, so
+                                  // that pass 3 (a copy) replaces the second evaluation for every instance whose columns all fit
+    int32_t* inst_over;           // [N][gridDim.x] set by pass 1 when a column of the CTA's 256 has more transitions than slots
     const int32_t* status;        // optional device word: non-zero = the transitions do not fit the caller's buffers,
                                   // pass 2 writes nothing (dm_paste_rle_strings)
 };
 
 constexpr int kRleThreads = 256;
+constexpr int kRleSlots = 32;  // transitions per column recorded in pass 1 (128 bytes per column; a clean mask has 2-4 per
+                               // column, the benchmark's noisy synthetic logits ~16-20)
 
 // exclusive scan of one int per thread over the CTA; returns the thread's prefix, `total` = CTA sum
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
@@ -72,8 +77,10 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int st_w = p.sw + 2;
     const int zero_i = p.sw + 1, nan_i = p.sw + 2;
-    if (PASS == 2 && q.status && *q.status) return;   // CTA-uniform
+    if (PASS >= 2 && q.status && *q.status) return;   // CTA-uniform
     for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
+        // with recorded slots: pass 3 copies the column blocks whose columns all fitted, pass 2 re-evaluates the others
+        if (PASS >= 2 && q.inst_over && (q.inst_over[(size_t)n * gridDim.x + blockIdx.x] != 0) != (PASS == 2)) continue;   // CTA-uniform
         const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
         int xa, xb, ya, yb;
         window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
@@ -93,7 +100,7 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
             cw = a.wh;
         }
         int32_t* out = nullptr;
-        if (PASS == 2) {
+        if (PASS >= 2) {
             // transitions of the instance's earlier columns: those of earlier CTAs + a scan inside this one
             int part = 0;
             for (int c = wxa + threadIdx.x; c < c0; c += kRleThreads) part += q.col_counts[(size_t)n * p.rw + c];
@@ -102,6 +109,13 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
             const int mine = live ? q.col_counts[(size_t)n * p.rw + x] : 0;
             const int pre = block_exclusive_scan(mine, s_warp, dummy);
             out = q.trans + q.inst_offsets[n] + before + pre;
+            if (PASS == 3) {   // the column's transitions were recorded by pass 1: copy them into place
+                if (live) {
+                    const int32_t* sl = q.slots + ((size_t)n * p.rw + x) * kRleSlots;
+                    for (int k = 0; k < mine; ++k) out[k] = sl[k];
+                }
+                continue;
+            }
         }
         const long long cls = p.labels ? p.labels[n] : 0;
         const float* __restrict__ m = p.masks + (long long)n * p.stride_n + cls * p.stride_c;
@@ -116,10 +130,15 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
         in.load(p, n);
         int prev = 0, cnt = 0;
         const int col_base = x * p.rh;
+        int32_t* const rec = (PASS == 1 && q.slots && live) ? q.slots + ((size_t)n * p.rw + x) * kRleSlots : nullptr;
         auto step = [&](int row, bool b) {
             if ((int)b != prev) {
-                if (PASS == 1) ++cnt;
-                else *out++ = col_base + row;
+                if (PASS == 1) {
+                    if (rec && cnt < kRleSlots) rec[cnt] = col_base + row;
+                    ++cnt;
+                } else {
+                    *out++ = col_base + row;
+                }
                 prev = (int)b;
             }
         };
@@ -198,6 +217,7 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
         if (prev) step(wyb, false);  // every column returns to 0 after its last window row
         if (PASS == 1) {
             if (live) q.col_counts[(size_t)n * p.rw + x] = cnt;
+            if (q.inst_over && cnt > kRleSlots) q.inst_over[(size_t)n * gridDim.x + blockIdx.x] = 1;
             int total = 0;
             block_exclusive_scan(cnt, s_warp, total);
             if (threadIdx.x == 0 && total) atomicAdd(q.inst_totals + n, total);
@@ -255,9 +275,9 @@ canvas_rle_kernel(const __grid_constant__ RleParams q) {
 
 static int rle_fill(dm::RleParams& q, int N, int rh, int rw, int pass, int32_t* col_counts, int32_t* inst_totals,
                     const int64_t* inst_offsets, int32_t* transitions) {
-    if (pass != 1 && pass != 2) return DM_EINVAL;
+    if (pass < 1 || pass > 3) return DM_EINVAL;   // (3: internal, dm_paste_rle_strings)
     if (!col_counts || !inst_totals) return DM_EINVAL;
-    if (pass == 2 && (!inst_offsets || !transitions)) return DM_EINVAL;
+    if (pass >= 2 && (!inst_offsets || !transitions)) return DM_EINVAL;
     if ((long long)rh * rw >= (1ll << 30)) return DM_EUNSUPPORTED;
     q.p.N = N;
     q.p.rh = rh;
@@ -274,7 +294,8 @@ static int paste_rle_impl(const float* masks, int64_t mask_stride_n, int64_t mas
                           const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
                           const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
                           int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
-                          const int64_t* inst_offsets, int32_t* transitions, const int32_t* status, dm_stream_t stream) {
+                          const int64_t* inst_offsets, int32_t* transitions, const int32_t* status, int32_t* slots,
+                          int32_t* inst_over, dm_stream_t stream) {
     if (N < 0 || S_h < 1 || S_w < 1 || img_h < 0 || img_w < 0) return DM_EINVAL;
     if (x_lo < 0 || y_lo < 0 || x_hi > img_w || y_hi > img_h || x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
     dm::RleParams q;
@@ -297,10 +318,13 @@ static int paste_rle_impl(const float* masks, int64_t mask_stride_n, int64_t mas
     q.p.y_lo = y_lo;
     q.p.thr = thr;
     q.status = status;
+    q.slots = slots;
+    q.inst_over = inst_over;
     q.p.total = (long long)q.p.rh * q.p.rw * N;
     dim3 grid((unsigned)((q.p.rw + dm::kRleThreads - 1) / dm::kRleThreads), (unsigned)(N < 65535 ? N : 65535));
     cudaStream_t st = (cudaStream_t)stream;
     if (pass == 1) dm::paste_rle_kernel<1><<<grid, dm::kRleThreads, 0, st>>>(q);
+    else if (pass == 3) dm::paste_rle_kernel<3><<<grid, dm::kRleThreads, 0, st>>>(q);
     else dm::paste_rle_kernel<2><<<grid, dm::kRleThreads, 0, st>>>(q);
     DM_LAUNCH_CHECK("dm_paste_rle");
     return DM_OK;
@@ -311,19 +335,10 @@ extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t m
                             const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
                             int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
                             const int64_t* inst_offsets, int32_t* transitions, dm_stream_t stream) {
+    if (pass != 1 && pass != 2) return DM_EINVAL;
     return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
                           x_lo, y_lo, x_hi, y_hi, thr, pass, col_counts, inst_totals, inst_offsets, transitions, nullptr,
-                          stream);
-}
-
-static int paste_rle_pass2_guarded(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
-                                   const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
-                                   const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi, int y_hi,
-                                   float thr, int32_t* col_counts, int32_t* inst_totals, const int64_t* inst_offsets,
-                                   int32_t* transitions, const int32_t* status, cudaStream_t st) {
-    return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
-                          x_lo, y_lo, x_hi, y_hi, thr, 2, col_counts, inst_totals, inst_offsets, transitions, status,
-                          (dm_stream_t)st);
+                          nullptr, nullptr, stream);
 }
 
 extern "C" int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int32_t* col_counts,
@@ -381,16 +396,13 @@ __device__ __forceinline__ void rle_code_write(long long x, char* out) {
     }
 }
 
-// value stored for count k of an instance whose surviving transitions are tp[0..m): the count itself
-// for k < 3, else its difference to the count two before.  k == m is the closing run.
-__device__ __forceinline__ long long rle_count(const int32_t* tp, int m, int k, long long total_pixels) {
-    auto t = [&](int i) -> long long { return i < 0 ? 0ll : (i < m ? (long long)tp[i] : total_pixels); };
-    return t(k) - t(k - 1);
-}
-__device__ __forceinline__ long long rle_stored(const int32_t* tp, int m, int k, long long total_pixels) {
-    const long long c = rle_count(tp, m, k, total_pixels);
-    return k > 2 ? c - rle_count(tp, m, k - 2, total_pixels) : c;
-}
+// Value stored for count k of an instance whose surviving transitions are tp[0..m): with
+// t(i) = 0 for i < 0, tp[i] for i < m, total_pixels beyond, count(k) = t(k) - t(k-1) (k == m is the
+// closing run); the string holds count(k) for k < 3, else count(k) - count(k-2).
+
+// Four consecutive items per thread and step: the kernels are chains of block scans (a few thousand transitions
+// per instance, one CTA per instance), so fewer, fatter steps is what shortens them (50 + 43 us -> see profiles/).
+constexpr int kRleItems = 4;
 
 template <int PASS>   // 1: compact + lengths, 2: write strings
 __global__ void __launch_bounds__(kRleThreads)
@@ -404,18 +416,30 @@ rle_string_kernel(const int32_t* __restrict__ trans, const int64_t* __restrict__
     const int cnt = (int)(inst_offsets[n + 1] - o0);
     const int32_t* t = trans + o0;
     int32_t* tp = compact + o0;
+    constexpr int STEP = kRleThreads * kRleItems;
     if (PASS == 1) {
         int m = 0;
-        for (int i0 = 0; i0 < cnt; i0 += kRleThreads) {
-            const int i = i0 + threadIdx.x;
-            int keep = 0, v = 0;
-            if (i < cnt) {
-                v = t[i];
-                keep = (i == 0 || t[i - 1] != v) && (i + 1 >= cnt || t[i + 1] != v);
+        for (int i0 = 0; i0 < cnt; i0 += STEP) {
+            const int ib = i0 + threadIdx.x * kRleItems;
+            // the thread's items and their two neighbours
+            int v[kRleItems + 2];
+#pragma unroll
+            for (int j = 0; j < kRleItems + 2; ++j) {
+                const int i = ib + j - 1;
+                v[j] = (i >= 0 && i < cnt) ? t[i] : -1 - j;   // (out of range: differs from every real neighbour)
+            }
+            int keep[kRleItems], mine = 0;
+#pragma unroll
+            for (int j = 0; j < kRleItems; ++j) {
+                const int i = ib + j;
+                keep[j] = i < cnt && (i == 0 || v[j] != v[j + 1]) && (i + 1 >= cnt || v[j + 2] != v[j + 1]);
+                mine += keep[j];
             }
             int tot;
-            const int pos = block_exclusive_scan(keep, s_warp, tot);
-            if (keep) tp[m + pos] = v;
+            int pos = m + block_exclusive_scan(mine, s_warp, tot);
+#pragma unroll
+            for (int j = 0; j < kRleItems; ++j)
+                if (keep[j]) tp[pos++] = v[j + 1];
             m += tot;
         }
         __syncthreads();
@@ -423,7 +447,23 @@ rle_string_kernel(const int32_t* __restrict__ trans, const int64_t* __restrict__
         const long long last = m > 0 ? (long long)tp[m - 1] : 0ll;
         const int nc = m + ((last < total_pixels || m == 0) ? 1 : 0);
         int len = 0;
-        for (int k = threadIdx.x; k < nc; k += kRleThreads) len += rle_code_len(rle_stored(tp, m, k, total_pixels));
+        for (int k0 = threadIdx.x * kRleItems; k0 < nc; k0 += STEP) {
+            // counts k0-2 .. k0+3 from the transitions k0-3 .. k0+3
+            long long tv[kRleItems + 3];
+#pragma unroll
+            for (int j = 0; j < kRleItems + 3; ++j) {
+                const int i = k0 + j - 3;
+                tv[j] = i < 0 ? 0ll : (i < m ? (long long)tp[i] : total_pixels);
+            }
+#pragma unroll
+            for (int j = 0; j < kRleItems; ++j) {
+                const int k = k0 + j;
+                if (k < nc) {
+                    const long long c = tv[j + 3] - tv[j + 2];
+                    len += rle_code_len(k > 2 ? c - (tv[j + 1] - tv[j]) : c);
+                }
+            }
+        }
         int tot;
         block_exclusive_scan(len, s_warp, tot);
         if (threadIdx.x == 0) {
@@ -436,17 +476,35 @@ rle_string_kernel(const int32_t* __restrict__ trans, const int64_t* __restrict__
         const int nc = m + ((last < total_pixels || m == 0) ? 1 : 0);
         char* dst = out + str_offsets[n];
         int base = 0;
-        for (int k0 = 0; k0 < nc; k0 += kRleThreads) {
-            const int k = k0 + threadIdx.x;
-            long long x = 0;
-            int len = 0;
-            if (k < nc) {
-                x = rle_stored(tp, m, k, total_pixels);
-                len = rle_code_len(x);
+        for (int kb = 0; kb < nc; kb += STEP) {
+            const int k0 = kb + threadIdx.x * kRleItems;
+            long long tv[kRleItems + 3];
+#pragma unroll
+            for (int j = 0; j < kRleItems + 3; ++j) {
+                const int i = k0 + j - 3;
+                tv[j] = i < 0 ? 0ll : (i < m ? (long long)tp[i] : total_pixels);
+            }
+            long long x[kRleItems];
+            int len[kRleItems], mine = 0;
+#pragma unroll
+            for (int j = 0; j < kRleItems; ++j) {
+                const int k = k0 + j;
+                x[j] = 0;
+                len[j] = 0;
+                if (k < nc) {
+                    const long long c = tv[j + 3] - tv[j + 2];
+                    x[j] = k > 2 ? c - (tv[j + 1] - tv[j]) : c;
+                    len[j] = rle_code_len(x[j]);
+                }
+                mine += len[j];
             }
             int tot;
-            const int pos = block_exclusive_scan(len, s_warp, tot);
-            if (k < nc) rle_code_write(x, dst + base + pos);
+            int pos = base + block_exclusive_scan(mine, s_warp, tot);
+#pragma unroll
+            for (int j = 0; j < kRleItems; ++j) {
+                if (len[j]) rle_code_write(x[j], dst + pos);
+                pos += len[j];
+            }
             base += tot;
         }
     }
@@ -526,16 +584,35 @@ extern "C" int dm_rle_strings(const int32_t* transitions, const int64_t* inst_of
 //   workspace  device scratch of dm_paste_rle_strings_workspace(N, x_hi - x_lo, capacity) bytes, 16-byte aligned
 //   header     device int64 [2 + N + 1]: status, total transitions, string offsets (N + 1)
 //   out        device chars, at least 6 * capacity + 8 * N + 8 bytes
+namespace {
+// layout of the caller's workspace (all offsets 16-byte aligned)
+struct RleWorkspace {
+    int64_t col_counts, totals, kept, str_len, status, inst_over, inst_offsets, slots, trans, compact, bytes;
+};
+RleWorkspace rle_workspace(int N, int rw, int64_t capacity) {
+    const int64_t n = N, w = rw > 0 ? rw : 1, cap = capacity > 0 ? capacity : 1;
+    auto up = [](int64_t v) { return (v + 15) & ~15ll; };
+    RleWorkspace ws;
+    int64_t o = 0;
+    ws.col_counts = o; o = up(o + 4 * n * w);
+    // totals | kept | str_len | status (4 words) | inst_over: one memset clears them
+    ws.totals = o; o += 4 * n;
+    ws.kept = o; o += 4 * n;
+    ws.str_len = o; o += 4 * n;
+    ws.status = o; o += 16;
+    ws.inst_over = o; o = up(o + 4 * n * ((w + dm::kRleThreads - 1) / dm::kRleThreads));
+    ws.inst_offsets = o; o = up(o + 8 * (n + 1));
+    ws.slots = o; o = up(o + 4 * n * w * dm::kRleSlots);
+    ws.trans = o; o = up(o + 4 * cap);
+    ws.compact = o; o = up(o + 4 * cap);
+    ws.bytes = o;
+    return ws;
+}
+}  // namespace
+
 extern "C" int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacity) {
     if (N < 0 || rw < 0 || capacity < 0) return -1;
-    const int64_t n = N, w = rw > 0 ? rw : 1, cap = capacity > 0 ? capacity : 1;
-    // col_counts [N*rw] + totals [N] + kept [N] + str_len [N] + status [4] (int32), offsets [N+1] (int64), trans + compact [cap] each
-    int64_t b = 4 * (n * w + 3 * n + 4);
-    b = (b + 15) & ~15ll;
-    b += 8 * (n + 1);
-    b = (b + 15) & ~15ll;
-    b += 2 * 4 * cap;
-    return b + 16;
+    return rle_workspace(N, rw, capacity).bytes;
 }
 
 extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
@@ -547,30 +624,35 @@ extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, i
     if (N == 0) return DM_OK;
     if (!workspace || !header || !out || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return DM_EINVAL;
     if (x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
-    const int64_t n = N, w = (x_hi - x_lo) > 0 ? (x_hi - x_lo) : 1, cap = capacity > 0 ? capacity : 1;
+    const RleWorkspace ws = rle_workspace(N, x_hi - x_lo, capacity);
     char* base = static_cast<char*>(workspace);
-    int32_t* col_counts = reinterpret_cast<int32_t*>(base);
-    int32_t* totals = col_counts + n * w;
-    int32_t* kept = totals + n;
-    int32_t* str_len = kept + n;
-    int32_t* status = str_len + n;
-    int64_t off = (4 * (n * w + 3 * n + 4) + 15) & ~15ll;
-    int64_t* inst_offsets = reinterpret_cast<int64_t*>(base + off);
-    off = (off + 8 * (n + 1) + 15) & ~15ll;
-    int32_t* trans = reinterpret_cast<int32_t*>(base + off);
-    int32_t* compact = trans + cap;
+    int32_t* col_counts = reinterpret_cast<int32_t*>(base + ws.col_counts);
+    int32_t* totals = reinterpret_cast<int32_t*>(base + ws.totals);
+    int32_t* kept = reinterpret_cast<int32_t*>(base + ws.kept);
+    int32_t* str_len = reinterpret_cast<int32_t*>(base + ws.str_len);
+    int32_t* status = reinterpret_cast<int32_t*>(base + ws.status);
+    int32_t* inst_over = reinterpret_cast<int32_t*>(base + ws.inst_over);
+    int64_t* inst_offsets = reinterpret_cast<int64_t*>(base + ws.inst_offsets);
+    int32_t* slots = reinterpret_cast<int32_t*>(base + ws.slots);
+    int32_t* trans = reinterpret_cast<int32_t*>(base + ws.trans);
+    int32_t* compact = reinterpret_cast<int32_t*>(base + ws.compact);
     cudaStream_t st = (cudaStream_t)stream;
-    DM_CUDA_CHECK(cudaMemsetAsync(totals, 0, sizeof(int32_t) * (3 * n + 4), st), "dm_paste_rle_strings/memset");
-    int rc = dm_paste_rle(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
-                          x_lo, y_lo, x_hi, y_hi, thr, 1, col_counts, totals, nullptr, nullptr, stream);
+    DM_CUDA_CHECK(cudaMemsetAsync(totals, 0, (size_t)(ws.inst_offsets - ws.totals), st), "dm_paste_rle_strings/memset");
+    auto pass = [&](int no) {
+        return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
+                              x_lo, y_lo, x_hi, y_hi, thr, no, col_counts, totals, inst_offsets, trans, status, slots,
+                              inst_over, stream);
+    };
+    // 1: count, and record up to kRleSlots transitions per column
+    int rc = pass(1);
     if (rc != DM_OK) return rc;
     dm::rle_totals_scan_kernel<<<1, dm::kRleThreads, 0, st>>>(totals, N, (long long)capacity, inst_offsets, status, header);
     DM_LAUNCH_CHECK("dm_paste_rle_strings/scan");
-    if ((y_hi - y_lo) > 0 && (x_hi - x_lo) > 0) {
-        rc = paste_rle_pass2_guarded(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h,
-                                     img_w, x_lo, y_lo, x_hi, y_hi, thr, col_counts, totals, inst_offsets, trans, status, st);
-        if (rc != DM_OK) return rc;
-    }
+    // 3: column blocks whose columns all fitted their slots are copied into place; 2: the others are evaluated again
+    rc = pass(3);
+    if (rc != DM_OK) return rc;
+    rc = pass(2);
+    if (rc != DM_OK) return rc;
     const long long total_pixels = (long long)(y_hi - y_lo) * (x_hi - x_lo);
     int64_t* str_offsets = header + 2;
     dm::rle_string_kernel<1><<<N, dm::kRleThreads, 0, st>>>(trans, inst_offsets, total_pixels, compact, kept, str_len,

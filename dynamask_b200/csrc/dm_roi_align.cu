@@ -2463,7 +2463,7 @@ struct RaConfig {
 static const RaConfig& config() {
     static const RaConfig c = [] {
         RaConfig r;
-        r.want = env_int("DM_RA_WANT", 24);
+        r.want = env_int("DM_RA_WANT", 0);   // work units per SM wanted from a single-bucket launch; 0: by pooled size
         r.cg = env_int("DM_RA_CG", 0);
         r.interleave = env_int("DM_RA_INTERLEAVE", 1);
         r.fwd_smem_kb = env_int("DM_RA_FWD_SMEM_KB", 100);
@@ -2613,7 +2613,12 @@ static int fill_params(RaParams& p, float* const* feat_ptrs, const int32_t* feat
             const int cpw_guess = pwv_guess >= 32 ? 1 : 32 / pwv_guess;
             // (on the TMA path a warp pass covers 4 * tma_ch channels)
             const int cg_min = 8 * (pwv_guess <= 8 && fwd_tma ? 4 * tma_ch(vec_guess, 4) : (cpw_guess > 4 ? 4 : cpw_guess));
-            const long long want = (long long)config().want * sm_count();
+            // the BACKWARD of pooled sizes up to 14x14 prefers whole-RoI units (a unit's tables and its cold ring start
+            // weigh more than the balance; kernel-only, 6 vs 24 units per SM: 14x14 x 256 RoIs bwd 139 -> 109 us,
+            // 7x7 x 1024 RoIs bwd 300 -> 286); the forward does not (14x14 x 2132 RoIs 338 -> 366 us), and 56x56 x 256
+            // RoIs needs the fine units in both directions (fwd 641 -> 1354 us).  (fwd_tma is false for the backward.)
+            const int want_sm = config().want > 0 ? config().want : (!fwd_tma && d.ph * d.pw <= 196 ? 6 : 24);
+            const long long want = (long long)want_sm * sm_count();
             int small = 256;
             while (small > cg_min && (long long)K * ((p.C + small - 1) / small) < want) small >>= 1;
             if (small < cg) cg = small;
