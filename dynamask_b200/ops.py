@@ -45,6 +45,26 @@ def _f32c(t, name):
     return t
 
 
+def call(op, *args, grad_inputs=()):
+    """Call a ``dynamask::`` custom op.  In plain eager execution with nothing to differentiate (inference under
+    ``torch.no_grad()``, index-only ops) the op's Python body runs directly: the dispatcher round trip of
+    ``torch.library.custom_op`` costs ~90 us per call on this box, a third of the host time of the per-image
+    inference tail (``tools/gpu/r03_tail.py``).  Under autograd, ``torch.compile`` tracing or any tensor subclass /
+    mode the registered op is used, so those see exactly what they saw before."""
+    body = getattr(op, '_init_fn', None)
+    if body is None or torch.compiler.is_compiling():
+        return op(*args)
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in grad_inputs):
+        return op(*args)
+    for a in args:
+        for t in (a if isinstance(a, (list, tuple)) else (a,)):
+            if isinstance(t, Tensor) and (type(t) is not Tensor or not t.is_cuda):
+                return op(*args)   # subclasses (fake / functional tensors) and CPU tensors (which must raise) go through
+    if torch._C._len_torch_dispatch_stack() > 0 or torch._C._len_torch_function_stack() > 0:
+        return op(*args)
+    return body(*args)
+
+
 # --------------------------------------------------------------------------------------------
 # dm_assign
 # --------------------------------------------------------------------------------------------
@@ -260,9 +280,9 @@ def multilevel_roi_align(feats, rois, out_sizes, spatial_scales, lvl=None, perm=
         if len(out_sizes) != 1:
             raise ValueError('counts is required with more than one bucket')
         counts = [rois.size(0)]
-    return roi_align_forward(list(feats), rois, lvl, perm, seg, [int(c) for c in counts], out_hw,
-                             [float(s) for s in spatial_scales], int(sampling_ratio),
-                             bool(aligned), bool(channels_last))
+    return call(roi_align_forward, list(feats), rois, lvl, perm, seg, [int(c) for c in counts], out_hw,
+                [float(s) for s in spatial_scales], int(sampling_ratio), bool(aligned), bool(channels_last),
+                grad_inputs=feats)
 
 
 # --------------------------------------------------------------------------------------------

@@ -92,7 +92,7 @@ class SingleRoIExtractor(BaseRoIExtractor):
 
     def map_roi_levels(self, rois, num_levels):
         """``[K,5]`` rois -> ``[K]`` int64 level index (0-based), computed by ``dm_assign``."""
-        lvl = ops.assign(rois, None, int(num_levels), float(self.finest_scale), 1)[0]
+        lvl = ops.call(ops.assign, rois, None, int(num_levels), float(self.finest_scale), 1)[0]
         return lvl.long()
 
     def _layer_args(self):
@@ -107,7 +107,7 @@ class SingleRoIExtractor(BaseRoIExtractor):
             return feats[0].new_zeros(0, self.out_channels, *out_size)
         if num_levels == 1:
             return self.roi_layers[0](feats[0], rois)
-        lvl = ops.assign(rois, None, num_levels, float(self.finest_scale), 1)[0]
+        lvl = ops.call(ops.assign, rois, None, num_levels, float(self.finest_scale), 1)[0]
         if roi_scale_factor is not None:
             rois = self.roi_rescale(rois, roi_scale_factor)
         scales = [layer.spatial_scale for layer in self.roi_layers[:num_levels]]
@@ -146,7 +146,7 @@ class BucketedRoIExtractor(SingleRoIExtractor):
         _, sampling_ratio, aligned = self._layer_args()
         nb = len(self.bucket_sizes)
         num_levels = len(feats)
-        lvl, bucket, perm, seg = ops.assign(rois, mask_labels, num_levels,
+        lvl, bucket, perm, seg = ops.call(ops.assign, rois, mask_labels, num_levels,
                                             float(self.finest_scale), nb)
         if counts is None:
             seg_host = seg.cpu()

@@ -17,6 +17,8 @@ ori = (800, 1333, 3)
 for i in range(2):
     bc._tail_image(dm, ext, feats, stages, labels, images[i][0], images[i][1], ori)
 torch.cuda.synchronize()
+NG = torch.no_grad() if os.environ.get('TAIL_NO_GRAD') else torch.enable_grad()
+NG.__enter__()
 for rep in range(3):
     ts = []
     pending = None
@@ -35,4 +37,20 @@ for rep in range(3):
     tot = (time.perf_counter() - t0) * 1e3
     print('rank %s rep %d: %.3f ms per image; enqueue ms %s; collect ms %s' % (
         os.environ.get('LOCAL_RANK', '-'), rep, tot / mine, ' '.join('%.2f' % (x[0] * 1e3) for x in ts[:12]), ' '.join('%.2f' % (x[1] * 1e3) for x in ts[:12])))
+NG.__exit__(None, None, None)
+if os.environ.get('TAIL_PROFILE'):
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    with torch.no_grad():
+        pr.enable()
+        pending = None
+        for i in range(mine):
+            _, nxt = bc._tail_image(dm, ext, feats, stages, labels, images[i][0], images[i][1], ori, wait=False)
+            if pending is not None:
+                pending.result()
+            pending = nxt
+        pending.result()
+        pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
 print('OMP_NUM_THREADS', os.environ.get('OMP_NUM_THREADS'), 'torch threads', torch.get_num_threads())
