@@ -12,8 +12,40 @@ import dynamask_b200 as dm  # noqa: E402
 dev = torch.device('cuda:%d' % int(os.environ.get('LOCAL_RANK', 0)))
 torch.cuda.set_device(dev)
 mine = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-feats, stages, labels, ext, images = bc._tail_setup(dm, dev, 400, mine, 100, (800, 1344), 256, 0.0)
-ori = (800, 1333, 3)
+C5 = len(sys.argv) > 2 and sys.argv[2] == 'c5'
+if C5:
+    feats, stages, labels, ext, images = bc._tail_setup(dm, dev, 500, mine, 300, (1024, 2048), 256, 0.8)
+    ori = (1024, 2048, 3)
+else:
+    feats, stages, labels, ext, images = bc._tail_setup(dm, dev, 400, mine, 100, (800, 1344), 256, 0.0)
+    ori = (800, 1333, 3)
+if os.environ.get('TAIL_SLOW'):
+    # report every torch.empty / library call that takes longer than 1 ms (allocator misses, blocking launches)
+    _empty = torch.empty
+
+    def empty(*a, **k):
+        t = time.perf_counter()
+        r = _empty(*a, **k)
+        dt = (time.perf_counter() - t) * 1e3
+        if dt > 1.0:
+            print('  slow torch.empty %.1f ms: %s %s' % (dt, a[:1], {kk: str(v) for kk, v in k.items()}))
+        return r
+    torch.empty = empty
+    from dynamask_b200 import _lib
+    lib = _lib.load()
+    for name in ('dm_paste_rle_strings', 'dm_roi_align_fwd', 'dm_refine_stages', 'dm_assign'):
+        f = getattr(lib, name)
+
+        def wrap(f=f, name=name):
+            def g(*a):
+                t = time.perf_counter()
+                r = f(*a)
+                dt = (time.perf_counter() - t) * 1e3
+                if dt > 1.0:
+                    print('  slow %s %.1f ms' % (name, dt))
+                return r
+            return g
+        setattr(lib, name, wrap())
 for i in range(2):
     bc._tail_image(dm, ext, feats, stages, labels, images[i][0], images[i][1], ori)
 torch.cuda.synchronize()
