@@ -268,6 +268,30 @@ def test_rle_ops_refuse_cpu_tensors():
         ops.paste_rle(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4), None, 8, 8, [0, 0, 8, 8], True, 0.5)
 
 
+def test_ops_call_keeps_the_dispatcher_for_cpu_tensors_and_autograd():
+    """ops.call runs a custom op's Python body directly only for plain CUDA tensors with nothing to differentiate;
+    CPU tensors still reach the dispatcher (and raise: there is no CPU implementation), plain functions are called."""
+    assert ops.call(lambda a, b: a + b, 2, 3) == 5
+    rois = torch.zeros(3, 5)
+    with pytest.raises(NotImplementedError):
+        ops.call(ops.assign, rois, None, 4, 56.0, 1)
+    import dynamask_b200 as dm
+    ext = dm.SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=0), 4, [4, 8])
+    with pytest.raises(NotImplementedError):
+        ext([torch.zeros(1, 4, 16, 16), torch.zeros(1, 4, 8, 8)], rois)
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        ext([torch.zeros(1, 4, 16, 16), torch.zeros(1, 4, 8, 8)], rois)
+
+
+def test_paste_rle_strings_workspace_is_declared_and_monotone():
+    lib = _lib.load()
+    a = lib.dm_paste_rle_strings_workspace(100, 1333, 1 << 16)
+    b = lib.dm_paste_rle_strings_workspace(100, 1333, 1 << 17)
+    c = lib.dm_paste_rle_strings_workspace(200, 1333, 1 << 16)
+    assert 0 < a < b and a < c and a % 16 == 0
+    assert lib.dm_paste_rle_strings_workspace(-1, 1, 1) == -1
+
+
 def test_polygon_masks_container_and_transforms():
     """Host side of PolygonMasks (reference tests/test_masks.py:300-330, :413-470 minus the
     rasterisation, which needs the device)."""
