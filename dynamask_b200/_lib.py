@@ -38,7 +38,7 @@ SIGNATURES = {
     'dm_rle_strings': (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dm_paste_rle_strings_workspace': (_i64, [_i, _i, _i64]),
     'dm_paste_rle_strings': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
-                                  _vp, _i64, _vp, _vp, _vp]),
+                                  _i, _vp, _i64, _vp, _vp, _vp]),
     'dm_rle_compress_host': (_i64, [_vp, _i64, _i64, _vp, _i64]),
     'dm_rle_compress_batch_host': (_i64, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     'dm_polygon_target': (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),

@@ -526,11 +526,13 @@ __global__ void __launch_bounds__(kRleThreads) rle_offsets_kernel(const int32_t*
     if (threadIdx.x == 0) str_offsets[N] = base;
 }
 
-// exclusive scan of the N per-instance transition counts -> inst_offsets[N+1]; header[0] = status (1 when the
-// total exceeds `capacity`: the later launches of the same call then write nothing), header[1] = total
+// exclusive scan of the N per-instance transition counts -> inst_offsets[N+1]; header[0] = status (bit 0: the
+// total exceeds `capacity`, the later launches of the same call then write nothing; bits 8..: column blocks whose
+// recorded slots overflowed, i.e. that are evaluated a second time), header[1] = total
 __global__ void __launch_bounds__(kRleThreads) rle_totals_scan_kernel(const int32_t* __restrict__ totals, int N,
                                                                       long long capacity, int64_t* __restrict__ inst_offsets,
-                                                                      int32_t* __restrict__ status, int64_t* __restrict__ header) {
+                                                                      int32_t* __restrict__ status, int64_t* __restrict__ header,
+                                                                      const int32_t* __restrict__ inst_over, int n_flags) {
     __shared__ int s_warp[kRleThreads / 32];
     long long base = 0;
     for (int i0 = 0; i0 < N; i0 += kRleThreads) {
@@ -541,11 +543,17 @@ __global__ void __launch_bounds__(kRleThreads) rle_totals_scan_kernel(const int3
         if (i < N) inst_offsets[i] = base + pos;
         base += tot;
     }
+    int over_blocks = 0;
+    if (inst_over) {
+        int mine = 0;
+        for (int i = threadIdx.x; i < n_flags; i += kRleThreads) mine += inst_over[i] != 0;
+        block_exclusive_scan(mine, s_warp, over_blocks);
+    }
     if (threadIdx.x == 0) {
         inst_offsets[N] = base;
         const int over = base > capacity ? 1 : 0;
         *status = over;
-        header[0] = over;
+        header[0] = (long long)over | ((long long)over_blocks << 8);
         header[1] = base;
     }
 }
@@ -618,8 +626,8 @@ extern "C" int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacit
 extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
                                     const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
                                     const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
-                                    int y_hi, float thr, void* workspace, int64_t capacity, int64_t* header,
-                                    char* out, dm_stream_t stream) {
+                                    int y_hi, float thr, int record_slots, void* workspace, int64_t capacity,
+                                    int64_t* header, char* out, dm_stream_t stream) {
     if (N < 0 || capacity < 0) return DM_EINVAL;
     if (N == 0) return DM_OK;
     if (!workspace || !header || !out || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return DM_EINVAL;
@@ -638,19 +646,24 @@ extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, i
     int32_t* compact = reinterpret_cast<int32_t*>(base + ws.compact);
     cudaStream_t st = (cudaStream_t)stream;
     DM_CUDA_CHECK(cudaMemsetAsync(totals, 0, (size_t)(ws.inst_offsets - ws.totals), st), "dm_paste_rle_strings/memset");
+    if (!record_slots) slots = inst_over = nullptr;   // plain two-pass evaluation (noisy masks: most columns would overflow)
     auto pass = [&](int no) {
         return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
                               x_lo, y_lo, x_hi, y_hi, thr, no, col_counts, totals, inst_offsets, trans, status, slots,
                               inst_over, stream);
     };
+    const int n_flags = (int)((ws.inst_offsets - ws.inst_over) / 4);
     // 1: count, and record up to kRleSlots transitions per column
     int rc = pass(1);
     if (rc != DM_OK) return rc;
-    dm::rle_totals_scan_kernel<<<1, dm::kRleThreads, 0, st>>>(totals, N, (long long)capacity, inst_offsets, status, header);
+    dm::rle_totals_scan_kernel<<<1, dm::kRleThreads, 0, st>>>(totals, N, (long long)capacity, inst_offsets, status, header,
+                                                              inst_over, n_flags);
     DM_LAUNCH_CHECK("dm_paste_rle_strings/scan");
     // 3: column blocks whose columns all fitted their slots are copied into place; 2: the others are evaluated again
-    rc = pass(3);
-    if (rc != DM_OK) return rc;
+    if (record_slots) {
+        rc = pass(3);
+        if (rc != DM_OK) return rc;
+    }
     rc = pass(2);
     if (rc != DM_OK) return rc;
     const long long total_pixels = (long long)(y_hi - y_lo) * (x_hi - x_lo);

@@ -453,7 +453,7 @@ def _paste_rle_two_pass(masks, boxes, labels, img_h, img_w, reg, apply_sigmoid, 
 
 
 # transitions per instance the next paste_rle_async call provisions for (adapts to what the masks needed)
-_RLE_HINT = {'per_inst': 4096, 'str_bytes': 1 << 16}
+_RLE_HINT = {'per_inst': 4096, 'str_bytes': 1 << 16, 'slots': True, 'calls': 0}
 
 
 # Pinned result buffers of paste_rle_async, by size: a buffer goes back here the moment its strings have been
@@ -479,7 +479,9 @@ class PendingRle:
     """RLE strings of one :func:`paste_rle_async` call on their way to the host.  ``result()`` waits
     for the call's event (one synchronisation) and returns the list of COCO RLE dicts."""
 
-    def __init__(self, n, size, event=None, pinned=None, head=0, prefix=0, blob=None, keep=None, redo=None, ready=None):
+    def __init__(self, n, size, event=None, pinned=None, head=0, prefix=0, blob=None, keep=None, redo=None, ready=None,
+                 slots=False):
+        self.slots = slots
         self.n, self.size, self.event, self.pinned = n, size, event, pinned
         self.head, self.prefix, self.blob, self.keep, self.redo, self._ready = head, prefix, blob, keep, redo, ready
 
@@ -488,7 +490,11 @@ class PendingRle:
             return self._ready
         self.event.synchronize()
         hdr = self.pinned[:self.head].view(torch.int64)
-        status, total = int(hdr[0]), int(hdr[1])
+        status, total = int(hdr[0]) & 1, int(hdr[1])
+        if self.slots:
+            # slot recording pays when most column blocks fit (clean masks); when at least half of the instances had
+            # a block evaluated twice anyway (noisy masks) the next calls go back to the plain two passes
+            _RLE_HINT['slots'] = (int(hdr[0]) >> 8) * 2 < self.n
         # provision for 1.5x what the densest image so far needed, in powers of two: the buffer sizes then stay the
         # same from call to call and come out of the caching allocators (no cudaMalloc / cudaHostAlloc per image)
         need = int(1.5 * total / max(self.n, 1)) + 256
@@ -531,6 +537,8 @@ def paste_rle_async(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_
         return PendingRle(0, size, ready=[])
     lib = _lib.load()
     cap = int(N * _RLE_HINT['per_inst'])
+    _RLE_HINT['calls'] += 1
+    slots = bool(_RLE_HINT['slots'] or _RLE_HINT['calls'] % 64 == 0)   # (probe again now and then)
     ws_bytes = int(lib.dm_paste_rle_strings_workspace(N, max(rw, 1), cap))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     head = (8 * (N + 3) + 15) & ~15
@@ -539,7 +547,7 @@ def paste_rle_async(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_
     with torch.cuda.device(dev):
         rc = lib.dm_paste_rle_strings(_ptr(masks), masks.stride(0), masks.stride(1), _ptr(labels), N, sh, sw,
                                       int(bool(apply_sigmoid)), _ptr(boxes), int(img_h), int(img_w), x_lo, y_lo,
-                                      x_hi, y_hi, float(thr), _ptr(ws), cap, _ptr(blob),
+                                      x_hi, y_hi, float(thr), int(slots), _ptr(ws), cap, _ptr(blob),
                                       ctypes.c_void_p(blob.data_ptr() + head), _stream(dev))
     _lib.check(rc, 'dm_paste_rle_strings')
     prefix = min(out_cap, int(_RLE_HINT['str_bytes']))
@@ -548,7 +556,7 @@ def paste_rle_async(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(dev))
     redo = lambda: _paste_rle_two_pass(masks, boxes, labels, img_h, img_w, reg, apply_sigmoid, thr)  # noqa: E731
-    return PendingRle(N, size, ev, pinned, head, prefix, blob, (ws, masks, boxes, labels), redo)
+    return PendingRle(N, size, ev, pinned, head, prefix, blob, (ws, masks, boxes, labels), redo, slots=slots)
 
 
 def paste_rle(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_h: int, img_w: int,

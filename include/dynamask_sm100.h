@@ -196,9 +196,13 @@ int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int 
  *   workspace  device scratch of dm_paste_rle_strings_workspace(N, x_hi - x_lo, capacity) bytes,
  *              16-byte aligned, owned by the caller until the call has finished on `stream`
  *   capacity   transitions the buffers hold (all instances together)
- *   header     device int64 [2 + N + 1]: header[0] = status (0 ok, 1 = the masks have more
- *              transitions than `capacity`: nothing else was written, repeat with capacity >=
- *              header[1]), header[1] = total transitions, header[2 .. 2+N] = string offsets
+ *   record_slots  != 0: the counting pass also records up to 32 transitions per canvas column, and column
+ *              blocks whose columns all fit are copied into place instead of being evaluated a second
+ *              time (clean masks: 2-4 transitions per column); 0: plain count + write passes
+ *   header     device int64 [2 + N + 1]: header[0] = status: bit 0 set = the masks have more
+ *              transitions than `capacity` (nothing else was written, repeat with capacity >=
+ *              header[1]), bits 8.. = column blocks that overflowed their slots and were evaluated
+ *              twice; header[1] = total transitions, header[2 .. 2+N] = string offsets
  *   out        device chars, at least 6 * capacity + 8 * N + 8 bytes
  * Other arguments as dm_paste_rle.  Replaces get_seg_masks + encode_mask_results
  * (mmdet/models/roi_heads/mask_heads/dynamask_head.py:279-342, mmdet/core/mask/utils.py:36-63).
@@ -207,8 +211,8 @@ int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacity);
 int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
                          const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
                          const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
-                         int y_hi, float thr, void* workspace, int64_t capacity, int64_t* header,
-                         char* out, dm_stream_t stream);
+                         int y_hi, float thr, int record_slots, void* workspace, int64_t capacity,
+                         int64_t* header, char* out, dm_stream_t stream);
 /*
  * HOST function: the transitions of one instance (host memory) -> pycocotools' compressed "counts"
  * string (rleToString).  Coinciding transition pairs cancel.  Returns the length written to `out`

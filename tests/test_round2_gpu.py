@@ -474,6 +474,21 @@ def test_paste_rle_async_equals_two_pass_and_recovers_from_small_capacity():
     try:
         got = ops.paste_rle_async(logits, boxes, None, H, W, list(reg), True, 0.5).result()
         assert got == want
+        # both forms of the second pass: recorded slots copied into place (clean masks: every column fits) ...
+        lin = (torch.arange(28, dtype=torch.float32) + 0.5) / 28 * 2 - 1
+        clean = (4.0 * (1.0 - (lin[None, :] ** 2 + lin[:, None] ** 2)))[None, None].repeat(23, 1, 1, 1).cuda()
+        want_clean = ops._paste_rle_two_pass(clean, boxes, None, H, W, reg, True, 0.5)
+        ops._RLE_HINT['slots'] = True
+        assert ops.paste_rle_async(clean, boxes, None, H, W, list(reg), True, 0.5).result() == want_clean
+        assert ops._RLE_HINT['slots'] is True          # nothing overflowed: recording stays on
+        # ... and plain count + write passes (noisy masks switch the recording off after one call)
+        noisy = torch.randn(23, 1, 28, 28, generator=torch.Generator().manual_seed(3)).cuda() * 3
+        want_noisy = ops._paste_rle_two_pass(noisy, boxes, None, H, W, reg, True, 0.5)
+        ops._RLE_HINT['slots'] = True
+        assert ops.paste_rle_async(noisy, boxes, None, H, W, list(reg), True, 0.5).result() == want_noisy
+        ops._RLE_HINT['slots'] = False
+        assert ops.paste_rle_async(noisy, boxes, None, H, W, list(reg), True, 0.5).result() == want_noisy
+        assert ops.paste_rle_async(clean, boxes, None, H, W, list(reg), True, 0.5).result() == want_clean
         # capacity far too small: the device reports it (nothing written), the call repeats with exact sizes
         ops._RLE_HINT['per_inst'] = 1
         assert ops.paste_rle_async(logits, boxes, None, H, W, list(reg), True, 0.5).result() == want
