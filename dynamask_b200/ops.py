@@ -60,7 +60,10 @@ def call(op, *args, grad_inputs=()):
         for t in (a if isinstance(a, (list, tuple)) else (a,)):
             if isinstance(t, Tensor) and (type(t) is not Tensor or not t.is_cuda):
                 return op(*args)   # subclasses (fake / functional tensors) and CPU tensors (which must raise) go through
-    if torch._C._len_torch_dispatch_stack() > 0 or torch._C._len_torch_function_stack() > 0:
+    try:   # any active __torch_dispatch__ / __torch_function__ mode must see the op
+        if torch._C._len_torch_dispatch_stack() > 0 or torch._C._len_torch_function_stack() > 0:
+            return op(*args)
+    except AttributeError:   # another torch version: stay on the registered op
         return op(*args)
     return body(*args)
 
