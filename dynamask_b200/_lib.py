@@ -36,7 +36,7 @@ SIGNATURES = {
                           _i, _vp, _vp, _vp, _vp, _vp]),
     'dm_rle_from_canvas': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'dm_rle_strings': (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'dm_paste_rle_strings_workspace': (_i64, [_i, _i, _i64]),
+    'dm_paste_rle_strings_workspace': (_i64, [_i, _i, _i, _i64]),
     'dm_paste_rle_strings': (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f,
                                   _i, _vp, _i64, _vp, _vp, _vp]),
     'dm_rle_compress_host': (_i64, [_vp, _i64, _i64, _vp, _i64]),

@@ -28,14 +28,15 @@ namespace dm {
 
 struct RleParams {
     PasteParams p;
-    int32_t* col_counts;          // [N][rw] transitions per column (window columns only are defined)
+    int32_t* col_counts;          // [N][nseg][rw] transitions per (row segment, column); window columns only are defined
+    int nseg, seg_rows;           // row segments of the region (grid.z): a column's rows are shared out over nseg CTAs
     int32_t* inst_totals;         // [N] transitions per instance (pass 1 adds into it: zero it first)
     const int64_t* inst_offsets;  // [N] exclusive scan of inst_totals (pass 2)
     int32_t* trans;               // [sum] transitions, instance after instance (pass 2)
     const uint8_t* canvas;        // canvas source, or null
     int32_t* slots;               // optional [N][rw][kRleSlots]: pass 1 also RECORDS a column's first kRleSlots transitions, so
                                   // that pass 3 (a copy) replaces the second evaluation for every instance whose columns all fit
-    int32_t* inst_over;           // [N][gridDim.x] set by pass 1 when a column of the CTA's 256 has more transitions than slots
+    int32_t* inst_over;           // [N][nseg][gridDim.x] set by pass 1 when a column of the CTA's 256 has more transitions than slots
     const int32_t* status;        // optional device word: non-zero = the transitions do not fit the caller's buffers,
                                   // pass 2 writes nothing (dm_paste_rle_strings)
 };
@@ -78,9 +79,17 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
     const int st_w = p.sw + 2;
     const int zero_i = p.sw + 1, nan_i = p.sw + 2;
     if (PASS >= 2 && q.status && *q.status) return;   // CTA-uniform
+    // Row segments: the chain of a column -- one thread walking down the window, 8 rows per barrier pair -- is what
+    // a launch waits for (a 500-row window: ~100 us with ~100 live CTAs on 148 SMs), so the region's rows are cut
+    // into nseg segments (grid.z) and every (column block, segment) is a CTA of its own.  A segment that does not
+    // start the window evaluates the row above it first to know the state it continues from; only the segment
+    // holding the window's last row closes the column.
+    const int seg = blockIdx.z, nseg = q.nseg;
+    auto cc = [&](int n_, int s_, int x_) -> int32_t& { return q.col_counts[((size_t)n_ * nseg + s_) * p.rw + x_]; };
     for (int n = blockIdx.y; n < p.N; n += gridDim.y) {
         // with recorded slots: pass 3 copies the column blocks whose columns all fitted, pass 2 re-evaluates the others
-        if (PASS >= 2 && q.inst_over && (q.inst_over[(size_t)n * gridDim.x + blockIdx.x] != 0) != (PASS == 2)) continue;   // CTA-uniform
+        if (PASS >= 2 && q.inst_over &&
+            (q.inst_over[((size_t)n * nseg + seg) * gridDim.x + blockIdx.x] != 0) != (PASS == 2)) continue;   // CTA-uniform
         const float4 bx = *reinterpret_cast<const float4*>(p.boxes + 4 * (size_t)n);
         int xa, xb, ya, yb;
         window_1d(bx.x, bx.z, p.sw, p.img_w, xa, xb);
@@ -89,6 +98,9 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
         if (c0 >= wxb) continue;                         // CTA-uniform
         window_1d(bx.y, bx.w, p.sh, p.img_h, ya, yb);
         const int wya = max(ya - p.y_lo, 0), wyb = min(yb - p.y_lo, p.rh);
+        // this CTA's rows [sa, sb) of the window
+        const int sa = max(wya, seg * q.seg_rows), sb = min(wyb, (seg + 1) * q.seg_rows);
+        if (sa >= sb) continue;                          // CTA-uniform (pass 1 leaves the zeroed count in place)
         const int x = c0 + threadIdx.x;
         const bool live = x < wxb;
         // this thread's column: VD index and weight, constant down the column
@@ -103,15 +115,23 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
         if (PASS >= 2) {
             // transitions of the instance's earlier columns: those of earlier CTAs + a scan inside this one
             int part = 0;
-            for (int c = wxa + threadIdx.x; c < c0; c += kRleThreads) part += q.col_counts[(size_t)n * p.rw + c];
+            for (int c = wxa + threadIdx.x; c < c0; c += kRleThreads)
+                for (int s2 = 0; s2 < nseg; ++s2) part += cc(n, s2, c);
             int before = 0, dummy = 0;
             block_exclusive_scan(part, s_warp, before);
-            const int mine = live ? q.col_counts[(size_t)n * p.rw + x] : 0;
-            const int pre = block_exclusive_scan(mine, s_warp, dummy);
-            out = q.trans + q.inst_offsets[n] + before + pre;
+            int col_total = 0, above = 0;                // the column's transitions in all segments / in the segments above
+            if (live)
+                for (int s2 = 0; s2 < nseg; ++s2) {
+                    const int v = cc(n, s2, x);
+                    col_total += v;
+                    if (s2 < seg) above += v;
+                }
+            const int mine = live ? cc(n, seg, x) : 0;
+            const int pre = block_exclusive_scan(col_total, s_warp, dummy);
+            out = q.trans + q.inst_offsets[n] + before + pre + above;
             if (PASS == 3) {   // the column's transitions were recorded by pass 1: copy them into place
                 if (live) {
-                    const int32_t* sl = q.slots + ((size_t)n * p.rw + x) * kRleSlots;
+                    const int32_t* sl = q.slots + (((size_t)n * nseg + seg) * p.rw + x) * kRleSlots;
                     for (int k = 0; k < mine; ++k) out[k] = sl[k];
                 }
                 continue;
@@ -130,8 +150,15 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
         in.load(p, n);
         int prev = 0, cnt = 0;
         const int col_base = x * p.rh;
-        int32_t* const rec = (PASS == 1 && q.slots && live) ? q.slots + ((size_t)n * p.rw + x) * kRleSlots : nullptr;
+        int32_t* const rec = (PASS == 1 && q.slots && live) ? q.slots + (((size_t)n * nseg + seg) * p.rw + x) * kRleSlots : nullptr;
+        const int r_first = sa > wya ? sa - 1 : sa;      // a continuing segment looks at the row above it first
+        bool peek = r_first < sa;
         auto step = [&](int row, bool b) {
+            if (peek) {                                  // (the row above the segment: state only, nothing emitted)
+                prev = (int)b;
+                peek = false;
+                return;
+            }
             if ((int)b != prev) {
                 if (PASS == 1) {
                     if (rec && cnt < kRleSlots) rec[cnt] = col_base + row;
@@ -142,8 +169,8 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
                 prev = (int)b;
             }
         };
-        for (int r0 = wya; r0 < wyb; r0 += hb) {
-            const int r1 = min(r0 + hb, wyb);
+        for (int r0 = r_first; r0 < sb; r0 += hb) {
+            const int r1 = min(r0 + hb, sb);
             bool staged = false;
             int mlo = 0, mrows = 0;
             {
@@ -214,10 +241,10 @@ paste_rle_kernel(const __grid_constant__ RleParams q) {
                 __syncthreads();
             }
         }
-        if (prev) step(wyb, false);  // every column returns to 0 after its last window row
+        if (prev && sb == wyb) step(wyb, false);  // every column returns to 0 after its last window row
         if (PASS == 1) {
-            if (live) q.col_counts[(size_t)n * p.rw + x] = cnt;
-            if (q.inst_over && cnt > kRleSlots) q.inst_over[(size_t)n * gridDim.x + blockIdx.x] = 1;
+            if (live) cc(n, seg, x) = cnt;
+            if (q.inst_over && cnt > kRleSlots) q.inst_over[((size_t)n * nseg + seg) * gridDim.x + blockIdx.x] = 1;
             int total = 0;
             block_exclusive_scan(cnt, s_warp, total);
             if (threadIdx.x == 0 && total) atomicAdd(q.inst_totals + n, total);
@@ -283,6 +310,8 @@ static int rle_fill(dm::RleParams& q, int N, int rh, int rw, int pass, int32_t* 
     q.p.rh = rh;
     q.p.rw = rw;
     q.col_counts = col_counts;
+    q.nseg = 1;
+    q.seg_rows = rh > 0 ? rh : 1;
     q.inst_totals = inst_totals;
     q.inst_offsets = inst_offsets;
     q.trans = transitions;
@@ -295,7 +324,7 @@ static int paste_rle_impl(const float* masks, int64_t mask_stride_n, int64_t mas
                           const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,
                           int y_hi, float thr, int pass, int32_t* col_counts, int32_t* inst_totals,
                           const int64_t* inst_offsets, int32_t* transitions, const int32_t* status, int32_t* slots,
-                          int32_t* inst_over, dm_stream_t stream) {
+                          int32_t* inst_over, int nseg, int seg_rows, dm_stream_t stream) {
     if (N < 0 || S_h < 1 || S_w < 1 || img_h < 0 || img_w < 0) return DM_EINVAL;
     if (x_lo < 0 || y_lo < 0 || x_hi > img_w || y_hi > img_h || x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
     dm::RleParams q;
@@ -320,8 +349,9 @@ static int paste_rle_impl(const float* masks, int64_t mask_stride_n, int64_t mas
     q.status = status;
     q.slots = slots;
     q.inst_over = inst_over;
+    if (nseg > 1) { q.nseg = nseg; q.seg_rows = seg_rows; }
     q.p.total = (long long)q.p.rh * q.p.rw * N;
-    dim3 grid((unsigned)((q.p.rw + dm::kRleThreads - 1) / dm::kRleThreads), (unsigned)(N < 65535 ? N : 65535));
+    dim3 grid((unsigned)((q.p.rw + dm::kRleThreads - 1) / dm::kRleThreads), (unsigned)(N < 65535 ? N : 65535), (unsigned)q.nseg);
     cudaStream_t st = (cudaStream_t)stream;
     if (pass == 1) dm::paste_rle_kernel<1><<<grid, dm::kRleThreads, 0, st>>>(q);
     else if (pass == 3) dm::paste_rle_kernel<3><<<grid, dm::kRleThreads, 0, st>>>(q);
@@ -338,7 +368,7 @@ extern "C" int dm_paste_rle(const float* masks, int64_t mask_stride_n, int64_t m
     if (pass != 1 && pass != 2) return DM_EINVAL;
     return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
                           x_lo, y_lo, x_hi, y_hi, thr, pass, col_counts, inst_totals, inst_offsets, transitions, nullptr,
-                          nullptr, nullptr, stream);
+                          nullptr, nullptr, 1, 0, stream);
 }
 
 extern "C" int dm_rle_from_canvas(const uint8_t* canvas, int N, int H, int W, int pass, int32_t* col_counts,
@@ -597,18 +627,29 @@ namespace {
 struct RleWorkspace {
     int64_t col_counts, totals, kept, str_len, status, inst_over, inst_offsets, slots, trans, compact, bytes;
 };
-RleWorkspace rle_workspace(int N, int rw, int64_t capacity) {
+// rows per segment / segments of a region of rh rows: 128-row segments, at most 16 of them
+constexpr int kRleSegRows = 128, kRleMaxSeg = 16;
+void rle_segments(int rh, int& nseg, int& seg_rows) {
+    seg_rows = kRleSegRows;
+    if ((rh + seg_rows - 1) / seg_rows > kRleMaxSeg) seg_rows = (rh + kRleMaxSeg - 1) / kRleMaxSeg;
+    nseg = rh > 0 ? (rh + seg_rows - 1) / seg_rows : 1;
+}
+// The workspace is sized for the segmented form without recorded slots AND for the one-segment form with them
+// (record_slots picks one per call): the slots of a segmented call would be nseg times as many.
+RleWorkspace rle_workspace(int N, int rw, int rh_max, int64_t capacity) {
     const int64_t n = N, w = rw > 0 ? rw : 1, cap = capacity > 0 ? capacity : 1;
+    int nseg, seg_rows;
+    rle_segments(rh_max, nseg, seg_rows);
     auto up = [](int64_t v) { return (v + 15) & ~15ll; };
     RleWorkspace ws;
     int64_t o = 0;
-    ws.col_counts = o; o = up(o + 4 * n * w);
-    // totals | kept | str_len | status (4 words) | inst_over: one memset clears them
+    // col_counts | totals | kept | str_len | status (4 words) | inst_over: one memset clears them
+    ws.col_counts = o; o = up(o + 4 * n * nseg * w);
     ws.totals = o; o += 4 * n;
     ws.kept = o; o += 4 * n;
     ws.str_len = o; o += 4 * n;
     ws.status = o; o += 16;
-    ws.inst_over = o; o = up(o + 4 * n * ((w + dm::kRleThreads - 1) / dm::kRleThreads));
+    ws.inst_over = o; o = up(o + 4 * n * nseg * ((w + dm::kRleThreads - 1) / dm::kRleThreads));
     ws.inst_offsets = o; o = up(o + 8 * (n + 1));
     ws.slots = o; o = up(o + 4 * n * w * dm::kRleSlots);
     ws.trans = o; o = up(o + 4 * cap);
@@ -618,9 +659,9 @@ RleWorkspace rle_workspace(int N, int rw, int64_t capacity) {
 }
 }  // namespace
 
-extern "C" int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacity) {
-    if (N < 0 || rw < 0 || capacity < 0) return -1;
-    return rle_workspace(N, rw, capacity).bytes;
+extern "C" int64_t dm_paste_rle_strings_workspace(int N, int rw, int rh, int64_t capacity) {
+    if (N < 0 || rw < 0 || rh < 0 || capacity < 0) return -1;
+    return rle_workspace(N, rw, rh, capacity).bytes;
 }
 
 extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
@@ -632,7 +673,9 @@ extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, i
     if (N == 0) return DM_OK;
     if (!workspace || !header || !out || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return DM_EINVAL;
     if (x_hi < x_lo || y_hi < y_lo) return DM_EINVAL;
-    const RleWorkspace ws = rle_workspace(N, x_hi - x_lo, capacity);
+    const RleWorkspace ws = rle_workspace(N, x_hi - x_lo, y_hi - y_lo, capacity);
+    int nseg = 1, seg_rows = y_hi - y_lo;
+    if (!record_slots) rle_segments(y_hi - y_lo, nseg, seg_rows);   // (recorded slots: one segment, as sized)
     char* base = static_cast<char*>(workspace);
     int32_t* col_counts = reinterpret_cast<int32_t*>(base + ws.col_counts);
     int32_t* totals = reinterpret_cast<int32_t*>(base + ws.totals);
@@ -645,14 +688,14 @@ extern "C" int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, i
     int32_t* trans = reinterpret_cast<int32_t*>(base + ws.trans);
     int32_t* compact = reinterpret_cast<int32_t*>(base + ws.compact);
     cudaStream_t st = (cudaStream_t)stream;
-    DM_CUDA_CHECK(cudaMemsetAsync(totals, 0, (size_t)(ws.inst_offsets - ws.totals), st), "dm_paste_rle_strings/memset");
+    DM_CUDA_CHECK(cudaMemsetAsync(col_counts, 0, (size_t)(ws.inst_offsets - ws.col_counts), st), "dm_paste_rle_strings/memset");
     if (!record_slots) slots = inst_over = nullptr;   // plain two-pass evaluation (noisy masks: most columns would overflow)
     auto pass = [&](int no) {
         return paste_rle_impl(masks, mask_stride_n, mask_stride_c, labels, N, S_h, S_w, apply_sigmoid, boxes, img_h, img_w,
                               x_lo, y_lo, x_hi, y_hi, thr, no, col_counts, totals, inst_offsets, trans, status, slots,
-                              inst_over, stream);
+                              inst_over, nseg, seg_rows, stream);
     };
-    const int n_flags = (int)((ws.inst_offsets - ws.inst_over) / 4);
+    const int n_flags = (int)((ws.inst_offsets - ws.inst_over) / 4);   // (zeroed beyond what a call uses)
     // 1: count, and record up to kRleSlots transitions per column
     int rc = pass(1);
     if (rc != DM_OK) return rc;

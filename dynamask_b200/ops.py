@@ -456,7 +456,10 @@ def _paste_rle_two_pass(masks, boxes, labels, img_h, img_w, reg, apply_sigmoid, 
 
 
 # transitions per instance the next paste_rle_async call provisions for (adapts to what the masks needed)
-_RLE_HINT = {'per_inst': 4096, 'str_bytes': 1 << 16, 'slots': True, 'calls': 0}
+# 'slots': record transitions in the counting pass (one row segment) instead of the row-segmented two passes; off --
+# the launch waits for its longest column chain, which the segments cut by the window height / 128 whatever the masks
+# look like, while recorded slots only pay when NO block of the image overflows them
+_RLE_HINT = {'per_inst': 4096, 'str_bytes': 1 << 16, 'slots': False, 'calls': 0}
 
 
 # Pinned result buffers of paste_rle_async, by size: a buffer goes back here the moment its strings have been
@@ -494,10 +497,8 @@ class PendingRle:
         self.event.synchronize()
         hdr = self.pinned[:self.head].view(torch.int64)
         status, total = int(hdr[0]) & 1, int(hdr[1])
-        if self.slots:
-            # slot recording pays when most column blocks fit (clean masks); when at least half of the instances had
-            # a block evaluated twice anyway (noisy masks) the next calls go back to the plain two passes
-            _RLE_HINT['slots'] = (int(hdr[0]) >> 8) * 2 < self.n
+        if self.slots and (int(hdr[0]) >> 8) > 0:
+            _RLE_HINT['slots'] = False   # a block overflowed its slots: the second pass ran at full length anyway
         # provision for 1.5x what the densest image so far needed, in powers of two: the buffer sizes then stay the
         # same from call to call and come out of the caching allocators (no cudaMalloc / cudaHostAlloc per image)
         need = int(1.5 * total / max(self.n, 1)) + 256
@@ -541,8 +542,8 @@ def paste_rle_async(masks: Tensor, boxes: Tensor, labels: Optional[Tensor], img_
     lib = _lib.load()
     cap = int(N * _RLE_HINT['per_inst'])
     _RLE_HINT['calls'] += 1
-    slots = bool(_RLE_HINT['slots'] or _RLE_HINT['calls'] % 64 == 0)   # (probe again now and then)
-    ws_bytes = int(lib.dm_paste_rle_strings_workspace(N, max(rw, 1), cap))
+    slots = bool(_RLE_HINT['slots'])
+    ws_bytes = int(lib.dm_paste_rle_strings_workspace(N, max(rw, 1), max(rh, 1), cap))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     head = (8 * (N + 3) + 15) & ~15
     out_cap = 6 * cap + 8 * N + 8

@@ -193,12 +193,13 @@ int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int 
  * anything; results are read after one synchronisation (or an event) chosen by the caller, which
  * lets an inference loop enqueue image i+1 while image i's strings travel to the host
  * (mmdet/apis/test.py:24-57 handles one image after the other).
- *   workspace  device scratch of dm_paste_rle_strings_workspace(N, x_hi - x_lo, capacity) bytes,
+ *   workspace  device scratch of dm_paste_rle_strings_workspace(N, x_hi - x_lo, y_hi - y_lo, capacity) bytes,
  *              16-byte aligned, owned by the caller until the call has finished on `stream`
  *   capacity   transitions the buffers hold (all instances together)
- *   record_slots  != 0: the counting pass also records up to 32 transitions per canvas column, and column
- *              blocks whose columns all fit are copied into place instead of being evaluated a second
- *              time (clean masks: 2-4 transitions per column); 0: plain count + write passes
+ *   record_slots  0 (default form): count + write passes, the region's rows cut into segments of 128 rows so
+ *              that a tall window is walked by several CTAs per column block; != 0: one segment, the
+ *              counting pass also records up to 32 transitions per canvas column and column blocks
+ *              whose columns all fit are copied into place instead of being evaluated a second time
  *   header     device int64 [2 + N + 1]: header[0] = status: bit 0 set = the masks have more
  *              transitions than `capacity` (nothing else was written, repeat with capacity >=
  *              header[1]), bits 8.. = column blocks that overflowed their slots and were evaluated
@@ -207,7 +208,7 @@ int dm_rle_strings(const int32_t* transitions, const int64_t* inst_offsets, int 
  * Other arguments as dm_paste_rle.  Replaces get_seg_masks + encode_mask_results
  * (mmdet/models/roi_heads/mask_heads/dynamask_head.py:279-342, mmdet/core/mask/utils.py:36-63).
  */
-int64_t dm_paste_rle_strings_workspace(int N, int rw, int64_t capacity);
+int64_t dm_paste_rle_strings_workspace(int N, int rw, int rh, int64_t capacity);
 int dm_paste_rle_strings(const float* masks, int64_t mask_stride_n, int64_t mask_stride_c,
                          const int64_t* labels, int N, int S_h, int S_w, int apply_sigmoid,
                          const float* boxes, int img_h, int img_w, int x_lo, int y_lo, int x_hi,

@@ -144,7 +144,7 @@ def test_paste_rle_strings_stays_inside_exactly_sized_buffers():
         want = ops._paste_rle_two_pass(masks, boxes, None, H, W, (0, 0, W, H), True, 0.5)
         for record in (1, 0):
             for cap in (1 << 16, 64):                          # roomy, and far too small (status = 1: nothing written)
-                ws = Guarded(lib.dm_paste_rle_strings_workspace(n, W, cap))
+                ws = Guarded(lib.dm_paste_rle_strings_workspace(n, W, H, cap))
                 hdr = Guarded(8 * (2 + n + 1))
                 out = Guarded(6 * cap + 8 * n + 8)
                 rc = lib.dm_paste_rle_strings(vp(masks.data_ptr()), masks.stride(0), masks.stride(1), None, n, 28, 28,

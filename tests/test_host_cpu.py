@@ -285,11 +285,11 @@ def test_ops_call_keeps_the_dispatcher_for_cpu_tensors_and_autograd():
 
 def test_paste_rle_strings_workspace_is_declared_and_monotone():
     lib = _lib.load()
-    a = lib.dm_paste_rle_strings_workspace(100, 1333, 1 << 16)
-    b = lib.dm_paste_rle_strings_workspace(100, 1333, 1 << 17)
-    c = lib.dm_paste_rle_strings_workspace(200, 1333, 1 << 16)
+    a = lib.dm_paste_rle_strings_workspace(100, 1333, 800, 1 << 16)
+    b = lib.dm_paste_rle_strings_workspace(100, 1333, 800, 1 << 17)
+    c = lib.dm_paste_rle_strings_workspace(200, 1333, 800, 1 << 16)
     assert 0 < a < b and a < c and a % 16 == 0
-    assert lib.dm_paste_rle_strings_workspace(-1, 1, 1) == -1
+    assert lib.dm_paste_rle_strings_workspace(-1, 1, 1, 1) == -1
 
 
 def test_polygon_masks_container_and_transforms():

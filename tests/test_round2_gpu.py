@@ -481,7 +481,7 @@ def test_paste_rle_async_equals_two_pass_and_recovers_from_small_capacity():
         ops._RLE_HINT['slots'] = True
         assert ops.paste_rle_async(clean, boxes, None, H, W, list(reg), True, 0.5).result() == want_clean
         assert ops._RLE_HINT['slots'] is True          # nothing overflowed: recording stays on
-        # ... and plain count + write passes (noisy masks switch the recording off after one call)
+        # ... and the row-segmented count + write passes (an overflowing block switches the recording off)
         noisy = torch.randn(23, 1, 28, 28, generator=torch.Generator().manual_seed(3)).cuda() * 3
         want_noisy = ops._paste_rle_two_pass(noisy, boxes, None, H, W, reg, True, 0.5)
         ops._RLE_HINT['slots'] = True
@@ -523,3 +523,29 @@ def test_paste_rle_async_pipelined_images():
     lab = torch.zeros(b.size(0), dtype=torch.long, device=b.device)
     p = dm().get_seg_masks_rle(l, det, lab, Cfg, (H, W, 3), 1.0, False, wait=False)
     assert p.result() == dm().get_seg_masks_rle(l, det, lab, Cfg, (H, W, 3), 1.0, False)
+
+
+def test_paste_rle_row_segments_on_tall_canvases():
+    """The row-segmented passes of dm_paste_rle_strings (128-row segments, at most 16) against the one-segment
+    two-pass form: windows spanning many segments, starting / ending exactly on segment boundaries, and a canvas
+    taller than 16 x 128 rows (wider segments)."""
+    from dynamask_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    saved = dict(ops._RLE_HINT)
+    try:
+        ops._RLE_HINT['slots'] = False
+        for (H, W) in ((1024, 160), (2100, 96), (256, 300)):
+            n = 9
+            logits = synth.make_mask_logits(n, 28, g).cuda()
+            boxes = synth.make_boxes(n, H, W, g).cuda()
+            boxes[0] = torch.tensor([3.0, 0.0, W - 3.0, float(H)])            # the whole height
+            boxes[1] = torch.tensor([10.0, 128.0, 60.0, 256.0])               # exactly one segment, on its boundaries
+            boxes[2] = torch.tensor([5.0, 127.0, 70.0, 129.0])                # two rows across a boundary
+            boxes[3] = torch.tensor([20.0, H - 40.0, 90.0, H + 30.0])         # hangs over the bottom edge
+            want = ops._paste_rle_two_pass(logits, boxes, None, H, W, (0, 0, W, H), True, 0.5)
+            assert ops.paste_rle_async(logits, boxes, None, H, W, [0, 0, W, H], True, 0.5).result() == want
+            sub = (8, 100, W - 8, H - 37)                                      # a region that starts inside a segment
+            want = ops._paste_rle_two_pass(logits, boxes, None, H, W, sub, True, 0.5)
+            assert ops.paste_rle_async(logits, boxes, None, H, W, list(sub), True, 0.5).result() == want
+    finally:
+        ops._RLE_HINT.update(saved)
