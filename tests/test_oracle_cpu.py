@@ -280,3 +280,19 @@ def test_polygon_rasteriser_matches_reference_known_answers():
                           np.pad(_REF_TRUTH2, ((0, 4), (0, 4)), 'constant').astype(bool))
     # test_masks.py:460-470 -- crop to [0,0,3,4]: pycocotools clips the boundary
     assert np.array_equal(O.polygon_to_bitmap(_REF_POLY_CROP, 4, 3), _REF_CROP_TRUTH.astype(bool))
+
+
+def test_polygon_crop_scale_promotion_is_the_numpy2_one():
+    """``PolygonMasks.crop_and_resize`` scales vertices by ``out_w / max(w, 0.1)`` with a Python int over a float32
+    box extent (``mmdet/core/mask/structures.py:476-486``).  NumPy >= 2 keeps that quotient in float32 -- the form
+    the kernel (``__fdiv_rn`` in ``dm_polygon.cu``), the oracle and the golden files use -- while NumPy 1.x promotes it
+    to float64, where a vertex within an ulp of a .5 rounding boundary of the x5 grid may land on the other side.
+    The bit-exact polygon-target claim is tied to this promotion; this test pins the assumption."""
+    import numpy as np
+    if int(np.__version__.split('.')[0]) < 2:
+        pytest.skip('NumPy 1.x promotes the crop scale to float64: goldens / kernel follow the NumPy >= 2 float32 form')
+    w = np.float32(7.3) - np.float32(0.25)
+    scale = 14 / max(w, 0.1)
+    assert type(scale) is np.float32
+    assert scale == np.float32(14.0) / w                      # one correctly rounded float32 division
+    assert float(scale) != 14.0 / float(w)                    # ... which is not the float64 quotient
